@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — fn evals/sec of a compiled `pytensor.function(..., mode="CUDA")` on B200, with roofline + CPU baseline.
+
+Contract:
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+  * N=1 workload = BASELINE.json configs[1]: the 32-scalar-op fused Elemwise + CAReduce graph over fp32 (4096,4096).
+    A "step" is one evaluation of the compiled function.
+  * `value`  : evals/s, inputs resident in HBM, device outputs (CUDA events, K steps, max over ranks).
+  * `e2e`    : evals/s through `pytensor.function(..., mode="CUDA")` with pinned HOST inputs and NumPy outputs
+               (H2D + D2H inside the timed region).
+  * `roofline`: achieved HBM GB/s of the dominant kernel (algorithmic bytes / its CUDA-event duration) over the
+               measured peak in MEASURED_PEAKS.json.
+  * `cpu_baseline`: the reference's own C linker (mode="CVM") on this box's host cores, same arrays.
+  * N>1: every rank evaluates its own (4096,4096) row-shard of an (N*4096,4096) problem — the graph is row-independent,
+    so there is no data-path collective ("weak"); the batch-sharded logp+grad graph with its NCCL all-reduce is reported
+    beside it under "sharded_logp".
+  * `--impl reference` times the reference C linker alone (rank 0 only under torchrun).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = max(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def pinned_like(arr):
+    """NumPy array backed by page-locked host memory (cudaHostAlloc through the C-ABI)."""
+    import ctypes
+
+    from pytensor_b200.runtime import lib as L
+
+    p = ctypes.c_void_p()
+    L.check(L.lib().ptk_host_alloc_pinned(ctypes.byref(p), arr.nbytes), "pinned alloc")
+    buf = (ctypes.c_char * arr.nbytes).from_address(p.value)
+    out = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    return out
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path: mode="CVM" on the host cores."""
+    if rank != 0:
+        return
+    from oracle import cvm
+    from pytensor_b200 import workloads as W
+
+    pytensor = cvm.configure("float32")
+    ins, outs, make_args, meta = W.cfg2_fused_elemwise(args.n)
+    f = pytensor.function(ins, outs, mode="CVM", trust_input=True)
+    a = make_args()
+    for _ in range(max(1, args.warmup)):
+        f(*a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        f(*a)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    env = cvm.describe()
+    print(json.dumps({
+        "impl": "reference", "metric": "fn evals/sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2: 32-op fused Elemwise+CAReduce, fp32 ({args.n},{args.n}), reference C linker (CVM)"},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": 1, "kind": "reference",
+                         "sample": f"{args.steps} full evaluations of the workload", "env": env},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time cfg3/cfg4 and report them under 'others'")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from oracle import cvm  # configures PYTENSOR_FLAGS for the host framework (compile dir, BLAS)
+
+    pytensor = cvm.configure("float32")
+    import pytensor_b200  # noqa: F401
+    from pytensor_b200 import workloads as W
+    from pytensor_b200.link.cuda import cuda_mode
+    from pytensor_b200.runtime import device as dev
+    from pytensor_b200.runtime import jit
+
+    dev.device()
+    ins, outs, make_args, meta = W.cfg2_fused_elemwise(args.n)
+    f_dev = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True), trust_input=True)
+    f_host = pytensor.function(ins, outs, mode="CUDA", trust_input=True)
+    host_args = [make_args(1 + 10 * rank), make_args(101 + 10 * rank)]
+    dev_args = [[dev.to_device(a) for a in s] for s in host_args]  # two input sets: 2 x 128 MiB > the 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------------------
+    for i in range(args.warmup):
+        f_dev(*dev_args[i % 2])
+    barrier()
+    l0 = jit.stats["launches"]
+    ex = f_dev.vm.executor
+    ex.event_log = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            f_dev(*dev_args[i % 2])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    log, ex.event_log = ex.event_log, None
+    launches = jit.stats["launches"] - l0
+    per_step = {}
+    for i, a, b in log:
+        per_step.setdefault(i, []).append(a.elapsed_time(b))
+    step_ms = {i: float(np.mean(v)) for i, v in per_step.items()}
+    dom = max(step_ms, key=step_ms.get)
+    dom_name = repr(ex.program.steps[dom].impl)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers through the public API -------------------------------------------------------------------
+    pin_args = [[pinned_like(a) for a in s] for s in host_args]
+    for i in range(3):
+        f_host(*pin_args[i % 2])
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        res = f_host(*pin_args[i % 2])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = world * e2e_steps / dt
+    h2d = int(sum(a.nbytes for a in host_args[0]))
+    d2h = int(sum(np.asarray(r).nbytes for r in res))
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    peaks = _peaks()
+    fused = "ElemwiseReduce" in dom_name
+    alg_bytes = meta["bytes"] if fused else 3 * 4 * args.n * args.n
+    achieved = alg_bytes / (step_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": dom_name,
+                "kernel_ms": step_ms[dom], "algorithmic_bytes": alg_bytes, "peak_source": peaks["source"],
+                "step_ms_by_node": {repr(ex.program.steps[i].impl): v for i, v in step_ms.items()},
+                "whole_graph": {"bytes": meta["bytes"], "gbs": meta["bytes"] * args.steps / (ms * 1e-3) / 1e9,
+                                "frac": meta["bytes"] * args.steps / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+
+    # ---- CPU baseline: the reference C linker on the host cores (rank 0, N=1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        f_ref = pytensor.function(ins, outs, mode="CVM", trust_input=True)
+        evs, n = cvm.time_function(f_ref, host_args[0], min_seconds=8.0, min_calls=3, max_calls=50)
+        cpu = {"value": evs, "unit": "evals/s", "cores": 1, "kind": "reference",
+               "sample": f"{n} full evaluations of the same workload (Elemwise/CAReduce C loops are single-threaded: "
+                         "config.openmp=False)", "env": cvm.describe()}
+
+    line = {
+        "metric": "fn evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 (BASELINE.json configs[1]): 32-scalar-op fused Elemwise+CAReduce graph, fp32 "
+                               f"({args.n},{args.n}) -> e ({args.n},{args.n}) f32, r=e.sum(1) f32 (acc f64)",
+                   "l2": "two alternating input sets, 384 MiB working set > 126 MB L2", "parallelism":
+                   f"{world} independent row shards (no collective)"},
+        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

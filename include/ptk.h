@@ -1,0 +1,135 @@
+/*
+ * ptk.h — C-ABI of libptk.so, the B200 (sm_100a) kernel library behind pytensor.link.cuda.CUDALinker.
+ *
+ * Conventions (mirrors the reference's C-thunk ABI: `int (*fn)(void* data)` returning 0 on success and stashing
+ * the error beside it — /root/reference/pytensor/link/c/c_code/lazylinker_c.c:498-534, link/c/basic.py:1690-1761):
+ *   - every entry point returns `ptk_status` (0 = ok); the message is fetched with ptk_last_error() (thread local);
+ *   - only plain pointers / integers / doubles cross the boundary — no torch, no numpy, no C++ types;
+ *   - device pointers are raw `void*` (e.g. torch.Tensor.data_ptr()); the caller owns ALL memory incl. workspaces;
+ *   - strides are in ELEMENTS, shapes int64; `stream` is a cudaStream_t passed as void* (0 = legacy default);
+ *   - nothing here synchronises the device unless its name says so.
+ *
+ * Each group cites the reference interface it replaces (file:line under /root/reference/).
+ */
+#ifndef PTK_H
+#define PTK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int ptk_status;
+#define PTK_OK 0
+#define PTK_ERR_CUDA 1
+#define PTK_ERR_NVRTC 2
+#define PTK_ERR_ARG 3
+#define PTK_ERR_UNSUPPORTED 4
+
+/* dtype codes (numpy kinds the reference's TensorType supports, pytensor/tensor/type.py:40-55; no bf16 there) */
+enum ptk_dtype {
+  PTK_BOOL = 0, PTK_I8 = 1, PTK_I16 = 2, PTK_I32 = 3, PTK_I64 = 4,
+  PTK_U8 = 5, PTK_U16 = 6, PTK_U32 = 7, PTK_U64 = 8,
+  PTK_F16 = 9, PTK_F32 = 10, PTK_F64 = 11
+};
+
+/* ---- runtime ---------------------------------------------------------------------------------------------- */
+int          ptk_version(void);
+const char*  ptk_last_error(void);
+/* Binds the driver API (libcuda.so.1 via cudaGetDriverEntryPoint) and queries the device. Must be called once per
+ * process before any other call that touches the GPU. Fails (never falls back) when no CUDA device is present. */
+ptk_status   ptk_init(int device);
+int          ptk_sm_count(void);
+int          ptk_device(void);
+ptk_status   ptk_sync_stream(void* stream);
+ptk_status   ptk_memcpy_h2d_async(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+ptk_status   ptk_memcpy_d2h_async(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+ptk_status   ptk_memcpy_d2d_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+ptk_status   ptk_memset_async(void* dst_dev, int byte, size_t bytes, void* stream);
+ptk_status   ptk_host_alloc_pinned(void** out, size_t bytes);
+ptk_status   ptk_host_free_pinned(void* p);
+
+/* ---- JIT: the per-Composite kernels (replaces the per-node g++ compile of the C linker:
+ *      pytensor/link/c/cmodule.py:2454-2643 GCC_compiler.compile_str, link/c/basic.py:1585 cthunk_factory) -------- */
+/* Compile CUDA C++ `src` for sm_100a with NVRTC. On success *cubin / *cubin_size receive a malloc'd image the caller
+ * releases with ptk_free(). `log` (may be NULL) receives a malloc'd compile log (also on failure). */
+ptk_status   ptk_jit_compile(const char* src, const char* const* opts, int n_opts,
+                             void** cubin, size_t* cubin_size, char** log);
+void         ptk_free(void* p);
+ptk_status   ptk_module_load(const void* image, size_t size, void** module);
+ptk_status   ptk_module_unload(void* module);
+ptk_status   ptk_module_get_function(void* module, const char* name, void** func);
+ptk_status   ptk_func_set_max_dynamic_smem(void* func, int bytes);
+ptk_status   ptk_func_max_active_blocks(void* func, int block_threads, int dyn_smem, int* out);
+/* flags: bit0 = cooperative launch (grid-wide barrier allowed); cluster_x > 1 launches thread-block clusters. */
+ptk_status   ptk_launch(void* func, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                        unsigned dyn_smem, void* stream, void** args, int flags, int cluster_x);
+
+/* ---- CUDA graphs: the replayable launch list of the VM (replaces the CVM per-call interpreter loop,
+ *      lazylinker_c.c:749-897 CLazyLinker_call) --------------------------------------------------------------- */
+ptk_status   ptk_graph_begin_capture(void* stream);
+ptk_status   ptk_graph_end_capture(void* stream, void** graph_exec);
+ptk_status   ptk_graph_launch(void* graph_exec, void* stream);
+ptk_status   ptk_graph_destroy(void* graph_exec);
+
+/* ---- events (profiling: VM.call_times, pytensor/link/vm.py:243-271) ------------------------------------------- */
+ptk_status   ptk_event_create(void** ev);
+ptk_status   ptk_event_record(void* ev, void* stream);
+ptk_status   ptk_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
+ptk_status   ptk_event_destroy(void* ev);
+ptk_status   ptk_stream_wait_event(void* stream, void* ev);
+
+/* ---- data movement glue (G3/G4: DeepCopyOp compile/ops.py:121, Alloc tensor/basic.py:1545,
+ *      IncSubtensor tensor/subtensor.py:1441, AdvancedSubtensor :1932, AdvancedIncSubtensor :2275) ------------ */
+/* dst[idx] = src[idx] for an ndim<=8 strided pair of equal shape; itemsize in {1,2,4,8}; a 0 src stride broadcasts. */
+ptk_status   ptk_copy_strided(void* dst, const int64_t* dst_strides, const void* src, const int64_t* src_strides,
+                              const int64_t* shape, int ndim, int itemsize, void* stream);
+/* dst[idx] (op)= src[idx]; op 0 = set (same as copy), 1 = add. dtype gives the arithmetic for add. */
+ptk_status   ptk_inc_strided(void* dst, const int64_t* dst_strides, const void* src, const int64_t* src_strides,
+                             const int64_t* shape, int ndim, int dtype, int op, void* stream);
+/* out[o, j, i] = src[o, idx[j], i]  (take along one axis; src viewed as (outer, n_src, inner), contiguous). Bit-exact. */
+ptk_status   ptk_take(void* out, const void* src, const int64_t* idx, int64_t outer, int64_t n_src, int64_t n_idx,
+                      int64_t inner, int itemsize, int* err_flag, void* stream);
+/* dst[o, idx[j], i] (op)= y[o, j, i]; op 0 = set, 1 = add (atomic; duplicates accumulate, order not defined —
+ * np.add.at semantics up to fp reassociation, tensor/subtensor.py:2513-2531). */
+ptk_status   ptk_put(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
+                     int64_t inner, int dtype, int op, int* err_flag, void* stream);
+
+/* ---- BLAS family (A5/A6: Gemm tensor/blas/gemm.py:76, Dot22 :248, Dot22Scalar :298, Gemv tensor/blas/gemv.py:16,
+ *      Ger tensor/blas/ger.py:8; the C linker calls sgemm_/dgemm_/sgemv_/dgemv_ at blas/c_code/codegen.py:463-805) */
+/* C[M,N] = alpha * A[M,K] @ B[K,N] + beta * C, arbitrary element strides, dtype PTK_F32 | PTK_F64.
+ * beta == 0 never reads C (so an AllocEmpty C holding NaNs is fine — gemv.py:79-86 contract).
+ * precision: 0 = native (fp32/fp64 FMA, <=1e-5 rel vs BLAS), 1 = bf16 operands on tcgen05 tensor cores with fp32
+ * TMEM accumulation (fp32 graphs only; needs `workspace` of ptk_gemm_workspace_bytes()). */
+size_t       ptk_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision);
+ptk_status   ptk_gemm(int dtype, int64_t M, int64_t N, int64_t K, double alpha,
+                      const void* A, int64_t sa0, int64_t sa1, const void* B, int64_t sb0, int64_t sb1,
+                      double beta, void* C, int64_t sc0, int64_t sc1,
+                      int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* Fused epilogue variant used by the linker peephole K5: C = act(alpha*A@B + bias[N]) with act 0=none, 1=tanh. */
+ptk_status   ptk_gemm_bias_act(int dtype, int64_t M, int64_t N, int64_t K,
+                      const void* A, int64_t sa0, int64_t sa1, const void* B, int64_t sb0, int64_t sb1,
+                      const void* bias, int act, void* C, int64_t sc0, int64_t sc1,
+                      int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
+ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
+                      const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);
+/* A[M,N] += alpha * x[M] y[N]^T */
+ptk_status   ptk_ger(int dtype, int64_t M, int64_t N, double alpha, const void* x, int64_t sx,
+                     const void* y, int64_t sy, void* A, int64_t sa0, int64_t sa1, void* stream);
+
+/* ---- dense linear algebra (A8/A9: Cholesky tensor/linalg/decomposition/cholesky.py:18 (potrf :52-83),
+ *      SolveTriangular tensor/linalg/solvers/triangular.py:13 (trtrs :41-71)) ------------------------------------ */
+/* In-place factorisation of `batch` column-or-row-major (n,n) matrices (row-major, ld = n). lower != 0 -> L with
+ * A = L L^T, the other triangle zeroed; non positive definite -> the whole matrix is NaN-filled (cholesky.py:78-80).*/
+ptk_status   ptk_potrf(int dtype, void* A, int64_t n, int64_t batch, int lower, void* stream);
+/* Solve op(A) X = B in place in B (n, nrhs) row-major, A (n,n) row-major; trans: 0 = A, 1 = A^T; unit_diag;
+ * singular (zero diagonal) -> B NaN-filled (triangular.py:68-69). */
+ptk_status   ptk_trsm(int dtype, const void* A, void* B, int64_t n, int64_t nrhs, int64_t batch,
+                      int lower, int trans, int unit_diag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_H */

@@ -1,0 +1,109 @@
+
+// ---- ptk scalar helpers (Python floor-division / modulo semantics of IntDiv / Mod) ----
+template <typename T> __device__ __forceinline__ T ptk_floordiv(T x, T y) {
+  if (y == 0) return 0;
+  T q = x / y;
+  if ((x % y != 0) && ((x < 0) != (y < 0))) --q;
+  return q;
+}
+template <typename T> __device__ __forceinline__ T ptk_imod_py(T x, T y) {
+  if (y == 0) return 0;
+  T r = x % y;
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+template <typename T> __device__ __forceinline__ T ptk_fmod_py(T x, T y) {
+  if (y == 0) return x - x + (T)__int_as_float(0x7fc00000);
+  T r = fmod(x, y);
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+
+
+template <typename T, int N> struct __align__(sizeof(T) * N) PVec { T v[N]; };
+template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv(const T* p) {
+  return *reinterpret_cast<const PVec<T, N>*>(p);
+}
+template <typename T, int N> __device__ __forceinline__ void ptk_stv(T* p, const PVec<T, N>& v) {
+  *reinterpret_cast<PVec<T, N>*>(p) = v;
+}
+
+__device__ __forceinline__ void ptk_body(const float i0, const float i1, float& o0) {
+  const float t0 = (float)(fabs(i0));
+  const float t1 = (float)((-(t0)));
+  const float t2 = (float)(exp((float)(t1)));
+  const float t3 = (float)(((i1) * (i1)));
+  const float t4 = (float)(((0x1.99999a0000000p-4f) * (t3)));
+  const float t5 = (float)(((i1) * (i0)));
+  const float t6 = (float)(((0x1.0000000000000p-1f) + (t5)));
+  const float t7 = (float)(((-0x1.cccccc0000000p-1f) * (t6)));
+  const float t8 = (float)(((0x1.cccccc0000000p-1f) * (t6)));
+  const float t9 = (float)((((t7) > (t8)) ? (t7) : (((t8) >= (t7)) ? (t8) : __int_as_float(0x7fc00000))));
+  const float t10 = (float)(((t9) + (t4)));
+  const float t11 = (float)(((t10) * (i0)));
+  const float t12 = (float)(((-0x1.0000000000000p-2f) + (t11)));
+  const float t13 = (float)(((-0x1.cccccc0000000p-1f) * (t12)));
+  const float t14 = (float)(((0x1.cccccc0000000p-1f) * (t12)));
+  const float t15 = (float)((((t13) > (t14)) ? (t13) : (((t14) >= (t13)) ? (t14) : __int_as_float(0x7fc00000))));
+  const float t16 = (float)(((t15) + (t4)));
+  const float t17 = (float)(((t16) * (i0)));
+  const float t18 = (float)(((0x1.0000000000000p-3f) + (t17)));
+  const float t19 = (float)(((-0x1.cccccc0000000p-1f) * (t18)));
+  const float t20 = (float)(((0x1.cccccc0000000p-1f) * (t18)));
+  const float t21 = (float)((((t19) > (t20)) ? (t19) : (((t20) >= (t19)) ? (t20) : __int_as_float(0x7fc00000))));
+  const float t22 = (float)(((t21) + (t4)));
+  const float t23 = (float)(((t22) * (i0)));
+  const float t24 = (float)(((0x1.8000000000000p-1f) + (t23)));
+  const float t25 = (float)(((-0x1.cccccc0000000p-1f) * (t24)));
+  const float t26 = (float)(((0x1.cccccc0000000p-1f) * (t24)));
+  const float t27 = (float)((((t25) > (t26)) ? (t25) : (((t26) >= (t25)) ? (t26) : __int_as_float(0x7fc00000))));
+  const float t28 = (float)(((t27) + (t4)));
+  const float t29 = (float)(((0x1.47ae140000000p-7f) * (t28)));
+  const float t30 = (float)(tanh((float)(t29)));
+  const float t31 = (float)(((t30) + (t2)));
+  o0 = (float)(t31);
+}
+
+#define VW 4
+#define U 4
+extern "C" __global__ void __launch_bounds__(256) ptk_ew_vec_5db4c6124dcbc138(const float* __restrict__ pi0, const float* __restrict__ pi1, float* __restrict__ po0, long long rsi0, long long rsi1, long long rso0, long long nchunks, unsigned int cpr, long long tail_start, long long n_total) {
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long base = gtid; base < nchunks; base += gstride * U) {
+      PVec<float, VW> vi0[U];
+      PVec<float, VW> vi1[U];
+      long long rr[U]; long long cc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {
+          long long r, c;
+          if (cpr == 0u) { r = 0; c = q * VW; }
+          else if (nchunks < 0x7fffffffLL) { unsigned int qq = (unsigned int)q; unsigned int r32 = qq / cpr; r = r32; c = (long long)(qq - r32 * cpr) * VW; }
+          else { r = q / cpr; c = (q - r * cpr) * VW; }
+          rr[u] = r; cc[u] = c;
+          vi0[u] = ptk_ldv<float, VW>(pi0 + r * rsi0 + c);
+          vi1[u] = ptk_ldv<float, VW>(pi1 + r * rsi1 + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {
+          const long long r = rr[u], c = cc[u];
+          PVec<float, VW> vo0;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            ptk_body(vi0[u].v[e], vi1[u].v[e], vo0.v[e]);
+          }
+          ptk_stv<float, VW>(po0 + r * rso0 + c, vo0);
+        }
+      }
+  }
+  // flat tail (rows == 1 only): the last n_total % VW elements
+  for (long long i = tail_start + gtid; i < n_total; i += gstride) {
+      float to0;
+      ptk_body(pi0[i], pi1[i], to0);
+      po0[i] = to0;
+  }
+}

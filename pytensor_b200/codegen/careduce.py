@@ -1,0 +1,247 @@
+"""CUDA source generation for CAReduce kernels (K2) and the fused map+reduce kernel (K3).
+
+Replaces `CAReduce._c_all` (pytensor/tensor/elemwise.py:1520-1678; loop generators elemwise_cgen.py:467,578).
+Accumulator dtype follows the reference (`_acc_dtype` elemwise.py:1383-1417: fp32 sums accumulate in fp64, small
+ints in int64); the combine order is a tree instead of the C loop's sequential order, which is why the parity bar
+for floating-point reductions is a tolerance and not bit-exactness.
+
+Kernel shapes (the host normalises every reduction to one of them):
+* `row`     — input(s) viewed as (rows, cols), reduce over the contiguous `cols`; TPR threads per row, 128-bit loads.
+              Optional fused map stage: a ScalarProgram applied to n_in operands (each contiguous or constant along
+              cols) whose outputs may also be stored — this is the Elemwise->Sum fusion the reference cannot do for
+              multi-input Elemwise (rewriting/elemwise.py:1119-1121).
+* `col`     — input viewed as (outer, red, inner) contiguous, reduce over the strided middle axis; threads along
+              `inner` (coalesced), optional split of `red` across blockIdx.z with a finishing pass.
+* `generic` — any strides: one thread per output element walks the reduced index space.
+* `finish`  — reduces `nsplit` partial accumulators per output (second pass of split reductions).
+"""
+
+from __future__ import annotations
+
+from .scalar import CTYPE, PRELUDE, ScalarProgram, emit_body, is_float, literal, single_op_program
+from .elemwise import _VEC_HELPERS, MAX_DIMS
+
+REDUCE_OPS = {
+    "add": lambda a, b, dt: f"(({a}) + ({b}))",
+    "mul": lambda a, b, dt: f"(({a}) * ({b}))",
+    "maximum": lambda a, b, dt: (f"ptk_nanmax(({a}), ({b}))" if is_float(dt) else f"((({b}) > ({a})) ? ({b}) : ({a}))"),
+    "minimum": lambda a, b, dt: (f"ptk_nanmin(({a}), ({b}))" if is_float(dt) else f"((({b}) < ({a})) ? ({b}) : ({a}))"),
+    "and": lambda a, b, dt: f"(({a}) & ({b}))",
+    "or": lambda a, b, dt: f"(({a}) | ({b}))",
+    "xor": lambda a, b, dt: f"(({a}) ^ ({b}))",
+}
+
+_RED_HELPERS = r"""
+template <typename T> __device__ __forceinline__ T ptk_nanmax(T a, T b) { return (b > a) ? b : ((a >= b) ? a : (a + b)); }
+template <typename T> __device__ __forceinline__ T ptk_nanmin(T a, T b) { return (b < a) ? b : ((a <= b) ? a : (a + b)); }
+template <typename T> __device__ __forceinline__ T ptk_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ unsigned char ptk_shfl_xor<unsigned char>(unsigned char v, int m) { return (unsigned char)__shfl_xor_sync(0xffffffffu, (int)v, m); }
+template <> __device__ __forceinline__ signed char ptk_shfl_xor<signed char>(signed char v, int m) { return (signed char)__shfl_xor_sync(0xffffffffu, (int)v, m); }
+template <> __device__ __forceinline__ short ptk_shfl_xor<short>(short v, int m) { return (short)__shfl_xor_sync(0xffffffffu, (int)v, m); }
+template <> __device__ __forceinline__ unsigned short ptk_shfl_xor<unsigned short>(unsigned short v, int m) { return (unsigned short)__shfl_xor_sync(0xffffffffu, (int)v, m); }
+"""
+
+
+def _combine(op, acc_dtype):
+    fn = REDUCE_OPS[op]
+    return f"__device__ __forceinline__ ACC ptk_red(ACC a, ACC b) {{ return (ACC){fn('a', 'b', acc_dtype)}; }}"
+
+
+def _block_reduce_code(tpr: int) -> str:
+    """Reduce `acc` across the TPR threads that share a row; result valid in the first of them."""
+    if tpr == 32:
+        return """
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc = ptk_red(acc, ptk_shfl_xor<ACC>(acc, m));
+"""
+    return f"""
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc = ptk_red(acc, ptk_shfl_xor<ACC>(acc, m));
+    __shared__ ACC s_part[{tpr // 32}];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {{
+      #pragma unroll
+      for (int w = 1; w < {tpr // 32}; ++w) acc = ptk_red(acc, s_part[w]);
+    }}
+    __syncthreads();
+"""
+
+
+def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: tuple, red_op: str, acc_dtype: str,
+                   out_dtype: str, identity, vw: int, tpr: int, inplace: dict | None = None) -> str:
+    """Fused map + row reduction.
+
+    prog: n_in inputs -> n_map outputs; output 0 of `prog` feeds the reduction.  store_map[k] tells whether map
+    output k is also written to memory (po{k}); col_modes as in the vec elemwise kernel (inputs then stored outputs).
+    Params: pi*, po* (stored map outputs only), pred (reduction result or partials), row strides (inputs, stored
+    outputs), rows, cols, nsplit.  grid = (row_blocks, nsplit); a block owns 256/TPR rows.
+    When nsplit > 1 `pred` holds ACC partials laid out [row][split], finished by the `finish` kernel.
+    """
+    n_in, n_map = len(prog.in_dtypes), len(prog.out_dtypes)
+    ACC, OUT = CTYPE[acc_dtype], CTYPE[out_dtype]
+    restrict = "" if inplace else " __restrict__"
+    params = [f"const {CTYPE[d]}*{restrict} pi{k}" for k, d in enumerate(prog.in_dtypes)]
+    stored = [k for k in range(n_map) if store_map[k]]
+    params += [f"{CTYPE[prog.out_dtypes[k]]}*{restrict} po{k}" for k in stored]
+    params += ["void* __restrict__ pred"]
+    params += [f"long long rsi{k}" for k in range(n_in)]
+    params += [f"long long rso{k}" for k in stored]
+    params += ["long long rows", "long long cols", "int nsplit"]
+    rows_per_block = 256 // tpr
+
+    ld = []
+    for k, d in enumerate(prog.in_dtypes):
+        T = CTYPE[d]
+        if col_modes[k] == 1:
+            ld.append(f"        const PVec<{T}, VW> vi{k} = ptk_ldv<{T}, VW>(pi{k} + r * rsi{k} + c);")
+        else:
+            ld.append(f"        const {T} vi{k} = pi{k}[r * rsi{k}];")
+    call_in = [f"vi{k}.v[e]" if col_modes[k] == 1 else f"vi{k}" for k in range(n_in)]
+    out_decl = "\n".join(f"        PVec<{CTYPE[d]}, VW> vo{k};" for k, d in enumerate(prog.out_dtypes))
+    call_out = [f"vo{k}.v[e]" for k in range(n_map)]
+    st = "\n".join(f"        ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(po{k} + r * rso{k} + c, vo{k});" for k in stored)
+    # scalar tail (cols % VW)
+    tail_in = [f"pi{k}[r * rsi{k} + c]" if col_modes[k] == 1 else f"pi{k}[r * rsi{k}]" for k in range(n_in)]
+    tail_tmp = "\n".join(f"        {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
+    tail_st = "\n".join(f"        po{k}[r * rso{k} + c] = to{k};" for k in stored)
+
+    return f"""{PRELUDE}
+{_VEC_HELPERS}
+{_RED_HELPERS}
+{emit_body(prog)}
+typedef {ACC} ACC;
+typedef {OUT} OUT;
+{_combine(red_op, acc_dtype)}
+#define VW {vw}
+#define TPR {tpr}
+
+extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
+  const int lane_in_row = threadIdx.x % TPR;
+  const int row_in_block = threadIdx.x / TPR;
+  const long long ncv = cols / VW;                       // vector chunks per row
+  const long long per_split = (ncv + nsplit - 1) / nsplit;
+  const int split = blockIdx.y;
+  const long long cv_lo = (long long)split * per_split;
+  const long long cv_hi = (cv_lo + per_split < ncv) ? (cv_lo + per_split) : ncv;
+  for (long long rb = (long long)blockIdx.x * {rows_per_block}; rb < rows; rb += (long long)gridDim.x * {rows_per_block}) {{
+    const long long r = rb + row_in_block;
+    ACC acc = (ACC){literal(acc_dtype, identity)};
+    if (r < rows) {{
+      for (long long cv = cv_lo + lane_in_row; cv < cv_hi; cv += TPR) {{
+        const long long c = cv * VW;
+{chr(10).join(ld)}
+{out_decl}
+        #pragma unroll
+        for (int e = 0; e < VW; ++e) {{
+          ptk_body({', '.join(call_in + call_out)});
+          acc = ptk_red(acc, (ACC)vo0.v[e]);
+        }}
+{st}
+      }}
+      if (split == nsplit - 1) {{
+        for (long long c = ncv * VW + lane_in_row; c < cols; c += TPR) {{
+{tail_tmp}
+          ptk_body({', '.join(tail_in + [f'to{k}' for k in range(n_map)])});
+          acc = ptk_red(acc, (ACC)to0);
+{tail_st}
+        }}
+      }}
+    }}
+{_block_reduce_code(tpr)}
+    if (lane_in_row == 0 && r < rows) {{
+      if (nsplit == 1) reinterpret_cast<OUT*>(pred)[r] = (OUT)acc;
+      else reinterpret_cast<ACC*>(pred)[r * nsplit + split] = acc;
+    }}
+  }}
+}}
+"""
+
+
+def gen_finish_kernel(name: str, red_op: str, acc_dtype: str, out_dtype: str, identity) -> str:
+    """out[o] = (OUT) reduce_s partial[o*nsplit + s]; one warp per output."""
+    ACC, OUT = CTYPE[acc_dtype], CTYPE[out_dtype]
+    return f"""{PRELUDE}
+{_RED_HELPERS}
+typedef {ACC} ACC;
+typedef {OUT} OUT;
+{_combine(red_op, acc_dtype)}
+extern "C" __global__ void __launch_bounds__(256) {name}(const ACC* __restrict__ part, OUT* __restrict__ out,
+                                                         long long n_out, int nsplit, long long part_stride_o,
+                                                         long long part_stride_s) {{
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long o = warp; o < n_out; o += nwarps) {{
+    ACC acc = (ACC){literal(acc_dtype, identity)};
+    for (int s = lane; s < nsplit; s += 32) acc = ptk_red(acc, part[o * part_stride_o + s * part_stride_s]);
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc = ptk_red(acc, ptk_shfl_xor<ACC>(acc, m));
+    if (lane == 0) out[o] = (OUT)acc;
+  }}
+}}
+"""
+
+
+def gen_col_kernel(name: str, in_dtype: str, red_op: str, acc_dtype: str, out_dtype: str, identity) -> str:
+    """Input (outer, red, inner) contiguous; out (outer, inner) [nsplit == 1] or ACC partials laid out
+    [split][outer][inner]. grid = (ceil(inner/256), outer, nsplit)."""
+    ACC, OUT, T = CTYPE[acc_dtype], CTYPE[out_dtype], CTYPE[in_dtype]
+    return f"""{PRELUDE}
+{_RED_HELPERS}
+typedef {ACC} ACC;
+typedef {OUT} OUT;
+{_combine(red_op, acc_dtype)}
+extern "C" __global__ void __launch_bounds__(256) {name}(const {T}* __restrict__ in, void* __restrict__ outp,
+                                                         long long outer, long long red, long long inner, int nsplit) {{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inner) return;
+  const long long per = (red + nsplit - 1) / nsplit;
+  const long long r_lo = (long long)blockIdx.z * per;
+  const long long r_hi = (r_lo + per < red) ? (r_lo + per) : red;
+  for (long long o = blockIdx.y; o < outer; o += gridDim.y) {{
+    const {T}* p = in + o * red * inner + i;
+    ACC a0 = (ACC){literal(acc_dtype, identity)}, a1 = a0, a2 = a0, a3 = a0;
+    long long r = r_lo;
+    for (; r + 3 < r_hi; r += 4) {{
+      const {T} x0 = p[r * inner], x1 = p[(r + 1) * inner], x2 = p[(r + 2) * inner], x3 = p[(r + 3) * inner];
+      a0 = ptk_red(a0, (ACC)x0); a1 = ptk_red(a1, (ACC)x1); a2 = ptk_red(a2, (ACC)x2); a3 = ptk_red(a3, (ACC)x3);
+    }}
+    for (; r < r_hi; ++r) a0 = ptk_red(a0, (ACC)p[r * inner]);
+    const ACC acc = ptk_red(ptk_red(a0, a1), ptk_red(a2, a3));
+    if (nsplit == 1) reinterpret_cast<OUT*>(outp)[o * inner + i] = (OUT)acc;
+    else reinterpret_cast<ACC*>(outp)[((long long)blockIdx.z * outer + o) * inner + i] = acc;
+  }}
+}}
+"""
+
+
+def gen_generic_kernel(name: str, in_dtype: str, red_op: str, acc_dtype: str, out_dtype: str, identity) -> str:
+    """One thread per output element. dims: kept dims (shape, input strides) then reduced dims (shape, strides)."""
+    ACC, OUT, T = CTYPE[acc_dtype], CTYPE[out_dtype], CTYPE[in_dtype]
+    return f"""{PRELUDE}
+{_RED_HELPERS}
+typedef {ACC} ACC;
+typedef {OUT} OUT;
+{_combine(red_op, acc_dtype)}
+struct RdDims {{ int nk; int nr; long long kshape[{MAX_DIMS}]; long long kst[{MAX_DIMS}]; long long rshape[{MAX_DIMS}]; long long rst[{MAX_DIMS}]; }};
+extern "C" __global__ void __launch_bounds__(256) {name}(const {T}* __restrict__ in, OUT* __restrict__ out,
+                                                         const RdDims d, long long n_out, long long n_red) {{
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += gstride) {{
+    long long rem = o, base = 0;
+    for (int k = d.nk - 1; k >= 0; --k) {{ const long long q = rem / d.kshape[k]; base += (rem - q * d.kshape[k]) * d.kst[k]; rem = q; }}
+    ACC acc = (ACC){literal(acc_dtype, identity)};
+    for (long long j = 0; j < n_red; ++j) {{
+      long long rj = j, off = base;
+      for (int k = d.nr - 1; k >= 0; --k) {{ const long long q = rj / d.rshape[k]; off += (rj - q * d.rshape[k]) * d.rst[k]; rj = q; }}
+      acc = ptk_red(acc, (ACC)in[off]);
+    }}
+    out[o] = (OUT)acc;
+  }}
+}}
+"""
+
+
+def identity_program(dtype: str) -> ScalarProgram:
+    return single_op_program("Identity", [dtype], dtype)

@@ -1,0 +1,172 @@
+"""CUDA source generation for fused Elemwise kernels (K1) — one kernel per `Elemwise(Composite)` node.
+
+Replaces what the C linker emits in `Elemwise._c_all` (pytensor/tensor/elemwise.py:848-1167: contiguous fast path
+:1118-1146, otherwise the stride-sorted loop nests of elemwise_cgen.py:294-465).  Two kernel shapes:
+
+* `vec`  — the HBM-bound shape.  After the host collapsed the iteration space to (rows, cols), every operand is
+  either contiguous along `cols` (128-bit `ld.global.v4` / `st.global.v4` per 4-byte element type, U chunks in
+  flight per thread) or constant along `cols` (row/scalar broadcast: one scalar load per chunk).  Grid-stride,
+  sized by the host to a multiple of the SM count.
+* `gen`  — any <= 8-d strided/broadcast pattern, one element per thread-iteration (index arithmetic per element).
+
+The scalar body is `codegen.scalar.emit_body(prog)`.
+"""
+
+from __future__ import annotations
+
+from .scalar import CTYPE, ITEMSIZE, PRELUDE, ScalarProgram, emit_body
+
+MAX_DIMS = 8
+VEC_UNROLL = 4
+
+_VEC_HELPERS = r"""
+template <typename T, int N> struct __align__(sizeof(T) * N) PVec { T v[N]; };
+template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv(const T* p) {
+  return *reinterpret_cast<const PVec<T, N>*>(p);
+}
+template <typename T, int N> __device__ __forceinline__ void ptk_stv(T* p, const PVec<T, N>& v) {
+  *reinterpret_cast<PVec<T, N>*>(p) = v;
+}
+"""
+
+
+def vec_width(dtypes) -> int:
+    """Elements per thread-chunk: 16 bytes of the widest... narrowest useful: 4 for 4/8-byte types, 8/16 for small."""
+    m = max(ITEMSIZE[d] for d in dtypes)
+    if m >= 4:
+        return 4
+    if m == 2:
+        return 8
+    return 16
+
+
+def gen_vec_kernel(prog: ScalarProgram, name: str, col_modes: tuple, inplace: dict, vw: int,
+                   unroll: int = VEC_UNROLL) -> str:
+    """col_modes[k] in {0,1} for the n_in inputs followed by the n_out outputs (outputs are always 1).
+    inplace: {out_idx: in_idx}.  Kernel params: pointers..., row strides..., nchunks, chunks_per_row, n_tail_start,
+    n_total (flat tail handling: elements [n_tail_start, n_total) are done one by one when rows == 1)."""
+    n_in, n_out = len(prog.in_dtypes), len(prog.out_dtypes)
+    restrict = "" if inplace else " __restrict__"
+    params = []
+    for k, d in enumerate(prog.in_dtypes):
+        params.append(f"const {CTYPE[d]}*{restrict} pi{k}")
+    for k, d in enumerate(prog.out_dtypes):
+        params.append(f"{CTYPE[d]}*{restrict} po{k}")
+    params += [f"long long rsi{k}" for k in range(n_in)]
+    params += [f"long long rso{k}" for k in range(n_out)]
+    params += ["long long nchunks", "unsigned int cpr", "long long tail_start", "long long n_total"]
+
+    loads, scal = [], []
+    for k, d in enumerate(prog.in_dtypes):
+        T = CTYPE[d]
+        if col_modes[k] == 1:
+            loads.append(f"      PVec<{T}, VW> vi{k}[U];")
+        else:
+            loads.append(f"      {T} vi{k}[U];")
+    ld_body = []
+    for k, d in enumerate(prog.in_dtypes):
+        T = CTYPE[d]
+        if col_modes[k] == 1:
+            ld_body.append(f"          vi{k}[u] = ptk_ldv<{T}, VW>(pi{k} + r * rsi{k} + c);")
+        else:
+            ld_body.append(f"          vi{k}[u] = pi{k}[r * rsi{k}];")
+    call_in = []
+    for k in range(n_in):
+        call_in.append(f"vi{k}[u].v[e]" if col_modes[k] == 1 else f"vi{k}[u]")
+    out_decl = "\n".join(f"          PVec<{CTYPE[d]}, VW> vo{k};" for k, d in enumerate(prog.out_dtypes))
+    call_out = [f"vo{k}.v[e]" for k in range(n_out)]
+    st_body = "\n".join(f"          ptk_stv<{CTYPE[d]}, VW>(po{k} + r * rso{k} + c, vo{k});"
+                        for k, d in enumerate(prog.out_dtypes))
+    tail_in = [f"pi{k}[i]" if col_modes[k] == 1 else f"pi{k}[0]" for k in range(n_in)]
+    tail_tmp = "\n".join(f"      {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
+    tail_st = "\n".join(f"      po{k}[i] = to{k};" for k in range(n_out))
+
+    return f"""{PRELUDE}
+{_VEC_HELPERS}
+{emit_body(prog)}
+
+#define VW {vw}
+#define U {unroll}
+extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long base = gtid; base < nchunks; base += gstride * U) {{
+{chr(10).join(loads)}
+      long long rr[U]; long long cc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {{
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {{
+          long long r, c;
+          if (cpr == 0u) {{ r = 0; c = q * VW; }}
+          else if (nchunks < 0x7fffffffLL) {{ unsigned int qq = (unsigned int)q; unsigned int r32 = qq / cpr; r = r32; c = (long long)(qq - r32 * cpr) * VW; }}
+          else {{ r = q / cpr; c = (q - r * cpr) * VW; }}
+          rr[u] = r; cc[u] = c;
+{chr(10).join(ld_body)}
+        }}
+      }}
+#pragma unroll
+      for (int u = 0; u < U; ++u) {{
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {{
+          const long long r = rr[u], c = cc[u];
+{out_decl}
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {{
+            ptk_body({', '.join(call_in + call_out)});
+          }}
+{st_body}
+        }}
+      }}
+  }}
+  // flat tail (rows == 1 only): the last n_total % VW elements
+  for (long long i = tail_start + gtid; i < n_total; i += gstride) {{
+{tail_tmp}
+      ptk_body({', '.join(tail_in + [f'to{k}' for k in range(n_out)])});
+{tail_st}
+  }}
+}}
+"""
+
+
+def gen_generic_kernel(prog: ScalarProgram, name: str, inplace: dict) -> str:
+    """Any-stride kernel. Params: pointers..., EwDims (by value), total."""
+    n_in, n_out = len(prog.in_dtypes), len(prog.out_dtypes)
+    nops = n_in + n_out
+    restrict = "" if inplace else " __restrict__"
+    params = []
+    for k, d in enumerate(prog.in_dtypes):
+        params.append(f"const {CTYPE[d]}*{restrict} pi{k}")
+    for k, d in enumerate(prog.out_dtypes):
+        params.append(f"{CTYPE[d]}*{restrict} po{k}")
+    params += ["const EwDims dims", "long long total"]
+    offs_decl = "\n".join(f"    long long off{j} = 0;" for j in range(nops))
+    offs_acc = "\n".join(f"        off{j} += cidx * dims.st[{j}][k];" for j in range(nops))
+    call_in = [f"pi{k}[off{k}]" for k in range(n_in)]
+    tmp_decl = "\n".join(f"    {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
+    stores = "\n".join(f"    po{k}[off{n_in + k}] = to{k};" for k in range(n_out))
+    return f"""{PRELUDE}
+{emit_body(prog)}
+
+struct EwDims {{ int ndim; long long shape[{MAX_DIMS}]; long long st[{nops}][{MAX_DIMS}]; }};
+
+extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {{
+    long long rem = i;
+{offs_decl}
+#pragma unroll
+    for (int k = {MAX_DIMS} - 1; k >= 0; --k) {{
+      if (k < dims.ndim) {{
+        const long long q = rem / dims.shape[k];
+        const long long cidx = rem - q * dims.shape[k];
+        rem = q;
+{offs_acc}
+      }}
+    }}
+{tmp_decl}
+    ptk_body({', '.join(call_in + [f'to{k}' for k in range(n_out)])});
+{stores}
+  }}
+}}
+"""

@@ -1,0 +1,285 @@
+// Native-precision BLAS family (fp32 / fp64 FMA pipes): GEMM with arbitrary element strides, GEMV, GER.
+// These are the "<= 1e-5 vs the C linker" paths behind Gemm / Dot22 / Dot22Scalar / Gemv / Ger
+// (pytensor/tensor/blas/gemm.py:76,248,298, gemv.py:16, ger.py:8); the bf16 tensor-core path is ptk_gemm_tc.cu.
+#include <algorithm>
+#include "ptk_common.h"
+
+namespace ptk {
+ptk_status gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
+                   const float* B, int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1,
+                   const float* bias, int act, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K);
+}  // namespace ptk
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+template <typename T>
+__device__ __forceinline__ T act_apply(T v, int act) {
+  if (act == 1) return tanh(v);
+  return v;
+}
+template <>
+__device__ __forceinline__ float act_apply<float>(float v, int act) {
+  if (act == 1) return tanhf(v);
+  return v;
+}
+
+// C = alpha * A @ B + beta * C (+ bias[n], act). A_KFAST: A's K stride is 1; B_NFAST: B's N stride is 1 — only the
+// thread->element mapping of the global loads changes so that a warp always walks the unit-stride direction.
+template <typename T, bool A_KFAST, bool B_NFAST>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(int64_t M, int64_t N, int64_t K, T alpha,
+                                                        const T* __restrict__ A, int64_t sa0, int64_t sa1,
+                                                        const T* __restrict__ B, int64_t sb0, int64_t sb1, T beta,
+                                                        T* __restrict__ C, int64_t sc0, int64_t sc1,
+                                                        const T* __restrict__ bias, int act) {
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  const int t = threadIdx.x;
+  const int tx = t % 16, ty = t / 16;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  for (int64_t k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (A_KFAST) { k = t % BK; m = t / BK + 16 * i; }
+      else         { m = t % BM; k = t / BM + 4 * i; }
+      int64_t gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < K) ? A[gm * sa0 + gk * sa1] : T(0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int n, k;
+      if (B_NFAST) { n = t % BN; k = t / BN + 4 * i; }
+      else         { k = t % BK; n = t / BK + 16 * i; }
+      int64_t gn = n0 + n, gk = k0 + k;
+      Bs[k][n] = (gn < N && gk < K) ? B[gk * sb0 + gn * sb1] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int64_t gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      T* p = C + gm * sc0 + gn * sc1;
+      T v = alpha * acc[i][j];
+      if (beta != T(0)) v += beta * (*p);  // beta == 0 must not read C (it may hold NaNs from AllocEmpty)
+      if (bias) v += bias[gn];
+      *p = act_apply<T>(v, act);
+    }
+  }
+}
+
+template <typename T>
+ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void* A, int64_t sa0, int64_t sa1,
+                       const void* B, int64_t sb0, int64_t sb1, double beta, void* C, int64_t sc0, int64_t sc1,
+                       const void* bias, int act, cudaStream_t st) {
+  if (M == 0 || N == 0) return PTK_OK;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+  if (grid.y > 65535) return ptk::fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: M too large for the SIMT path");
+  bool akf = (sa1 == 1) || K == 1, bnf = (sb1 == 1) || N == 1;
+  if (sa0 == 1 && sa1 != 1) akf = false;
+  if (sb0 == 1 && sb1 != 1) bnf = false;
+#define PTK_G(AK, BNF)                                                                                       \
+  gemm_simt_kernel<T, AK, BNF><<<grid, 256, 0, st>>>(M, N, K, (T)alpha, (const T*)A, sa0, sa1, (const T*)B, \
+                                                      sb0, sb1, (T)beta, (T*)C, sc0, sc1, (const T*)bias, act)
+  if (akf && bnf) PTK_G(true, true);
+  else if (akf && !bnf) PTK_G(true, false);
+  else if (!akf && bnf) PTK_G(false, true);
+  else PTK_G(false, false);
+#undef PTK_G
+  PTK_LAUNCH_CHECK("gemm_simt");
+  return PTK_OK;
+}
+
+// ---- GEMV ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scale_vec_kernel(T* y, int64_t sy, int64_t M, T beta) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) y[i * sy] = (beta == T(0)) ? T(0) : beta * y[i * sy];
+}
+
+// One warp per (row, column-chunk); lanes walk the unit-stride (or sa1-strided) direction of the row.
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_row_kernel(int64_t M, int64_t N, T alpha, const T* __restrict__ A,
+                                                       int64_t sa0, int64_t sa1, const T* __restrict__ x, int64_t sx,
+                                                       T beta, T* __restrict__ y, int64_t sy, int64_t chunk,
+                                                       int64_t nchunks) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < M * nchunks; w += nwarps) {
+    int64_t m = w / nchunks, c = w - m * nchunks;
+    int64_t n_lo = c * chunk, n_hi = min(N, n_lo + chunk);
+    const T* row = A + m * sa0;
+    T s = T(0);
+    for (int64_t n = n_lo + lane; n < n_hi; n += 32) s += row[n * sa1] * x[n * sx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (nchunks == 1) {
+        T v = alpha * s;
+        if (beta != T(0)) v += beta * y[m * sy];
+        y[m * sy] = v;
+      } else {
+        atomicAdd(&y[m * sy], alpha * s);  // y was pre-scaled by beta
+      }
+    }
+  }
+}
+
+// A is "column fast" (sa0 == 1): lanes own consecutive rows m, each block walks one chunk of columns.
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_col_kernel(int64_t M, int64_t N, T alpha, const T* __restrict__ A,
+                                                       int64_t sa0, int64_t sa1, const T* __restrict__ x, int64_t sx,
+                                                       T* __restrict__ y, int64_t sy, int64_t chunk) {
+  __shared__ T red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 32 rows x 8 column groups
+  int64_t m = (int64_t)blockIdx.x * 32 + lane;
+  int64_t n_lo = (int64_t)blockIdx.y * chunk, n_hi = min(N, n_lo + chunk);
+  T s = T(0);
+  if (m < M)
+    for (int64_t n = n_lo + grp; n < n_hi; n += 8) s += A[m * sa0 + n * sa1] * x[n * sx];
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && m < M) {
+    T tot = T(0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tot += red[g][lane];
+    atomicAdd(&y[m * sy], alpha * tot);  // y was pre-scaled by beta
+  }
+}
+
+template <typename T>
+ptk_status launch_gemv(int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1, const void* x,
+                       int64_t sx, double beta, void* y, int64_t sy, cudaStream_t st) {
+  if (M == 0) return PTK_OK;
+  const int sms = std::max(1, ptk::sm_count());
+  if (sa0 == 1 && sa1 != 1 && N > 1) {
+    scale_vec_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, st>>>((T*)y, sy, M, (T)beta);
+    int64_t mblocks = (M + 31) / 32;
+    int64_t want = std::max<int64_t>(1, (int64_t)sms * 4 / mblocks);
+    int64_t nchunks = std::min<int64_t>(want, (N + 63) / 64);
+    nchunks = std::max<int64_t>(1, std::min<int64_t>(nchunks, 65535));
+    int64_t chunk = (N + nchunks - 1) / nchunks;
+    dim3 grid((unsigned)mblocks, (unsigned)nchunks);
+    gemv_col_kernel<T><<<grid, 256, 0, st>>>(M, N, (T)alpha, (const T*)A, sa0, sa1, (const T*)x, sx, (T*)y, sy, chunk);
+    PTK_LAUNCH_CHECK("gemv_col");
+    return PTK_OK;
+  }
+  // row kernel: split long rows so that at least ~4 warps per SM exist
+  int64_t nchunks = 1;
+  int64_t target = (int64_t)sms * 32;
+  if (M < target && N > 4096) nchunks = std::min<int64_t>((target + M - 1) / M, (N + 1023) / 1024);
+  int64_t chunk = (N + nchunks - 1) / nchunks;
+  if (nchunks > 1) scale_vec_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, st>>>((T*)y, sy, M, (T)beta);
+  int64_t warps = M * nchunks;
+  unsigned blocks = (unsigned)std::min<int64_t>((warps + 7) / 8, (int64_t)sms * 16);
+  gemv_row_kernel<T><<<blocks, 256, 0, st>>>(M, N, (T)alpha, (const T*)A, sa0, sa1, (const T*)x, sx, (T)beta, (T*)y,
+                                             sy, chunk, nchunks);
+  PTK_LAUNCH_CHECK("gemv_row");
+  return PTK_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ger_kernel(int64_t M, int64_t N, T alpha, const T* __restrict__ x, int64_t sx,
+                                                  const T* __restrict__ y, int64_t sy, T* __restrict__ A, int64_t sa0,
+                                                  int64_t sa1) {
+  int64_t total = M * N, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t m = i / N, n = i - m * N;
+    A[m * sa0 + n * sa1] += alpha * x[m * sx] * y[n * sy];
+  }
+}
+
+}  // namespace
+
+using namespace ptk;
+
+extern "C" {
+
+size_t ptk_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision) {
+  if (precision == 1) return ptk::gemm_tc_workspace(M, N, K);
+  return 0;
+}
+
+ptk_status ptk_gemm_bias_act(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t sa0, int64_t sa1,
+                             const void* B, int64_t sb0, int64_t sb1, const void* bias, int act, void* C, int64_t sc0,
+                             int64_t sc1, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  PTK_REQUIRE_INIT();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == 1) {
+    if (dtype != PTK_F32) return fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: the bf16 tensor-core path takes fp32 graphs only");
+    return ptk::gemm_tc(M, N, K, 1.0f, (const float*)A, sa0, sa1, (const float*)B, sb0, sb1, 0.0f, (float*)C, sc0,
+                        sc1, (const float*)bias, act, workspace, workspace_bytes, st);
+  }
+  if (dtype == PTK_F32) return launch_gemm<float>(M, N, K, 1.0, A, sa0, sa1, B, sb0, sb1, 0.0, C, sc0, sc1, bias, act, st);
+  if (dtype == PTK_F64) return launch_gemm<double>(M, N, K, 1.0, A, sa0, sa1, B, sb0, sb1, 0.0, C, sc0, sc1, bias, act, st);
+  return fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: dtype must be float32 or float64");
+}
+
+ptk_status ptk_gemm(int dtype, int64_t M, int64_t N, int64_t K, double alpha, const void* A, int64_t sa0,
+                    int64_t sa1, const void* B, int64_t sb0, int64_t sb1, double beta, void* C, int64_t sc0,
+                    int64_t sc1, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  PTK_REQUIRE_INIT();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == 1) {
+    if (dtype != PTK_F32) return fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: the bf16 tensor-core path takes fp32 graphs only");
+    return ptk::gemm_tc(M, N, K, (float)alpha, (const float*)A, sa0, sa1, (const float*)B, sb0, sb1, (float)beta,
+                        (float*)C, sc0, sc1, nullptr, 0, workspace, workspace_bytes, st);
+  }
+  if (dtype == PTK_F32) return launch_gemm<float>(M, N, K, alpha, A, sa0, sa1, B, sb0, sb1, beta, C, sc0, sc1, nullptr, 0, st);
+  if (dtype == PTK_F64) return launch_gemm<double>(M, N, K, alpha, A, sa0, sa1, B, sb0, sb1, beta, C, sc0, sc1, nullptr, 0, st);
+  return fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: dtype must be float32 or float64");
+}
+
+ptk_status ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
+                    const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream) {
+  PTK_REQUIRE_INIT();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PTK_F32) return launch_gemv<float>(M, N, alpha, A, sa0, sa1, x, sx, beta, y, sy, st);
+  if (dtype == PTK_F64) return launch_gemv<double>(M, N, alpha, A, sa0, sa1, x, sx, beta, y, sy, st);
+  return fail(PTK_ERR_UNSUPPORTED, "ptk_gemv: dtype must be float32 or float64");
+}
+
+ptk_status ptk_ger(int dtype, int64_t M, int64_t N, double alpha, const void* x, int64_t sx, const void* y,
+                   int64_t sy, void* A, int64_t sa0, int64_t sa1, void* stream) {
+  PTK_REQUIRE_INIT();
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = M * N;
+  if (total == 0) return PTK_OK;
+  unsigned g = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)std::max(1, ptk::sm_count()) * 16);
+  if (dtype == PTK_F32)
+    ger_kernel<float><<<g, 256, 0, st>>>(M, N, (float)alpha, (const float*)x, sx, (const float*)y, sy, (float*)A, sa0, sa1);
+  else if (dtype == PTK_F64)
+    ger_kernel<double><<<g, 256, 0, st>>>(M, N, alpha, (const double*)x, sx, (const double*)y, sy, (double*)A, sa0, sa1);
+  else return fail(PTK_ERR_UNSUPPORTED, "ptk_ger: dtype must be float32 or float64");
+  PTK_LAUNCH_CHECK("ger");
+  return PTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// Data-movement glue kernels (HBM-bound byte work): strided copy / set / inc, take (gather) and put (scatter).
+// Replaces the C loops the reference emits for DeepCopyOp, Alloc, IncSubtensor, AdvancedSubtensor and
+// AdvancedIncSubtensor (pytensor/compile/ops.py:121, tensor/basic.py:1545, tensor/subtensor.py:1441,1932,2275).
+#include <algorithm>
+#include "ptk_common.h"
+
+namespace {
+
+constexpr int kMaxDims = 8;
+
+struct Dims {
+  int ndim;
+  int64_t shape[kMaxDims];
+  int64_t a[kMaxDims];  // dst strides (elements)
+  int64_t b[kMaxDims];  // src strides (elements)
+};
+
+// Drop size-1 dims and merge neighbours that are contiguous in BOTH operands; returns total element count.
+int64_t collapse(Dims& d, const int64_t* shape, const int64_t* sa, const int64_t* sb, int ndim) {
+  int64_t total = 1;
+  int n = 0;
+  for (int i = 0; i < ndim; ++i) {
+    total *= shape[i];
+    if (shape[i] == 1) continue;
+    if (n > 0 && d.a[n - 1] == sa[i] * shape[i] && d.b[n - 1] == sb[i] * shape[i]) {
+      d.shape[n - 1] *= shape[i];
+      d.a[n - 1] = sa[i];
+      d.b[n - 1] = sb[i];
+    } else {
+      d.shape[n] = shape[i];
+      d.a[n] = sa[i];
+      d.b[n] = sb[i];
+      ++n;
+    }
+  }
+  if (n == 0) {
+    d.shape[0] = 1;
+    d.a[0] = 0;
+    d.b[0] = 0;
+    n = 1;
+  }
+  d.ndim = n;
+  return total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_strided_kernel(T* __restrict__ dst, const T* __restrict__ src, Dims d,
+                                                           int64_t total) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t r = i, oa = 0, ob = 0;
+#pragma unroll
+    for (int k = kMaxDims - 1; k >= 0; --k) {
+      if (k < d.ndim) {
+        int64_t q = r / d.shape[k];
+        int64_t c = r - q * d.shape[k];
+        oa += c * d.a[k];
+        ob += c * d.b[k];
+        r = q;
+      }
+    }
+    dst[oa] = src[ob];
+  }
+}
+
+// Contiguous destination and source both 16-byte aligned: plain 128-bit streaming copy.
+__global__ void __launch_bounds__(256) copy_vec16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                         int64_t n16) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
+template <typename T>
+__device__ __forceinline__ void atomic_add_t(T* p, T v) { atomicAdd(p, v); }
+template <>
+__device__ __forceinline__ void atomic_add_t<int64_t>(int64_t* p, int64_t v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+template <>
+__device__ __forceinline__ void atomic_add_t<uint64_t>(uint64_t* p, uint64_t v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) inc_strided_kernel(T* __restrict__ dst, const T* __restrict__ src, Dims d,
+                                                          int64_t total) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t r = i, oa = 0, ob = 0;
+#pragma unroll
+    for (int k = kMaxDims - 1; k >= 0; --k) {
+      if (k < d.ndim) {
+        int64_t q = r / d.shape[k];
+        int64_t c = r - q * d.shape[k];
+        oa += c * d.a[k];
+        ob += c * d.b[k];
+        r = q;
+      }
+    }
+    dst[oa] = dst[oa] + src[ob];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) take_kernel(T* __restrict__ out, const T* __restrict__ src,
+                                                   const int64_t* __restrict__ idx, int64_t outer, int64_t n_src,
+                                                   int64_t n_idx, int64_t inner, int* err) {
+  int64_t total = outer * n_idx * inner;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int64_t i = t % inner;
+    int64_t r = t / inner;
+    int64_t j = r % n_idx;
+    int64_t o = r / n_idx;
+    int64_t k = idx[j];
+    if (k < 0) k += n_src;
+    if (k < 0 || k >= n_src) {
+      if (err) atomicExch(err, 1);
+      continue;
+    }
+    out[t] = src[(o * n_src + k) * inner + i];
+  }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) put_kernel(T* __restrict__ dst, const T* __restrict__ y,
+                                                  const int64_t* __restrict__ idx, int64_t outer, int64_t n_dst,
+                                                  int64_t n_idx, int64_t inner, int* err) {
+  int64_t total = outer * n_idx * inner;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int64_t i = t % inner;
+    int64_t r = t / inner;
+    int64_t j = r % n_idx;
+    int64_t o = r / n_idx;
+    int64_t k = idx[j];
+    if (k < 0) k += n_dst;
+    if (k < 0 || k >= n_dst) {
+      if (err) atomicExch(err, 1);
+      continue;
+    }
+    T* p = dst + (o * n_dst + k) * inner + i;
+    if (OP == 0) *p = y[t];
+    else atomic_add_t<T>(p, y[t]);
+  }
+}
+
+inline unsigned grid_for(int64_t total, int threads = 256) {
+  int64_t blocks = (total + threads - 1) / threads;
+  int64_t cap = (int64_t)ptk::sm_count() * 16;
+  if (cap <= 0) cap = 148 * 16;
+  return (unsigned)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+}  // namespace
+
+using namespace ptk;
+
+extern "C" {
+
+ptk_status ptk_copy_strided(void* dst, const int64_t* dst_strides, const void* src, const int64_t* src_strides,
+                            const int64_t* shape, int ndim, int itemsize, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (ndim < 0 || ndim > kMaxDims) return fail(PTK_ERR_ARG, "ptk_copy_strided: ndim > 8");
+  Dims d;
+  int64_t total = collapse(d, shape, dst_strides, src_strides, ndim);
+  if (total == 0) return PTK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.ndim == 1 && d.a[0] == 1 && d.b[0] == 1) {
+    size_t bytes = (size_t)total * itemsize;
+    if (bytes % 16 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0)) {
+      copy_vec16_kernel<<<grid_for(bytes / 16), 256, 0, st>>>((uint4*)dst, (const uint4*)src, bytes / 16);
+      PTK_LAUNCH_CHECK("copy_vec16");
+      return PTK_OK;
+    }
+  }
+  unsigned g = grid_for(total);
+  switch (itemsize) {
+    case 1: copy_strided_kernel<uint8_t><<<g, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, d, total); break;
+    case 2: copy_strided_kernel<uint16_t><<<g, 256, 0, st>>>((uint16_t*)dst, (const uint16_t*)src, d, total); break;
+    case 4: copy_strided_kernel<uint32_t><<<g, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, d, total); break;
+    case 8: copy_strided_kernel<uint64_t><<<g, 256, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, d, total); break;
+    default: return fail(PTK_ERR_ARG, "ptk_copy_strided: itemsize must be 1, 2, 4 or 8");
+  }
+  PTK_LAUNCH_CHECK("copy_strided");
+  return PTK_OK;
+}
+
+ptk_status ptk_inc_strided(void* dst, const int64_t* dst_strides, const void* src, const int64_t* src_strides,
+                           const int64_t* shape, int ndim, int dtype, int op, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (op == 0) return ptk_copy_strided(dst, dst_strides, src, src_strides, shape, ndim, dtype_size(dtype), stream);
+  if (ndim < 0 || ndim > kMaxDims) return fail(PTK_ERR_ARG, "ptk_inc_strided: ndim > 8");
+  Dims d;
+  int64_t total = collapse(d, shape, dst_strides, src_strides, ndim);
+  if (total == 0) return PTK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = grid_for(total);
+#define PTK_INC(T) inc_strided_kernel<T><<<g, 256, 0, st>>>((T*)dst, (const T*)src, d, total); break;
+  switch (dtype) {
+    case PTK_F32: PTK_INC(float)
+    case PTK_F64: PTK_INC(double)
+    case PTK_I8: PTK_INC(int8_t)
+    case PTK_I16: PTK_INC(int16_t)
+    case PTK_I32: PTK_INC(int32_t)
+    case PTK_I64: PTK_INC(int64_t)
+    case PTK_U8: PTK_INC(uint8_t)
+    case PTK_U16: PTK_INC(uint16_t)
+    case PTK_U32: PTK_INC(uint32_t)
+    case PTK_U64: PTK_INC(uint64_t)
+    default: return fail(PTK_ERR_UNSUPPORTED, "ptk_inc_strided: dtype");
+  }
+#undef PTK_INC
+  PTK_LAUNCH_CHECK("inc_strided");
+  return PTK_OK;
+}
+
+ptk_status ptk_take(void* out, const void* src, const int64_t* idx, int64_t outer, int64_t n_src, int64_t n_idx,
+                    int64_t inner, int itemsize, int* err_flag, void* stream) {
+  PTK_REQUIRE_INIT();
+  int64_t total = outer * n_idx * inner;
+  if (total == 0) return PTK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = grid_for(total);
+#define PTK_TAKE(T) \
+  take_kernel<T><<<g, 256, 0, st>>>((T*)out, (const T*)src, idx, outer, n_src, n_idx, inner, err_flag); break;
+  switch (itemsize) {
+    case 1: PTK_TAKE(uint8_t)
+    case 2: PTK_TAKE(uint16_t)
+    case 4: PTK_TAKE(uint32_t)
+    case 8: PTK_TAKE(uint64_t)
+    default: return fail(PTK_ERR_ARG, "ptk_take: itemsize must be 1, 2, 4 or 8");
+  }
+#undef PTK_TAKE
+  PTK_LAUNCH_CHECK("take");
+  return PTK_OK;
+}
+
+ptk_status ptk_put(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
+                   int64_t inner, int dtype, int op, int* err_flag, void* stream) {
+  PTK_REQUIRE_INIT();
+  int64_t total = outer * n_idx * inner;
+  if (total == 0) return PTK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = grid_for(total);
+#define PTK_PUT(T)                                                                                              \
+  if (op == 0) put_kernel<T, 0><<<g, 256, 0, st>>>((T*)dst, (const T*)y, idx, outer, n_dst, n_idx, inner, err_flag); \
+  else put_kernel<T, 1><<<g, 256, 0, st>>>((T*)dst, (const T*)y, idx, outer, n_dst, n_idx, inner, err_flag);   \
+  break;
+  switch (dtype) {
+    case PTK_F32: PTK_PUT(float)
+    case PTK_F64: PTK_PUT(double)
+    case PTK_I32: PTK_PUT(int32_t)
+    case PTK_I64: PTK_PUT(int64_t)
+    case PTK_U32: PTK_PUT(uint32_t)
+    case PTK_U64: PTK_PUT(uint64_t)
+    default: return fail(PTK_ERR_UNSUPPORTED, "ptk_put: dtype (f32/f64/i32/i64/u32/u64 only)");
+  }
+#undef PTK_PUT
+  PTK_LAUNCH_CHECK("put");
+  return PTK_OK;
+}
+
+}  // extern "C"

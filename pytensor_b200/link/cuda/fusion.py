@@ -1,0 +1,18 @@
+"""Linker-level kernel-boundary re-fusion (peepholes over the lowered step list).
+
+The reference's rewriter decides the node boundaries we receive; two fusions it cannot express are done here, after
+lowering, because they only make sense for a device backend:
+  * Elemwise(Composite) -> CAReduce over the trailing axes of one of its outputs, as ONE kernel (K3): the reference
+    refuses to fuse a multi-input Elemwise into a CAReduce (pytensor/tensor/rewriting/elemwise.py:1119-1121), so the
+    C linker re-reads the elementwise result from memory; the fused kernel keeps it in registers.
+  * Dot22 -> Elemwise{act(x + bias)} epilogue (K5), see nodes_blas.
+"""
+
+from __future__ import annotations
+
+
+def fuse_steps(steps, output_slots, opts):
+    from pytensor_b200.link.cuda.fusion_passes import fuse_elemwise_reduce
+
+    steps = fuse_elemwise_reduce(steps, output_slots, opts)
+    return steps

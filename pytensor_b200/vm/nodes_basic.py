@@ -1,0 +1,440 @@
+"""Glue nodes: views, shape plumbing, allocation, copies, basic and advanced indexing.
+
+Views (DimShuffle, Subtensor, Reshape of a contiguous buffer) are metadata only — no kernel, exactly like the
+reference (`DimShuffle` is pure stride arithmetic, pytensor/tensor/elemwise.py:186-256).  Every byte that moves does
+so in a libptk kernel (ptk_copy_strided / ptk_inc_strided / ptk_take / ptk_put), which keeps gather/slicing
+bit-exact by construction.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..runtime import device as dev
+from ..runtime import lib as _lib
+from .nodes_elemwise import Node
+from .values import Val
+
+
+def _host_int(v: Val) -> int:
+    return int(np.asarray(v.host()).reshape(-1)[0]) if np.ndim(v.host()) else int(v.host())
+
+
+class DimShuffleNode(Node):
+    """Reference: DimShuffle, pytensor/tensor/elemwise.py:41 (view_map {0:[0]} :115; dropped dims must be 1 :195-203)."""
+
+    def __init__(self, new_order, input_ndim, name="DimShuffle"):
+        self.new_order = tuple(new_order)
+        self.input_ndim = input_ndim
+        self.drop = [i for i in range(input_ndim) if i not in self.new_order]
+        self.name = name
+
+    def run(self, vals):
+        v = vals[0]
+        shape = v.shape
+        for i in self.drop:
+            if shape[i] != 1:
+                raise ValueError(f"{self.name}: cannot drop dim {i} of length {shape[i]} (must be 1)")
+        out = Val()
+        if v.d is not None:
+            t = v.d
+            oshape, ostride = [], []
+            for o in self.new_order:
+                if o == "x":
+                    oshape.append(1)
+                    ostride.append(1)
+                else:
+                    oshape.append(t.shape[o])
+                    ostride.append(t.stride(o))
+            out.d = t.as_strided(oshape, ostride, t.storage_offset())
+        if v.h is not None:
+            h = np.asarray(v.h)
+            perm = [o for o in self.new_order if o != "x"]
+            hh = h.transpose(perm + self.drop).reshape([h.shape[p] for p in perm]) if h.ndim else h
+            oshape = [1 if o == "x" else h.shape[o] for o in self.new_order]
+            out.h = hh.reshape(oshape)
+        return [out]
+
+
+class ViewNode(Node):
+    """Identity-like ops whose output is the input value (ViewOp, SpecifyShape, ScalarFromTensor, TensorFromScalar,
+    Rebroadcast...)."""
+
+    def __init__(self, name="View"):
+        self.name = name
+
+    def run(self, vals):
+        v = vals[0]
+        return [Val(h=v.h, d=v.d)]
+
+
+class DeepCopyNode(Node):
+    """Reference: DeepCopyOp, pytensor/compile/ops.py:121."""
+
+    name = "DeepCopyOp"
+
+    def run(self, vals):
+        v = vals[0]
+        if v.d is not None:
+            return [Val(d=dev.clone(v.d))]
+        return [Val(h=np.array(v.h, copy=True))]
+
+
+class ShapeINode(Node):
+    """Reference: Shape_i, pytensor/tensor/shape.py:201 — host-side int64 scalar, never a device value."""
+
+    def __init__(self, i):
+        self.i = i
+        self.name = f"Shape_i{{{i}}}"
+
+    def run(self, vals):
+        return [Val(h=np.asarray(vals[0].shape[self.i], dtype="int64"))]
+
+
+class ShapeNode(Node):
+    name = "Shape"
+
+    def run(self, vals):
+        return [Val(h=np.asarray(vals[0].shape, dtype="int64"))]
+
+
+class MakeVectorNode(Node):
+    """Reference: MakeVector, pytensor/tensor/basic.py:1900."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.name = "MakeVector"
+
+    def run(self, vals):
+        return [Val(h=np.asarray([np.asarray(v.host()).reshape(()) for v in vals], dtype=self.dtype).reshape(len(vals)))]
+
+
+class AllocEmptyNode(Node):
+    """Reference: AllocEmpty, pytensor/tensor/basic.py:4197 — contents undefined."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.name = "AllocEmpty"
+
+    def run(self, vals):
+        shape = [_host_int(v) for v in vals]
+        return [Val(d=dev.empty(shape, self.dtype))]
+
+
+def _broadcast_view(t: torch.Tensor, shape) -> torch.Tensor:
+    """View of `t` broadcast (0 strides) to `shape`, left-padding dims like NumPy."""
+    nd = len(shape)
+    pad = nd - t.dim()
+    if pad < 0:
+        raise ValueError("cannot broadcast to fewer dims")
+    strides = []
+    for i in range(nd):
+        if i < pad:
+            strides.append(0)
+        else:
+            ts = t.shape[i - pad]
+            if ts == shape[i]:
+                strides.append(t.stride(i - pad))
+            elif ts == 1:
+                strides.append(0)
+            else:
+                raise ValueError(f"cannot broadcast shape {tuple(t.shape)} to {tuple(shape)}")
+    return t.as_strided(tuple(shape), tuple(strides), t.storage_offset())
+
+
+class AllocNode(Node):
+    """Reference: Alloc, pytensor/tensor/basic.py:1545 — value broadcast into a fresh buffer."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.name = "Alloc"
+
+    def run(self, vals):
+        val = vals[0].dev()
+        shape = [_host_int(v) for v in vals[1:]]
+        out = dev.empty(shape, self.dtype)
+        if out.numel():
+            dev.copy_strided(out, _broadcast_view(val, shape))
+        return [Val(d=out)]
+
+
+class ReshapeNode(Node):
+    """Reference: Reshape, pytensor/tensor/shape.py:613 (view of a contiguous buffer, copy otherwise)."""
+
+    def __init__(self, ndim):
+        self.ndim = ndim
+        self.name = "Reshape"
+
+    def run(self, vals):
+        v = vals[0]
+        shp = [int(s) for s in np.asarray(vals[1].host()).reshape(-1)]
+        total = v.size
+        if -1 in shp:
+            known = 1
+            for s in shp:
+                if s != -1:
+                    known *= s
+            shp[shp.index(-1)] = total // known if known else 0
+        n = 1
+        for s in shp:
+            n *= s
+        if n != total:
+            raise ValueError(f"Reshape: cannot reshape array of size {total} into shape {tuple(shp)}")
+        if v.d is None:
+            return [Val(h=np.asarray(v.h).reshape(shp))]
+        t = dev.contiguous(v.d)
+        return [Val(d=t.view(shp))]
+
+
+# ---- basic indexing ---------------------------------------------------------------------------------------------------
+def _build_index(idx_template, index_vals):
+    """idx_template entries: int position | (start, stop, step) of None/int positions -> python index tuple."""
+    def get(p):
+        return None if p is None else _host_int(index_vals[p])
+
+    out = []
+    for e in idx_template:
+        if isinstance(e, tuple):
+            out.append(slice(get(e[0]), get(e[1]), get(e[2])))
+        else:
+            out.append(get(e))
+    return tuple(out)
+
+
+def _probe(shape, strides, index):
+    """NumPy-exact basic indexing on metadata only: returns (shape, strides, element offset) of x[index]."""
+    base = np.empty(1, dtype=np.int8)
+    if any(s == 0 for s in shape):
+        v = np.lib.stride_tricks.as_strided(base, shape=tuple(shape), strides=tuple(0 for _ in shape))
+        w = v[index]
+        return tuple(w.shape), tuple(0 for _ in w.shape), 0
+    v = np.lib.stride_tricks.as_strided(base, shape=tuple(shape), strides=tuple(int(s) for s in strides))
+    w = v[index]
+    off = w.__array_interface__["data"][0] - v.__array_interface__["data"][0]
+    return tuple(w.shape), tuple(w.strides), int(off)
+
+
+class _Region:
+    """A strided window into a device buffer that may carry negative strides (torch cannot express those)."""
+
+    def __init__(self, base: torch.Tensor, shape, strides, offset):
+        self.base, self.shape, self.strides, self.offset = base, tuple(shape), tuple(strides), offset
+
+    def as_tensor(self):
+        if all(s >= 0 for s in self.strides):
+            return self.base.as_strided(self.shape, self.strides, self.base.storage_offset() + self.offset)
+        return None
+
+    @property
+    def ptr(self):
+        return self.base.data_ptr() + self.offset * self.base.element_size()
+
+
+def _copy_region_out(reg: _Region, dtype) -> torch.Tensor:
+    out = torch.empty(reg.shape, dtype=reg.base.dtype, device=reg.base.device)
+    if out.numel():
+        L = _lib.lib()
+        _lib.check(L.ptk_copy_strided(dev.ptr(out), dev.i64_array(out.stride()), reg.ptr, dev.i64_array(reg.strides),
+                                      dev.i64_array(reg.shape), len(reg.shape), out.element_size(), dev.stream_ptr()),
+                   "ptk_copy_strided")
+    return out
+
+
+class SubtensorNode(Node):
+    """Reference: Subtensor, pytensor/tensor/subtensor.py:868 (a view; bit-exact by construction)."""
+
+    def __init__(self, idx_template, name="Subtensor"):
+        self.idx_template = idx_template
+        self.name = name
+
+    def run(self, vals):
+        v = vals[0]
+        index = _build_index(self.idx_template, vals[1:])
+        if v.d is None:
+            return [Val(h=np.asarray(v.h)[index])]
+        t = v.d
+        shape, strides, off = _probe(t.shape, t.stride(), index)
+        reg = _Region(t, shape, strides, off)
+        view = reg.as_tensor()
+        if view is None:
+            view = _copy_region_out(reg, t.dtype)
+        return [Val(d=view)]
+
+
+class IncSubtensorNode(Node):
+    """Reference: IncSubtensor, pytensor/tensor/subtensor.py:1441 (x[idx] += y or x[idx] = y; optional in place)."""
+
+    def __init__(self, idx_template, inplace, set_instead_of_inc, dtype, name="IncSubtensor"):
+        self.idx_template = idx_template
+        self.inplace = inplace
+        self.set_instead_of_inc = set_instead_of_inc
+        self.dtype = dtype
+        self.destroy = {0: 0} if inplace else {}
+        self.name = name
+
+    def run(self, vals):
+        x = vals[0].dev()
+        y = vals[1].dev()
+        index = _build_index(self.idx_template, vals[2:])
+        if not self.inplace:
+            x = dev.clone(x)
+        shape, strides, off = _probe(x.shape, x.stride(), index)
+        n = 1
+        for s in shape:
+            n *= s
+        if n:
+            yb = _broadcast_view(y, shape)
+            L = _lib.lib()
+            ptr = x.data_ptr() + off * x.element_size()
+            _lib.check(L.ptk_inc_strided(ptr, dev.i64_array(strides), dev.ptr(yb), dev.i64_array(yb.stride()),
+                                         dev.i64_array(shape), len(shape), _lib.DTYPE_CODE[self.dtype],
+                                         0 if self.set_instead_of_inc else 1, dev.stream_ptr()), "ptk_inc_strided")
+        return [Val(d=x)]
+
+
+# ---- advanced indexing: one integer index array on one axis, all other axes taken in full ------------------------------
+class TakeNode(Node):
+    """AdvancedSubtensor with the take-along-axis pattern (pytensor/tensor/subtensor.py:1932, `_take_axis` :1940)."""
+
+    def __init__(self, axis, name="AdvancedSubtensor"):
+        self.axis = axis
+        self.name = name
+        self._flag = None
+
+    def run(self, vals):
+        x = dev.contiguous(vals[0].dev())
+        idx = vals[1]
+        it = idx.dev()
+        if dev.TORCH_TO_NP[it.dtype] != "int64":
+            from .nodes_cast import cast_to  # local import to avoid a cycle
+            it = cast_to(it, "int64")
+        it = dev.contiguous(it)
+        ax = self.axis
+        outer = 1
+        for s in x.shape[:ax]:
+            outer *= s
+        inner = 1
+        for s in x.shape[ax + 1:]:
+            inner *= s
+        n_src = x.shape[ax]
+        oshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
+        out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+        if out.numel():
+            if n_src == 0:
+                raise IndexError("index out of bounds (taking from an empty axis)")
+            flag = _err_flag()
+            _lib.check(_lib.lib().ptk_take(dev.ptr(out), dev.ptr(x), dev.ptr(it), outer, n_src, it.numel(), inner,
+                                           x.element_size(), dev.ptr(flag), dev.stream_ptr()), "ptk_take")
+            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
+        return [Val(d=out)]
+
+
+class PutNode(Node):
+    """AdvancedIncSubtensor with the same single-axis pattern (pytensor/tensor/subtensor.py:2275): x[.., idx, ..] += y
+    (duplicates accumulate, np.add.at semantics :2513-2531) or = y."""
+
+    def __init__(self, axis, inplace, set_instead_of_inc, dtype, name="AdvancedIncSubtensor"):
+        self.axis = axis
+        self.inplace = inplace
+        self.set_instead_of_inc = set_instead_of_inc
+        self.dtype = dtype
+        self.destroy = {0: 0} if inplace else {}
+        self.name = name
+
+    def run(self, vals):
+        x = vals[0].dev()
+        if not self.inplace:
+            x = dev.clone(x)
+        elif not x.is_contiguous():
+            raise NotImplementedError(f"{self.name}: in-place scatter into a non-contiguous buffer")
+        x = x if x.is_contiguous() else dev.contiguous(x)
+        it = vals[2].dev()
+        if dev.TORCH_TO_NP[it.dtype] != "int64":
+            from .nodes_cast import cast_to
+            it = cast_to(it, "int64")
+        it = dev.contiguous(it)
+        ax = self.axis
+        outer = 1
+        for s in x.shape[:ax]:
+            outer *= s
+        inner = 1
+        for s in x.shape[ax + 1:]:
+            inner *= s
+        yshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
+        y = vals[1].dev()
+        yb = _broadcast_view(y, yshape)
+        yc = dev.contiguous(yb) if not yb.is_contiguous() else yb
+        n = 1
+        for s in yshape:
+            n *= s
+        if n:
+            flag = _err_flag()
+            _lib.check(_lib.lib().ptk_put(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, x.shape[ax], it.numel(), inner,
+                                          _lib.DTYPE_CODE[self.dtype], 0 if self.set_instead_of_inc else 1,
+                                          dev.ptr(flag), dev.stream_ptr()), "ptk_put")
+            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
+        return [Val(d=x)]
+
+
+# ---- deferred device-side error flags (checked by the VM at the end of a call, at its one sync point) -------------------
+_pending_flags: list = []
+
+
+def _err_flag() -> torch.Tensor:
+    t = torch.empty((1,), dtype=torch.int32, device=dev.device())
+    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(t), 0, 4, dev.stream_ptr()), "memset")
+    return t
+
+
+def check_pending_flags():
+    """Called by the VM after its end-of-call synchronisation; raises IndexError like the reference's C code."""
+    if not _pending_flags:
+        return
+    flags = list(_pending_flags)
+    _pending_flags.clear()
+    for flag, msg in flags:
+        if int(dev.to_host(flag)[0]) != 0:
+            raise IndexError(msg)
+
+
+class AssertNode(Node):
+    """Reference: Assert / CheckAndRaise, pytensor/raise_op.py:148 (view of input 0 when all conditions hold)."""
+
+    def __init__(self, msg, exc_name="AssertionError"):
+        self.msg = msg
+        self.exc_name = exc_name
+        self.name = "Assert"
+
+    def run(self, vals):
+        for c in vals[1:]:
+            if not bool(np.all(np.asarray(c.host()))):
+                exc = {"AssertionError": AssertionError, "ValueError": ValueError}.get(self.exc_name, AssertionError)
+                raise exc(self.msg)
+        v = vals[0]
+        return [Val(h=v.h, d=v.d)]
+
+
+class JoinNode(Node):
+    """Reference: Join, pytensor/tensor/basic.py:2405 (concatenate along the static `axis`)."""
+
+    def __init__(self, dtype, axis, name="Join"):
+        self.dtype = dtype
+        self.axis = axis
+        self.name = name
+
+    def run(self, vals):
+        axis = self.axis
+        parts = [v.dev() for v in vals]
+        nd = parts[0].dim()
+        axis %= nd
+        oshape = list(parts[0].shape)
+        oshape[axis] = sum(p.shape[axis] for p in parts)
+        out = dev.empty(oshape, self.dtype)
+        pos = 0
+        for p in parts:
+            n = p.shape[axis]
+            if p.numel():
+                dev.copy_strided(out.narrow(axis, pos, n), p)
+            pos += n
+        return [Val(d=out)]

@@ -1,0 +1,194 @@
+"""BLAS-family nodes (reference: pytensor/tensor/blas/gemm.py:76 Gemm, :248 Dot22, :298 Dot22Scalar,
+gemv.py:16 Gemv, ger.py:8 Ger, and the generic Dot of pytensor/tensor/math.py).  All arithmetic runs in
+ptk_gemm / ptk_gemv / ptk_ger; `precision` selects the bf16 tcgen05 tensor-core path for fp32 matrices."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..runtime import device as dev
+from ..runtime import lib as _lib
+from .nodes_basic import _broadcast_view
+from .nodes_elemwise import Node
+from .values import Val
+
+# Linker-level knob: 0 = native fp32/fp64 FMA (<= 1e-5 vs BLAS); 1 = bf16 operands / fp32 TMEM accumulation
+TC_MIN_DIM = 256
+
+_workspace = {"buf": None}
+
+
+def _get_workspace(nbytes: int):
+    buf = _workspace["buf"]
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev.device())
+        _workspace["buf"] = buf
+    return buf
+
+
+def _scalar(v: Val) -> float:
+    return float(np.asarray(v.host()).reshape(-1)[0])
+
+
+def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0):
+    """C = alpha*A@B + beta*C (or act(A@B + bias) when bias/act given) through the C-ABI."""
+    M, K = A.shape
+    K2, N = B.shape
+    if K != K2 or tuple(C.shape) != (M, N):
+        raise ValueError(f"gemm: shape mismatch {tuple(A.shape)} @ {tuple(B.shape)} -> {tuple(C.shape)}")
+    L = _lib.lib()
+    use_tc = precision == 1 and dtype == "float32" and min(M, N, K) >= TC_MIN_DIM
+    ws_ptr, ws_bytes = None, 0
+    if use_tc:
+        ws_bytes = int(L.ptk_gemm_workspace_bytes(M, N, K, 1))
+        ws = _get_workspace(ws_bytes)
+        ws_ptr = dev.ptr(ws)
+    code = _lib.DTYPE_CODE[dtype]
+    st = dev.stream_ptr()
+    if bias is not None or act:
+        _lib.check(L.ptk_gemm_bias_act(code, M, N, K, dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B), B.stride(0),
+                                       B.stride(1), dev.ptr(bias) if bias is not None else None, act, dev.ptr(C),
+                                       C.stride(0), C.stride(1), 1 if use_tc else 0, ws_ptr, ws_bytes, st),
+                   "ptk_gemm_bias_act")
+    else:
+        _lib.check(L.ptk_gemm(code, M, N, K, float(alpha), dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B),
+                              B.stride(0), B.stride(1), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
+                              1 if use_tc else 0, ws_ptr, ws_bytes, st), "ptk_gemm")
+
+
+def gemv(dtype, alpha, A, x, beta, y):
+    M, N = A.shape
+    if x.shape[0] != N or y.shape[0] != M:
+        raise ValueError(f"gemv: shape mismatch {tuple(A.shape)} @ {tuple(x.shape)} -> {tuple(y.shape)}")
+    _lib.check(_lib.lib().ptk_gemv(_lib.DTYPE_CODE[dtype], M, N, float(alpha), dev.ptr(A), A.stride(0), A.stride(1),
+                                   dev.ptr(x), x.stride(0), float(beta), dev.ptr(y), y.stride(0), dev.stream_ptr()),
+               "ptk_gemv")
+
+
+class Dot22Node(Node):
+    def __init__(self, dtype, precision=0, scalar=False, name="Dot22"):
+        self.dtype, self.precision, self.scalar, self.name = dtype, precision, scalar, name
+
+    def run(self, vals):
+        A, B = vals[0].dev(), vals[1].dev()
+        alpha = _scalar(vals[2]) if self.scalar else 1.0
+        out = dev.empty((A.shape[0], B.shape[1]), self.dtype)
+        if out.numel():
+            if A.shape[1] == 0:
+                _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(),
+                                                       dev.stream_ptr()), "memset")
+            else:
+                gemm(self.dtype, alpha, A, B, 0.0, out, self.precision)
+        return [Val(d=out)]
+
+
+class GemmNode(Node):
+    """z_out = b*z + a*x@y; in place on z when `inplace` (gemm.py:111-114), z broadcast otherwise (:194-198)."""
+
+    def __init__(self, dtype, inplace, precision=0, name="Gemm"):
+        self.dtype, self.inplace, self.precision, self.name = dtype, inplace, precision, name
+        self.destroy = {0: 0} if inplace else {}
+
+    def run(self, vals):
+        z, a, x, y, b = vals
+        X, Y = x.dev(), y.dev()
+        alpha, beta = _scalar(a), _scalar(b)
+        Z = z.dev()
+        M, N = X.shape[0], Y.shape[1]
+        if self.inplace and tuple(Z.shape) == (M, N):
+            out = Z
+        else:
+            out = dev.empty((M, N), self.dtype)
+            if out.numel() and beta != 0.0:
+                dev.copy_strided(out, _broadcast_view(Z, (M, N)))
+        if out.numel():
+            if X.shape[1] == 0:
+                if beta == 0.0:
+                    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(),
+                                                           dev.stream_ptr()), "memset")
+                else:
+                    gemm(self.dtype, 0.0, out[:, :1], out[:1, :], beta, out, 0)
+            else:
+                gemm(self.dtype, alpha, X, Y, beta, out, self.precision)
+        return [Val(d=out)]
+
+
+class GemvNode(Node):
+    """y_out = beta*y + alpha*A@x; beta == 0 never reads y (gemv.py:79-86)."""
+
+    def __init__(self, dtype, inplace, name="Gemv"):
+        self.dtype, self.inplace, self.name = dtype, inplace, name
+        self.destroy = {0: 0} if inplace else {}
+
+    def run(self, vals):
+        y, alpha, A, x, beta = vals
+        Y, Am, X = y.dev(), A.dev(), x.dev()
+        al, be = _scalar(alpha), _scalar(beta)
+        out = Y if self.inplace else (dev.clone(Y) if be != 0.0 else dev.empty(tuple(Y.shape), self.dtype))
+        if out.numel():
+            if Am.shape[1] == 0:
+                al = 0.0
+                Am = out.as_strided((out.shape[0], 1), (out.stride(0), 1), out.storage_offset())
+                X = out[:1]
+                if be == 0.0:
+                    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(),
+                                                           dev.stream_ptr()), "memset")
+                    return [Val(d=out)]
+            gemv(self.dtype, al, Am, X, be, out)
+        return [Val(d=out)]
+
+
+class GerNode(Node):
+    """A_out = A + alpha * outer(x, y) (ger.py:8)."""
+
+    def __init__(self, dtype, inplace, name="Ger"):
+        self.dtype, self.inplace, self.name = dtype, inplace, name
+        self.destroy = {0: 0} if inplace else {}
+
+    def run(self, vals):
+        A, alpha, x, y = vals
+        Am = A.dev() if self.inplace else dev.clone(A.dev())
+        X, Y = x.dev(), y.dev()
+        if Am.numel():
+            _lib.check(_lib.lib().ptk_ger(_lib.DTYPE_CODE[self.dtype], Am.shape[0], Am.shape[1], _scalar(alpha),
+                                          dev.ptr(X), X.stride(0), dev.ptr(Y), Y.stride(0), dev.ptr(Am), Am.stride(0),
+                                          Am.stride(1), dev.stream_ptr()), "ptk_ger")
+        return [Val(d=Am)]
+
+
+class DotNode(Node):
+    """Generic Dot for float vectors/matrices that the BLAS rewrites left alone (1-d x 1-d, etc.)."""
+
+    def __init__(self, dtype, precision=0, name="Dot"):
+        self.dtype, self.precision, self.name = dtype, precision, name
+
+    def run(self, vals):
+        A, B = vals[0].dev(), vals[1].dev()
+        if A.dim() == 2 and B.dim() == 2:
+            return Dot22Node(self.dtype, self.precision).run(vals)
+        if A.dim() == 2 and B.dim() == 1:
+            out = dev.empty((A.shape[0],), self.dtype)
+            if out.numel():
+                if A.shape[1] == 0:
+                    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(), dev.stream_ptr()), "memset")
+                else:
+                    gemv(self.dtype, 1.0, A, B, 0.0, out)
+            return [Val(d=out)]
+        if A.dim() == 1 and B.dim() == 2:
+            out = dev.empty((B.shape[1],), self.dtype)
+            if out.numel():
+                if B.shape[0] == 0:
+                    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(), dev.stream_ptr()), "memset")
+                else:
+                    gemv(self.dtype, 1.0, B.t(), A, 0.0, out)
+            return [Val(d=out)]
+        if A.dim() == 1 and B.dim() == 1:
+            out = dev.empty((1,), self.dtype)
+            if A.shape[0] == 0:
+                _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.element_size(), dev.stream_ptr()), "memset")
+            else:
+                Am = A.as_strided((1, A.shape[0]), (A.shape[0] * max(1, A.stride(0)), A.stride(0)), A.storage_offset())
+                gemv(self.dtype, 1.0, Am, B, 0.0, out)
+            return [Val(d=out.view(()))]
+        raise NotImplementedError(f"Dot with ndims {A.dim()},{B.dim()}")

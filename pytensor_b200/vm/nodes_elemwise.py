@@ -1,0 +1,459 @@
+"""Executable nodes for the Elemwise / CAReduce family (reference: pytensor/tensor/elemwise.py:375 Elemwise,
+:1233 CAReduce).  Plain data + launch logic; no pytensor import, so a lowered program can be pickled and run on a box
+that only has torch + libptk.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_longlong, c_uint, c_void_p
+
+import numpy as np
+
+from ..codegen import careduce as cg_red
+from ..codegen import elemwise as cg_ew
+from ..codegen.scalar import ITEMSIZE, ScalarProgram, is_float
+from ..runtime import device as dev
+from ..runtime import jit
+from ..runtime import lib as _lib
+from .values import Val
+
+_uid = [0]
+
+
+def _kname(prefix: str) -> str:
+    _uid[0] += 1
+    return f"{prefix}_{_uid[0]}"
+
+
+class Node:
+    """Base of all executable nodes. `run(vals) -> list[Val]`."""
+
+    n_out = 1
+    name = "node"
+    destroy = {}  # out_idx -> in_idx (the output reuses that input's buffer)
+
+    def run(self, vals):
+        raise NotImplementedError
+
+    def __repr__(self):
+        return f"<{type(self).__name__} {self.name}>"
+
+
+def _collapse(shape, strides_list):
+    """Merge adjacent dims that are mergeable for EVERY operand. Returns (shape, strides_list)."""
+    nd = len(shape)
+    keep = [i for i in range(nd) if shape[i] != 1]
+    if not keep:
+        return [1], [[0] for _ in strides_list]
+    shp = [shape[keep[0]]]
+    sts = [[st[keep[0]]] for st in strides_list]
+    for i in keep[1:]:
+        ok = all(st_acc[-1] == st[i] * shape[i] for st_acc, st in zip(sts, strides_list))
+        if ok:
+            shp[-1] *= shape[i]
+            for st_acc, st in zip(sts, strides_list):
+                st_acc[-1] = st[i]
+        else:
+            shp.append(shape[i])
+            for st_acc, st in zip(sts, strides_list):
+                st_acc.append(st[i])
+    return shp, sts
+
+
+def _dense_order(t):
+    """Permutation (slowest dim first) if `t` is a dense permuted buffer, else None."""
+    nd = t.dim()
+    if nd <= 1:
+        return None
+    order = sorted(range(nd), key=lambda i: (-t.stride(i), i))
+    expect = 1
+    for i in reversed(order):
+        if t.shape[i] != 1 and t.stride(i) != expect:
+            return None
+        expect *= t.shape[i]
+    return order
+
+
+def host_eval_program(prog: ScalarProgram, inputs):
+    """Evaluate an integer/bool ScalarProgram on host arrays (shape arithmetic only — see vm/values.py)."""
+    def ref(r):
+        k, i = r
+        if k == "i":
+            return inputs[i]
+        if k == "c":
+            d, v = prog.consts[i]
+            return np.asarray(v, dtype=d)
+        return tmp[i]
+
+    tmp = []
+    for inst in prog.insts:
+        a = [np.asarray(ref(r)) for r in inst.args]
+        op, od = inst.op, inst.out_dtype
+        if op == "Add":
+            r = a[0]
+            for x in a[1:]:
+                r = r + x
+        elif op == "Mul":
+            r = a[0]
+            for x in a[1:]:
+                r = r * x
+        elif op == "Sub":
+            r = a[0] - a[1]
+        elif op == "Neg":
+            r = -a[0]
+        elif op == "Abs":
+            r = np.abs(a[0])
+        elif op == "IntDiv":
+            r = np.floor_divide(a[0], np.where(a[1] == 0, 1, a[1]))
+        elif op == "Mod":
+            r = np.mod(a[0], np.where(a[1] == 0, 1, a[1]))
+        elif op == "Maximum":
+            r = np.maximum(a[0], a[1])
+        elif op == "Minimum":
+            r = np.minimum(a[0], a[1])
+        elif op in ("Cast", "Identity"):
+            r = a[0]
+        elif op == "Second":
+            r = np.broadcast_to(a[1], np.broadcast(a[0], a[1]).shape)
+        elif op == "Switch":
+            r = np.where(a[0], a[1], a[2])
+        elif op == "Sqr":
+            r = a[0] * a[0]
+        elif op == "Sign":
+            r = np.sign(a[0])
+        elif op in ("LT", "GT", "LE", "GE", "EQ", "NEQ"):
+            r = {"LT": np.less, "GT": np.greater, "LE": np.less_equal, "GE": np.greater_equal, "EQ": np.equal,
+                 "NEQ": np.not_equal}[op](a[0], a[1])
+        elif op in ("AND", "OR", "XOR"):
+            r = {"AND": np.bitwise_and, "OR": np.bitwise_or, "XOR": np.bitwise_xor}[op](a[0], a[1])
+        elif op == "Invert":
+            r = np.invert(a[0])
+        elif op == "TrueDiv" and is_float(od):
+            r = np.true_divide(a[0], a[1])
+        elif op in ("Ceil", "Floor", "Trunc", "RoundHalfToEven"):
+            r = {"Ceil": np.ceil, "Floor": np.floor, "Trunc": np.trunc, "RoundHalfToEven": np.rint}[op](a[0])
+        else:
+            return None
+        tmp.append(np.asarray(r).astype(od))
+    return [np.asarray(ref(r)).astype(d) for r, d in zip(prog.outputs, prog.out_dtypes)]
+
+
+class ElemwiseNode(Node):
+    """One fused elementwise kernel: n_in broadcast operands -> n_out results (Elemwise with a Composite or a
+    single ScalarOp; pytensor/tensor/elemwise.py:375).  `in_bcast[k][d]` is the STATIC broadcast pattern: a runtime
+    length-1 dim that is not typed broadcastable is an error (elemwise.py:825-840)."""
+
+    HOST_MAX = 64
+
+    def __init__(self, prog: ScalarProgram, ndim: int, in_bcast, inplace: dict, name="Elemwise"):
+        self.prog = prog
+        self.ndim = ndim
+        self.in_bcast = [tuple(b) for b in in_bcast]
+        self.inplace = dict(inplace)
+        self.destroy = dict(inplace)
+        self.n_in = len(prog.in_dtypes)
+        self.n_out = len(prog.out_dtypes)
+        self.name = name
+        self._kernels = {}
+        self._host_ok = all((not is_float(d)) for d in list(prog.in_dtypes) + list(prog.out_dtypes))
+
+    # -- shape logic -------------------------------------------------------------------------------------------------
+    def _out_shape(self, shapes):
+        out = []
+        for d in range(self.ndim):
+            s = None
+            for k, shp in enumerate(shapes):
+                if self.in_bcast[k][d]:
+                    if shp[d] != 1:
+                        raise ValueError(f"{self.name}: input {k} is typed broadcastable in dim {d} but has length {shp[d]}")
+                    continue
+                if s is None:
+                    s = shp[d]
+                elif shp[d] != s:
+                    raise ValueError(
+                        f"{self.name}: input dimension mismatch in dim {d}: {s} vs {shp[d]} (input {k}); "
+                        "runtime broadcasting of a non-broadcastable dim is not allowed"
+                    )
+            out.append(1 if s is None else int(s))
+        return out
+
+    def run(self, vals):
+        if self._host_ok and all(v.d is None for v in vals):
+            shapes = [v.shape for v in vals]
+            oshape = self._out_shape(shapes)
+            if int(np.prod(oshape, dtype=np.int64)) <= self.HOST_MAX:
+                res = host_eval_program(self.prog, [np.asarray(v.h) for v in vals])
+                if res is not None:
+                    return [Val(h=np.broadcast_to(r, oshape).copy() if tuple(np.shape(r)) != tuple(oshape) else r)
+                            for r in res]
+        oshape = self._out_shape([v.shape for v in vals])  # shape errors surface before any transfer
+        ins = [v.dev() for v in vals]
+        # output layout follows a dense full-shape input (elemwise.py:935-961) so that the pair collapses together
+        order = None
+        for k, t in enumerate(ins):
+            if tuple(t.shape) == tuple(oshape) and not any(self.in_bcast[k]):
+                order = _dense_order(t)
+                break
+        outs = []
+        for k, dt in enumerate(self.prog.out_dtypes):
+            if k in self.inplace:
+                outs.append(ins[self.inplace[k]])
+            else:
+                outs.append(dev.empty_like_layout(oshape, dt, order))
+        total = 1
+        for s in oshape:
+            total *= s
+        if total == 0:
+            return [Val(d=o) for o in outs]
+        self._launch(ins, outs, oshape)
+        return [Val(d=o) for o in outs]
+
+    # -- launch --------------------------------------------------------------------------------------------------------
+    def _launch(self, ins, outs, oshape):
+        nd = self.ndim
+        ops = ins + outs
+        strides = []
+        for k, t in enumerate(ins):
+            strides.append([0 if (self.in_bcast[k][d] or t.shape[d] == 1 and oshape[d] != 1) else t.stride(d)
+                            for d in range(nd)])
+        for t in outs:
+            strides.append([t.stride(d) for d in range(nd)])
+        # iterate in the memory order of the first output
+        perm = sorted(range(nd), key=lambda i: (-outs[0].stride(i), i)) if nd > 1 else list(range(nd))
+        shp = [oshape[i] for i in perm]
+        sts = [[st[i] for i in perm] for st in strides]
+        cshape, csts = _collapse(shp, sts)
+        stream = dev.stream_ptr()
+        total = 1
+        for s in cshape:
+            total *= s
+        dtypes = list(self.prog.in_dtypes) + list(self.prog.out_dtypes)
+        vw = cg_ew.vec_width(dtypes)
+        if len(cshape) <= 2 and self._vec_ok(ops, dtypes, cshape, csts, vw):
+            rows = cshape[0] if len(cshape) == 2 else 1
+            cols = cshape[-1]
+            col_modes = tuple(1 if st[-1] == 1 else 0 for st in csts)
+            key = ("vec", col_modes, vw)
+            fn = self._kernels.get(key)
+            if fn is None:
+                fn, _ = jit.get_function_gen(
+                    lambda kn: cg_ew.gen_vec_kernel(self.prog, kn, col_modes, self.inplace, vw), "ptk_ew_vec")
+                self._kernels[key] = fn
+            cpr_chunks = cols // vw
+            nchunks = rows * cpr_chunks
+            tail_start = cpr_chunks * vw if rows == 1 else cols
+            n_total = cols if rows == 1 else cols  # tail loop is a no-op for rows > 1 (cols % vw == 0 enforced)
+            args = [c_void_p(dev.ptr(t)) for t in ops]
+            args += [c_longlong(st[0] if len(cshape) == 2 else 0) for st in csts]
+            args += [c_longlong(nchunks), c_uint(cpr_chunks if rows > 1 else 0), c_longlong(tail_start),
+                     c_longlong(n_total)]
+            per_block = 256 * cg_ew.VEC_UNROLL
+            want = max(1, (max(nchunks, n_total - tail_start) + per_block - 1) // per_block)
+            grid = min(want, _lib.sm_count() * 8)
+            jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, stream)
+            return
+        if len(cshape) > cg_ew.MAX_DIMS:
+            raise NotImplementedError(f"{self.name}: more than {cg_ew.MAX_DIMS} non-collapsible dims")
+        key = ("gen",)
+        fn = self._kernels.get(key)
+        nops = len(ops)
+        if fn is None:
+            if nops > 48:
+                raise NotImplementedError(f"{self.name}: {nops} strided operands exceed the by-value descriptor")
+            fn, _ = jit.get_function_gen(lambda kn: cg_ew.gen_generic_kernel(self.prog, kn, self.inplace), "ptk_ew_gen")
+            self._kernels[key] = fn
+
+        class EwDims(ctypes.Structure):
+            _fields_ = [("ndim", c_int), ("shape", c_longlong * cg_ew.MAX_DIMS),
+                        ("st", (c_longlong * cg_ew.MAX_DIMS) * nops)]
+
+        d = EwDims()
+        d.ndim = len(cshape)
+        for i, s in enumerate(cshape):
+            d.shape[i] = s
+        for j, st in enumerate(csts):
+            for i, s in enumerate(st):
+                d.st[j][i] = s
+        args = [c_void_p(dev.ptr(t)) for t in ops] + [d, c_longlong(total)]
+        grid = min(max(1, (total + 255) // 256), _lib.sm_count() * 16)
+        jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, stream)
+
+    @staticmethod
+    def _vec_ok(ops, dtypes, cshape, csts, vw):
+        two_d = len(cshape) == 2
+        cols = cshape[-1]
+        if two_d and cols % vw != 0:
+            return False
+        for t, dt, st in zip(ops, dtypes, csts):
+            inner = st[-1]
+            if inner not in (0, 1):
+                return False
+            if inner == 1:
+                if dev.ptr(t) % (ITEMSIZE[dt] * vw) != 0:
+                    return False
+                if two_d and st[0] % vw != 0:
+                    return False
+        if not two_d and cols < vw:
+            return True  # pure tail loop
+        return True
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class CAReduceNode(Node):
+    """Reduction over `axes` with a commutative-associative scalar op (pytensor/tensor/elemwise.py:1233).
+    acc_dtype / out_dtype follow `_acc_dtype` / `_output_dtype` (:1352-1417)."""
+
+    def __init__(self, red_op: str, axes, ndim: int, in_dtype: str, acc_dtype: str, out_dtype: str, identity,
+                 name="CAReduce"):
+        self.red_op = red_op
+        self.axes = tuple(sorted(range(ndim) if axes is None else [a % ndim for a in axes])) if ndim else ()
+        self.ndim = ndim
+        self.in_dtype = in_dtype
+        self.acc_dtype = acc_dtype
+        self.out_dtype = out_dtype
+        self.identity = identity
+        self.name = name
+        self._kernels = {}
+
+    def _fn(self, key, gen):
+        fn = self._kernels.get(key)
+        if fn is None:
+            fn, _ = jit.get_function_gen(gen, "ptk_red_" + key[0])
+            self._kernels[key] = fn
+        return fn
+
+    def _fill_identity(self, out):
+        src = dev.to_device(np.asarray(self.identity, dtype=self.out_dtype).reshape(()))
+        dev.copy_strided(out, src.as_strided(tuple(out.shape), (0,) * out.dim()))
+
+    def run(self, vals):
+        t = vals[0].dev()
+        shape = tuple(t.shape)
+        kept = [i for i in range(self.ndim) if i not in self.axes]
+        oshape = [shape[i] for i in kept]
+        out = dev.empty(oshape, self.out_dtype)
+        n_out = 1
+        for s in oshape:
+            n_out *= s
+        n_red = 1
+        for a in self.axes:
+            n_red *= shape[a]
+        if n_out == 0:
+            return [Val(d=out)]
+        if n_red == 0:
+            self._fill_identity(out)
+            return [Val(d=out)]
+        if not self.axes:  # nothing to reduce: a dtype-casting copy
+            self._generic(t, out, kept, n_out, 1)
+            return [Val(d=out)]
+        tc = dev.contiguous(t)
+        # group dims of the contiguous input into alternating kept / reduced runs
+        groups = []  # (is_red, size)
+        for i in range(self.ndim):
+            if shape[i] == 1:
+                continue
+            r = i in self.axes
+            if groups and groups[-1][0] == r:
+                groups[-1] = (r, groups[-1][1] * shape[i])
+            else:
+                groups.append((r, shape[i]))
+        pattern = tuple(g[0] for g in groups)
+        sizes = [g[1] for g in groups]
+        if pattern in ((True,), ()):
+            self._row(tc, out, 1, n_red)
+        elif pattern == (False, True):
+            self._row(tc, out, sizes[0], sizes[1])
+        elif pattern == (True, False):
+            self._col(tc, out, 1, sizes[0], sizes[1])
+        elif pattern == (False, True, False):
+            self._col(tc, out, sizes[0], sizes[1], sizes[2])
+        elif pattern == (False,):
+            self._generic(t, out, kept, n_out, 1)
+        else:
+            self._generic(t, out, kept, n_out, n_red)
+        return [Val(d=out)]
+
+    # -- kernels -------------------------------------------------------------------------------------------------------
+    def _row(self, tc, out, rows, cols):
+        stream = dev.stream_ptr()
+        sms = _lib.sm_count()
+        isz = ITEMSIZE[self.in_dtype]
+        vw = 4 if isz >= 4 else (8 if isz == 2 else 16)
+        if dev.ptr(tc) % (isz * vw) != 0 or (rows > 1 and cols % vw != 0):
+            vw = 1
+        tpr = 256 if cols >= 2048 else 32
+        rows_per_block = 256 // tpr
+        row_blocks = (rows + rows_per_block - 1) // rows_per_block
+        nsplit = 1
+        ncv = cols // vw
+        if row_blocks < sms * 2 and ncv >= tpr * 16:
+            nsplit = int(min((sms * 4 + row_blocks - 1) // row_blocks, max(1, ncv // (tpr * 8)), 1024))
+        prog = cg_red.identity_program(self.in_dtype)
+        key = ("row", vw, tpr)
+        fn = self._fn(key, lambda kn: cg_red.gen_row_kernel(prog, kn, (1,), (False,), self.red_op, self.acc_dtype,
+                                                              self.out_dtype, self.identity, vw, tpr))
+        gx = min(row_blocks, sms * 32)
+        if nsplit == 1:
+            args = [c_void_p(dev.ptr(tc)), c_void_p(dev.ptr(out)), c_longlong(cols), c_longlong(rows),
+                    c_longlong(cols), c_int(1)]
+            jit.launch(fn, (gx, 1), (256,), jit.KernelArgs(args), 0, stream)
+            return
+        part = dev.empty((rows, nsplit), self.acc_dtype)
+        args = [c_void_p(dev.ptr(tc)), c_void_p(dev.ptr(part)), c_longlong(cols), c_longlong(rows), c_longlong(cols),
+                c_int(nsplit)]
+        jit.launch(fn, (gx, nsplit), (256,), jit.KernelArgs(args), 0, stream)
+        self._finish(part, out, rows, nsplit, nsplit, 1)
+
+    def _finish(self, part, out, n_out, nsplit, stride_o, stride_s):
+        fn = self._fn(("finish",), lambda kn: cg_red.gen_finish_kernel(kn, self.red_op, self.acc_dtype,
+                                                                        self.out_dtype, self.identity))
+        args = [c_void_p(dev.ptr(part)), c_void_p(dev.ptr(out)), c_longlong(n_out), c_int(nsplit),
+                c_longlong(stride_o), c_longlong(stride_s)]
+        grid = min(max(1, (n_out + 7) // 8), _lib.sm_count() * 16)
+        jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())
+
+    def _col(self, tc, out, outer, red, inner):
+        stream = dev.stream_ptr()
+        sms = _lib.sm_count()
+        fn = self._fn(("col",), lambda kn: cg_red.gen_col_kernel(kn, self.in_dtype, self.red_op, self.acc_dtype,
+                                                                  self.out_dtype, self.identity))
+        gx = (inner + 255) // 256
+        gy = min(outer, 65535)
+        nsplit = 1
+        if gx * gy < sms * 2 and red >= 64:
+            nsplit = int(min((sms * 4 + gx * gy - 1) // (gx * gy), red // 16, 65535))
+            nsplit = max(nsplit, 1)
+        if nsplit == 1:
+            args = [c_void_p(dev.ptr(tc)), c_void_p(dev.ptr(out)), c_longlong(outer), c_longlong(red),
+                    c_longlong(inner), c_int(1)]
+            jit.launch(fn, (gx, gy, 1), (256,), jit.KernelArgs(args), 0, stream)
+            return
+        part = dev.empty((nsplit, outer, inner), self.acc_dtype)
+        args = [c_void_p(dev.ptr(tc)), c_void_p(dev.ptr(part)), c_longlong(outer), c_longlong(red), c_longlong(inner),
+                c_int(nsplit)]
+        jit.launch(fn, (gx, gy, nsplit), (256,), jit.KernelArgs(args), 0, stream)
+        self._finish(part, out, outer * inner, nsplit, 1, outer * inner)
+
+    def _generic(self, t, out, kept, n_out, n_red):
+        MAXD = cg_ew.MAX_DIMS
+
+        class RdDims(ctypes.Structure):
+            _fields_ = [("nk", c_int), ("nr", c_int), ("kshape", c_longlong * MAXD), ("kst", c_longlong * MAXD),
+                        ("rshape", c_longlong * MAXD), ("rst", c_longlong * MAXD)]
+
+        red_axes = [a for a in self.axes]
+        if len(kept) > MAXD or len(red_axes) > MAXD:
+            raise NotImplementedError("CAReduce over more than 8 kept or reduced dims")
+        d = RdDims()
+        d.nk, d.nr = len(kept), len(red_axes)
+        for i, a in enumerate(kept):
+            d.kshape[i], d.kst[i] = t.shape[a], t.stride(a)
+        for i, a in enumerate(red_axes):
+            d.rshape[i], d.rst[i] = t.shape[a], t.stride(a)
+        fn = self._fn(("generic",), lambda kn: cg_red.gen_generic_kernel(kn, self.in_dtype, self.red_op,
+                                                                          self.acc_dtype, self.out_dtype,
+                                                                          self.identity))
+        args = [c_void_p(dev.ptr(t)), c_void_p(dev.ptr(out)), d, c_longlong(n_out), c_longlong(n_red)]
+        grid = min(max(1, (n_out + 255) // 256), _lib.sm_count() * 16)
+        jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())

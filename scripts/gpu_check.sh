@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# One gpurun call: parity tests, smoke, bench, ncu launch list. Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+( time timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -q -m gpu -x ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+( timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
+tail -2 gpurun_out/smoke.log
+( timeout 600 python bench.py --steps 30 --warmup 5 ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+tail -c 3000 gpurun_out/bench.json
+if [ "${NCU:-1}" = "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptk_ew_vec -s 4 -c 2 -o gpurun_out/prof_ew -f \
+     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+fi
+echo done

@@ -1,0 +1,44 @@
+"""Backend test idiom of the reference (tests/link/pytorch/test_basic.py:43-87 `compare_pytorch_and_py`): compile the
+same graph with the backend mode and with the oracle mode, assert closeness.  Here the oracle is the reference's C
+linker (`mode="CVM"`), as BASELINE.json's north_star demands."""
+
+import os
+
+import numpy as np
+
+from oracle import cvm
+
+pytensor = cvm.configure()
+import pytensor_b200  # noqa: E402,F401  (registers mode="CUDA")
+
+
+def tol_for(dtype):
+    # the reference's own notion of "close" (pytensor/tensor/math.py:92-103): fp32 1e-5, fp64 rtol 1e-5
+    return dict(rtol=1e-5, atol=1e-5) if np.dtype(dtype) == np.float32 else dict(rtol=1e-5, atol=1e-8)
+
+
+def compare_cuda_and_cvm(inputs, outputs, test_inputs, mode="CUDA", rtol=None, atol=None, exact=False, cvm_kwargs=None):
+    single = not isinstance(outputs, list | tuple)
+    outs = [outputs] if single else list(outputs)
+    f_cuda = pytensor.function(inputs, outs, mode=mode)
+    f_ref = pytensor.function(inputs, outs, mode="CVM", **(cvm_kwargs or {}))
+    if os.environ.get("PTK_DRY") == "1":  # developer dry run without a GPU: lowering + reference only
+        from pytensor_b200.precompile import trace_function
+
+        f_ref(*[np.array(x, copy=True) for x in test_inputs])
+        trace_function(f_cuda, [np.array(x, copy=True) for x in test_inputs])  # launch logic + NVRTC, no device
+        return f_cuda, None
+    got = f_cuda(*[np.array(x, copy=True) for x in test_inputs])
+    exp = f_ref(*[np.array(x, copy=True) for x in test_inputs])
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        g, e = np.asarray(g), np.asarray(e)
+        assert g.dtype == e.dtype, (g.dtype, e.dtype)
+        assert g.shape == e.shape, (g.shape, e.shape)
+        if exact or e.dtype.kind in "biu":
+            np.testing.assert_array_equal(g, e)
+        else:
+            t = tol_for(e.dtype)
+            np.testing.assert_allclose(g, e, rtol=rtol if rtol is not None else t["rtol"],
+                                       atol=atol if atol is not None else t["atol"], equal_nan=True)
+    return f_cuda, got

@@ -1,0 +1,89 @@
+"""Parity of the native-precision BLAS family (K4/K6 fp32/fp64 paths) vs the C linker — alpha/beta grid and
+layouts after the reference's TestGemm (tests/tensor/test_blas.py:94-191, :286-404) and BaseGemv (:1412-1620)."""
+
+import numpy as np
+import pytest
+
+from helpers import compare_cuda_and_cvm, pytensor
+
+import pytensor.tensor as pt
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_graph(gpu):
+    # BASELINE.json configs[0]: a/a + (M+a).dot(v), fp64 (README.rst:38-61)
+    a = pt.dscalar("a")
+    v = pt.dvector("v")
+    M = pt.dmatrix("M")
+    d = a / a + (M + a).dot(v)
+    rng = np.random.default_rng(0)
+    f, _ = compare_cuda_and_cvm([a, v, M], [d], [1.5, np.ones(1024), rng.standard_normal((1024, 1024))])
+    names = [type(n.op).__name__ for n in f.maker.fgraph.toposort()]
+    assert "Gemv" in names
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shapes", [((4, 5), (5, 3)), ((64, 64), (64, 64)), ((130, 70), (70, 257)), ((1, 9), (9, 1)),
+                                    ((300, 1), (1, 200)), ((0, 4), (4, 5)), ((3, 0), (0, 5))])
+def test_dot22(gpu, dtype, shapes):
+    rng = np.random.default_rng(21)
+    x = pt.tensor("x", dtype=dtype, shape=(None, None))
+    y = pt.tensor("y", dtype=dtype, shape=(None, None))
+    xv = rng.standard_normal(shapes[0]).astype(dtype)
+    yv = rng.standard_normal(shapes[1]).astype(dtype)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "float32" else {}
+    compare_cuda_and_cvm([x, y], [pt.dot(x, y), pt.dot(x, y) * 0.6], [xv, yv], **tol)
+
+
+@pytest.mark.parametrize("a,b", [(1.0, 1.0), (0.6, 0.0), (-1.0, 0.6), (0.0, 1.0), (0.6, -1.0)])
+def test_gemm_alpha_beta(gpu, a, b):
+    rng = np.random.default_rng(22)
+    z = pt.dmatrix("z")
+    x = pt.dmatrix("x")
+    y = pt.dmatrix("y")
+    zv, xv, yv = rng.standard_normal((33, 47)), rng.standard_normal((33, 29)), rng.standard_normal((29, 47))
+    f, _ = compare_cuda_and_cvm([z, x, y], [b * z + a * pt.dot(x, y)], [zv, xv, yv])
+
+
+def test_gemm_transposed_operands(gpu):
+    rng = np.random.default_rng(23)
+    x = pt.fmatrix("x")
+    y = pt.fmatrix("y")
+    xv = rng.standard_normal((65, 129)).astype("float32")
+    yv = rng.standard_normal((65, 77)).astype("float32")
+    compare_cuda_and_cvm([x, y], [pt.dot(x.T, y), pt.dot(y.T, x), pt.dot(x.T[::2], y[:, ::3])], [xv, yv], rtol=1e-4,
+                         atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_gemv_variants(gpu, dtype):
+    rng = np.random.default_rng(24)
+    A = pt.tensor("A", dtype=dtype, shape=(None, None))
+    x = pt.tensor("x", dtype=dtype, shape=(None,))
+    y = pt.tensor("y", dtype=dtype, shape=(None,))
+    Av = rng.standard_normal((70, 1300)).astype(dtype)
+    xv = rng.standard_normal(1300).astype(dtype)
+    yv = rng.standard_normal(70).astype(dtype)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "float32" else {}
+    compare_cuda_and_cvm([A, x, y], [pt.dot(A, x), y + 0.5 * pt.dot(A, x), pt.dot(A.T, y), pt.dot(x, A.T),
+                                     pt.dot(x, x)], [Av, xv, yv], **tol)
+
+
+def test_tall_skinny_gemv_transposed(gpu):
+    # cfg-5 secondary shape: X (N,8)^T @ r
+    rng = np.random.default_rng(25)
+    X = pt.dmatrix("X")
+    r = pt.dvector("r")
+    Xv = rng.standard_normal((1 << 16, 8))
+    rv = rng.standard_normal(1 << 16)
+    compare_cuda_and_cvm([X, r], [pt.dot(X.T, r), pt.dot(X, X.T[:, 0])], [Xv, rv], rtol=1e-9)
+
+
+def test_ger(gpu):
+    rng = np.random.default_rng(26)
+    A = pt.dmatrix("A")
+    x = pt.dvector("x")
+    y = pt.dvector("y")
+    compare_cuda_and_cvm([A, x, y], [A + 0.3 * pt.outer(x, y)],
+                         [rng.standard_normal((40, 50)), rng.standard_normal(40), rng.standard_normal(50)])
