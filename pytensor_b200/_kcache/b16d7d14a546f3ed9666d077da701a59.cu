@@ -1,0 +1,52 @@
+
+// ---- ptk scalar helpers (Python floor-division / modulo semantics of IntDiv / Mod) ----
+template <typename T> __device__ __forceinline__ T ptk_floordiv(T x, T y) {
+  if (y == 0) return 0;
+  T q = x / y;
+  if ((x % y != 0) && ((x < 0) != (y < 0))) --q;
+  return q;
+}
+template <typename T> __device__ __forceinline__ T ptk_imod_py(T x, T y) {
+  if (y == 0) return 0;
+  T r = x % y;
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+template <typename T> __device__ __forceinline__ T ptk_fmod_py(T x, T y) {
+  if (y == 0) return x - x + (T)__int_as_float(0x7fc00000);
+  T r = fmod(x, y);
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+
+__device__ __forceinline__ void ptk_body(const float i0, const float i1, float& o0) {
+  const float t0 = (float)(((i0) * (i1)));
+  const float t1 = (float)(((0x1.99999a0000000p-4f) + (t0)));
+  const float t2 = (float)(tanh((float)(t1)));
+  o0 = (float)(t2);
+}
+struct ScDims { int ndim; long long shape[8]; long long st[2][8]; long long tstride[2]; long long store[1]; };
+extern "C" __global__ void __launch_bounds__(256) ptk_scan_fused_b1b014928f191738(float* pst0, const float* __restrict__ pns0, const ScDims d, long long total, long long T) {
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
+    long long rem = e;
+    long long off0 = 0;
+    long long off1 = 0;
+#pragma unroll
+    for (int k = 8 - 1; k >= 0; --k) {
+      if (k < d.ndim) {
+        const long long q = rem / d.shape[k]; const long long c = rem - q * d.shape[k]; rem = q;
+        off0 += c * d.st[0][k];
+        off1 += c * d.st[1][k];
+      }
+    }
+    const float ns0 = pns0[off1];
+    float w0_0 = pst0[off0 + 0LL * d.tstride[0]];
+    for (long long i = 0; i < T; ++i) {
+      float nv0;
+      ptk_body(w0_0, ns0, nv0);
+      w0_0 = nv0;
+      if (i >= T - d.store[0]) pst0[off0 + ((1LL + i) % d.store[0]) * d.tstride[0]] = nv0;
+    }
+  }
+}

@@ -41,7 +41,7 @@ def vec_width(dtypes) -> int:
 
 
 def gen_vec_kernel(prog: ScalarProgram, name: str, col_modes: tuple, inplace: dict, vw: int,
-                   unroll: int = VEC_UNROLL) -> str:
+                   unroll: int = VEC_UNROLL, flat: bool = False) -> str:
     """col_modes[k] in {0,1} for the n_in inputs followed by the n_out outputs (outputs are always 1).
     inplace: {out_idx: in_idx}.  Kernel params: pointers..., row strides..., nchunks, chunks_per_row, n_tail_start,
     n_total (flat tail handling: elements [n_tail_start, n_total) are done one by one when rows == 1)."""
@@ -66,7 +66,12 @@ def gen_vec_kernel(prog: ScalarProgram, name: str, col_modes: tuple, inplace: di
     ld_body = []
     for k, d in enumerate(prog.in_dtypes):
         T = CTYPE[d]
-        if col_modes[k] == 1:
+        if flat:
+            if col_modes[k] == 1:
+                ld_body.append(f"          vi{k}[u] = ptk_ldv<{T}, VW>(pi{k} + q * VW);")
+            else:
+                ld_body.append(f"          vi{k}[u] = pi{k}[0];")
+        elif col_modes[k] == 1:
             ld_body.append(f"          vi{k}[u] = ptk_ldv<{T}, VW>(pi{k} + r * rsi{k} + c);")
         else:
             ld_body.append(f"          vi{k}[u] = pi{k}[r * rsi{k}];")
@@ -75,12 +80,20 @@ def gen_vec_kernel(prog: ScalarProgram, name: str, col_modes: tuple, inplace: di
         call_in.append(f"vi{k}[u].v[e]" if col_modes[k] == 1 else f"vi{k}[u]")
     out_decl = "\n".join(f"          PVec<{CTYPE[d]}, VW> vo{k};" for k, d in enumerate(prog.out_dtypes))
     call_out = [f"vo{k}.v[e]" for k in range(n_out)]
-    st_body = "\n".join(f"          ptk_stv<{CTYPE[d]}, VW>(po{k} + r * rso{k} + c, vo{k});"
-                        for k, d in enumerate(prog.out_dtypes))
+    if flat:
+        st_body = "\n".join(f"          ptk_stv<{CTYPE[d]}, VW>(po{k} + q * VW, vo{k});"
+                            for k, d in enumerate(prog.out_dtypes))
+    else:
+        st_body = "\n".join(f"          ptk_stv<{CTYPE[d]}, VW>(po{k} + r * rso{k} + c, vo{k});"
+                            for k, d in enumerate(prog.out_dtypes))
     tail_in = [f"pi{k}[i]" if col_modes[k] == 1 else f"pi{k}[0]" for k in range(n_in)]
     tail_tmp = "\n".join(f"      {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
     tail_st = "\n".join(f"      po{k}[i] = to{k};" for k in range(n_out))
 
+    ROWCOL = """          long long r, c;
+          if (nchunks < 0x7fffffffLL) { unsigned int qq = (unsigned int)q; unsigned int r32 = qq / cpr; r = r32; c = (long long)(qq - r32 * cpr) * VW; }
+          else { r = q / cpr; c = (q - r * cpr) * VW; }
+          rr[u] = r; cc[u] = c;"""
     return f"""{PRELUDE}
 {_VEC_HELPERS}
 {emit_body(prog)}
@@ -92,16 +105,12 @@ extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
   const long long gstride = (long long)gridDim.x * blockDim.x;
   for (long long base = gtid; base < nchunks; base += gstride * U) {{
 {chr(10).join(loads)}
-      long long rr[U]; long long cc[U];
+{'' if flat else '      long long rr[U]; long long cc[U];'}
 #pragma unroll
       for (int u = 0; u < U; ++u) {{
         const long long q = base + (long long)u * gstride;
         if (q < nchunks) {{
-          long long r, c;
-          if (cpr == 0u) {{ r = 0; c = q * VW; }}
-          else if (nchunks < 0x7fffffffLL) {{ unsigned int qq = (unsigned int)q; unsigned int r32 = qq / cpr; r = r32; c = (long long)(qq - r32 * cpr) * VW; }}
-          else {{ r = q / cpr; c = (q - r * cpr) * VW; }}
-          rr[u] = r; cc[u] = c;
+{'' if flat else ROWCOL}
 {chr(10).join(ld_body)}
         }}
       }}
@@ -109,7 +118,7 @@ extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
       for (int u = 0; u < U; ++u) {{
         const long long q = base + (long long)u * gstride;
         if (q < nchunks) {{
-          const long long r = rr[u], c = cc[u];
+{'' if flat else '          const long long r = rr[u], c = cc[u];'}
 {out_decl}
 #pragma unroll
           for (int e = 0; e < VW; ++e) {{

@@ -159,6 +159,8 @@ def _mod(a, it, ot):
 
 def _maximum(a, it, ot):
     x, y = a
+    if ot == "float32" and all(t == "float32" for t in it):
+        return f"ptk_max_nan_f32(({x}), ({y}))"  # one FMNMX.NAN: NaN-propagating like the reference's Maximum.c_code
     if is_float(ot):
         return f"((({y}) > ({x})) ? ({y}) : ((({x}) >= ({y})) ? ({x}) : {_nan(ot)}))"
     return f"((({y}) > ({x})) ? ({y}) : ({x}))"
@@ -166,6 +168,8 @@ def _maximum(a, it, ot):
 
 def _minimum(a, it, ot):
     x, y = a
+    if ot == "float32" and all(t == "float32" for t in it):
+        return f"ptk_min_nan_f32(({x}), ({y}))"
     if is_float(ot):
         return f"((({y}) < ({x})) ? ({y}) : ((({x}) <= ({y})) ? ({x}) : {_nan(ot)}))"
     return f"((({y}) < ({x})) ? ({y}) : ({x}))"
@@ -291,7 +295,10 @@ OPS = {
 }
 
 PRELUDE = r"""
-// ---- ptk scalar helpers (Python floor-division / modulo semantics of IntDiv / Mod) ----
+// ---- ptk scalar helpers ----
+__device__ __forceinline__ float ptk_max_nan_f32(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float ptk_min_nan_f32(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+// Python floor-division / modulo semantics of IntDiv / Mod
 template <typename T> __device__ __forceinline__ T ptk_floordiv(T x, T y) {
   if (y == 0) return 0;
   T q = x / y;

@@ -1,10 +1,379 @@
-// placeholder: replaced by the tcgen05/TMEM kernel
+// bf16 tensor-core GEMM for fp32 graphs on sm_100a: tcgen05.mma (cta_group::1, M=128, N=256, K=16) with fp32
+// accumulators in TMEM, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-stage mbarrier ring,
+// persistent CTAs (one per SM) with a double-buffered TMEM accumulator so that the epilogue of tile i overlaps the MMAs
+// of tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (tcgen05.ld 32x32b -> alpha/beta/bias/tanh -> global).
+//
+// Replaces the sgemm_ call the C linker emits for Dot22 / Gemm (pytensor/tensor/blas/c_code/codegen.py:463-540) on the
+// "bf16 on tcgen05" configuration of BASELINE.json: the graph dtype stays float32 (the reference has no bfloat16 dtype,
+// pytensor/tensor/type.py:40-55), operands are rounded to bf16 by a conversion pass into a caller-owned workspace
+// (A as [M,K] K-major, B transposed to [N,K] K-major), products accumulate in fp32.
+#include <cuda_bf16.h>
+#include <algorithm>
 #include "ptk_common.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;  // 2 accumulators x 256 fp32 columns
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KiB
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//  [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between row groups) | [46,48) version = 1 |
+//  [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10, both K-major,
+// N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct EpiParams {
+  float alpha, beta;
+  float* C;
+  long long sc0, sc1;
+  const float* bias;
+  int act;
+  int M, N, K;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;                              // STAGES x 16 KiB
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;     // STAGES x 32 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [ACC_STAGES]
+  uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tm = t % m_tiles, tn = t / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, tm * BLOCK_M);
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, tn * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2);
+            const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2);
+            umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tm = t % m_tiles, tn = t / m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)tm * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + row * p.sc0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const long long col0 = (long long)tn * BLOCK_N + c0;
+        if (row_ok && col0 < p.N) {
+          const bool full = (col0 + 32 <= p.N);
+          if (full && p.sc1 == 1 && p.beta == 0.0f && ((((uintptr_t)(crow + col0)) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = p.alpha * __uint_as_float(r[j + e]);
+                if (p.bias) x += p.bias[col0 + j + e];
+                if (p.act == 1) x = tanhf(x);
+                vv[e] = x;
+              }
+              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long col = col0 + j;
+              if (col < p.N) {
+                float* dst = crow + col * p.sc1;
+                float x = p.alpha * __uint_as_float(r[j]);
+                if (p.beta != 0.0f) x += p.beta * (*dst);
+                if (p.bias) x += p.bias[col];
+                if (p.act == 1) x = tanhf(x);
+                *dst = x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- fp32 -> bf16 operand staging: dst[r][c] (row-major, pitch ld) = bf16(src[r*sr + c*sc]) ----------------------------
+// Tiled through shared memory so that both the read (along whichever source stride is 1) and the write (along c) coalesce.
+__global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src, long long sr, long long sc,
+                                                           __nv_bfloat16* __restrict__ dst, long long ld, long long R,
+                                                           long long Cc) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool col_fast = (sc == 1) || (sr != 1);
+  if (col_fast) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long r = r0 + ty + 8 * i, c = c0 + tx;
+      tile[ty + 8 * i][tx] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+    }
+  } else {  // source is row-fast (sr == 1): read with threads along r, transpose in smem
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long r = r0 + tx, c = c0 + ty + 8 * i;
+      tile[tx][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long r = r0 + ty + 8 * i, c = c0 + tx;
+    if (r < R && c < Cc) dst[r * ld + c] = __float2bfloat16_rn(tile[ty + 8 * i][tx]);
+  }
+}
+
+ptk_status make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ptk::drv().TensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
+                                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return ptk::check_cu(r, "cuTensorMapEncodeTiled");
+}
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
 namespace ptk {
-size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K) { return 0; }
+
+size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K) {
+  long long Kp = round_up(K, 8);
+  return (size_t)(round_up(M * Kp * 2, 256) + round_up(N * Kp * 2, 256) + 256);
+}
+
 ptk_status gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
                    const float* B, int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1,
                    const float* bias, int act, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  return fail(PTK_ERR_UNSUPPORTED, "gemm_tc not built");
+  if (M == 0 || N == 0) return PTK_OK;
+  if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) return fail(PTK_ERR_ARG, "gemm_tc: dims exceed int32");
+  if (workspace == nullptr || workspace_bytes < gemm_tc_workspace(M, N, K))
+    return fail(PTK_ERR_ARG, "gemm_tc: workspace too small (see ptk_gemm_workspace_bytes)");
+  const long long Kp = round_up(K, 8);
+  uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  __nv_bfloat16* Abf = reinterpret_cast<__nv_bfloat16*>(w);
+  __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(w + round_up(M * Kp * 2, 256));
+  {
+    dim3 ga((unsigned)((K + 31) / 32), (unsigned)((M + 31) / 32));
+    convert_bf16_kernel<<<ga, 256, 0, st>>>(A, sa0, sa1, Abf, Kp, M, K);
+    // B[K,N] -> Bt[N,K]: dst row index = n (source stride sb1), dst col index = k (source stride sb0)
+    dim3 gb((unsigned)((K + 31) / 32), (unsigned)((N + 31) / 32));
+    convert_bf16_kernel<<<gb, 256, 0, st>>>(B, sb1, sb0, Bbf, Kp, N, K);
+    PTK_LAUNCH_CHECK("convert_bf16");
+  }
+  CUtensorMap ta, tb;
+  ptk_status s;
+  if ((s = make_tmap(&ta, Abf, (uint64_t)M, (uint64_t)K, (uint64_t)Kp, BLOCK_M)) != PTK_OK) return s;
+  if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, BLOCK_N)) != PTK_OK) return s;
+  EpiParams p;
+  p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = std::max(1, std::min(m_tiles * n_tiles, ptk::sm_count()));
+  gemm_bf16_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  PTK_LAUNCH_CHECK("gemm_bf16_tc");
+  return PTK_OK;
 }
-}
+
+}  // namespace ptk

@@ -274,7 +274,7 @@ ptk_status ptk_launch(void* func, unsigned gx, unsigned gy, unsigned gz, unsigne
 
 // ---- graphs ----------------------------------------------------------------------------------------------------------
 ptk_status ptk_graph_begin_capture(void* stream) {
-  PTK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  PTK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
   return PTK_OK;
 }
 ptk_status ptk_graph_end_capture(void* stream, void** graph_exec) {

@@ -32,8 +32,14 @@ def register():
 
     @rewrite_scan_inner_graph.register(CUDALinker)
     def _cuda_rewrite_scan_inner_graph(linker, op, node, inner, *, mode):
-        # Functional variant (inner_graph.py:85-90): the persistent kernel / device loop manages its own buffers, so
-        # no in-place taps are baked into the inner graph.
+        # The device loop / persistent kernel manages the tap buffers itself, so no in-place taps are baked into the
+        # inner graph (functional variant, inner_graph.py:85-90) — and every inner input is protected from destruction
+        # (they are views into the circular buffers); in-place between inner intermediates is still allowed.
+        from pytensor.compile.aliasing import add_supervisor_to_fgraph
+        from pytensor.compile.io import In
+
+        specs = [In(x, borrow=True, mutable=False) for x in inner.inputs]
+        add_supervisor_to_fgraph(fgraph=inner, input_specs=specs, accept_inplace=True)
         scan_inner_optimizer(op, mode).rewrite(inner)
 
     @rewrite_ofg_inner_graph.register(CUDALinker)

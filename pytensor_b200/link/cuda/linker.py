@@ -45,6 +45,7 @@ class CudaVM:
         self.thunks = thunks
         self.position_of_error = -1
         self.time_thunks = False
+        self.borrow_outputs = False
         self.call_times = executor.call_times
         self.call_counts = executor.call_counts
 
@@ -56,7 +57,7 @@ class CudaVM:
         except Exception:
             self.position_of_error = ex.position_of_error
             raise
-        outs = outputs_to_host(out_vals, self.device_outputs)
+        outs = outputs_to_host(out_vals, self.device_outputs, copy_device=ex.last_from_graph and not self.borrow_outputs)
         for cell, o in zip(self.output_storage, outs):
             cell[0] = o
         if output_subset is not None:
@@ -91,13 +92,16 @@ class CUDALinker(LocalLinker):
     required_rewrites: tuple[str, ...] = ("minimum_compile",)
     incompatible_rewrites: tuple[str, ...] = ("cxx_only",)
 
-    def __init__(self, allow_gc=None, gemm_precision="fp32", device_outputs=False, schedule=None, fuse=True):
+    def __init__(self, allow_gc=None, gemm_precision="fp32", device_outputs=False, schedule=None, fuse=True,
+                 use_graph=True, borrow_outputs=False):
         if allow_gc is None:
             allow_gc = config.allow_gc
         self.fgraph = None
         self.gemm_precision = gemm_precision
         self.device_outputs = device_outputs
         self.fuse = fuse
+        self.use_graph = use_graph
+        self.borrow_outputs = borrow_outputs  # device outputs may alias VM-owned memory that the next call overwrites
         self.updated_vars = {}
         super().__init__(allow_gc=allow_gc, scheduler=schedule)
 
@@ -107,7 +111,8 @@ class CUDALinker(LocalLinker):
         if self.fgraph is not None and self.fgraph is not fgraph:
             return type(self)(
                 allow_gc=self.allow_gc, gemm_precision=self.gemm_precision, device_outputs=self.device_outputs,
-                schedule=self._scheduler, fuse=self.fuse,
+                schedule=self._scheduler, fuse=self.fuse, use_graph=self.use_graph,
+                borrow_outputs=self.borrow_outputs,
             ).accept(fgraph, no_recycling, profile)
         self.fgraph = fgraph
         self.no_recycling = no_recycling
@@ -127,9 +132,10 @@ class CUDALinker(LocalLinker):
             fgraph, order, input_storage, output_storage, storage_map
         )
         program, thunks = build_program(fgraph, order, self.lowering_options(), storage_map)
-        executor = Executor(program, allow_gc=bool(self.allow_gc))
+        executor = Executor(program, allow_gc=bool(self.allow_gc), use_graph=bool(self.use_graph))
         vm = CudaVM(fgraph, order, executor, input_storage, output_storage, storage_map, bool(self.allow_gc),
                     self.device_outputs, thunks)
+        vm.borrow_outputs = self.borrow_outputs
         return (
             vm,
             [Container(i, s) for i, s in zip(fgraph.inputs, input_storage, strict=True)],

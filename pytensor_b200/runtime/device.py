@@ -38,7 +38,21 @@ def device() -> torch.device:
         require_cuda()
         _lib.init(torch.cuda.current_device())
         _device = torch.device("cuda", torch.cuda.current_device())
+        # The backend runs on its own (capturable) stream, which it also makes torch's current stream so that the
+        # caching allocator, the caller's torch ops and our kernels are all ordered on one stream. The legacy default
+        # stream cannot be captured into a CUDA graph.
+        global _vm_stream
+        _vm_stream = torch.cuda.Stream(device=_device)
+        torch.cuda.set_stream(_vm_stream)
     return _device
+
+
+_vm_stream = None
+
+
+def vm_stream():
+    device()
+    return _vm_stream
 
 
 def stream_ptr() -> int:
@@ -57,8 +71,62 @@ def np_dtype_name(x) -> str:
     return np.asarray(x).dtype.name
 
 
+class GraphUnsupported(RuntimeError):
+    """Raised when something that cannot be part of a CUDA graph (a device->host read, a blocking copy) is attempted
+    while the VM is capturing; the VM then abandons the capture and runs the call eagerly."""
+
+
+class Arena:
+    """Bump allocator over one device buffer: gives the captured CUDA graph stable addresses (no allocator calls while
+    capturing, same pointers on every replay)."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes: int):
+        self.buf = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device())
+        self.off = 0
+
+    def alloc(self, shape, tdtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=tdtype, device="meta").element_size()
+        start = self.off
+        self.off = (start + nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.off > self.buf.numel():
+            raise GraphUnsupported("arena exhausted (allocation pattern changed between the measuring run and capture)")
+        if nbytes == 0:
+            return torch.empty(tuple(shape), dtype=tdtype, device=self.buf.device)
+        return self.buf[start:start + nbytes].view(tdtype).view(tuple(shape))
+
+
+class _AllocState:
+    arena = None        # Arena while capturing
+    measuring = False   # count bytes of every allocation (the eager run that precedes a capture)
+    measured = 0
+    capturing = False
+
+
+alloc_state = _AllocState()
+
+
+def empty_t(shape, tdtype) -> torch.Tensor:
+    """The single device-allocation point of the backend."""
+    shape = tuple(int(s) for s in shape)
+    st = alloc_state
+    if st.arena is not None:
+        return st.arena.alloc(shape, tdtype)
+    if st.measuring:
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=tdtype, device="meta").element_size()
+        st.measured += (nbytes + Arena.ALIGN - 1) // Arena.ALIGN * Arena.ALIGN + Arena.ALIGN
+    return torch.empty(shape, dtype=tdtype, device=device())
+
+
 def empty(shape, dtype: str) -> torch.Tensor:
-    return torch.empty(tuple(int(s) for s in shape), dtype=NP_TO_TORCH[dtype], device=device())
+    return empty_t(shape, NP_TO_TORCH[dtype])
 
 
 def empty_like_layout(shape, dtype: str, order) -> torch.Tensor:
@@ -102,13 +170,13 @@ def contiguous(t: torch.Tensor) -> torch.Tensor:
     """C-contiguous version of `t` (itself when already contiguous); the copy runs in the libptk copy kernel."""
     if t.is_contiguous():
         return t
-    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    out = empty_t(t.shape, t.dtype)
     copy_strided(out, t)
     return out
 
 
 def clone(t: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    out = empty_t(t.shape, t.dtype)
     copy_strided(out, t)
     return out
 
@@ -123,12 +191,29 @@ def to_device(arr) -> torch.Tensor:
     if not a.flags.c_contiguous:
         a = np.ascontiguousarray(a)
     out = empty(a.shape, a.dtype.name)
+    if a.size and alloc_state.capturing:
+        # a host value that is a function of the call signature only (shape integers, constants): upload it NOW on a
+        # side stream into its arena slot so that the captured graph finds it there on every replay
+        side = _side_stream()
+        _lib.check(_lib.lib().ptk_memcpy_h2d_async(ptr(out), a.ctypes.data, a.nbytes, side.cuda_stream), "h2d")
+        _lib.check(_lib.lib().ptk_sync_stream(side.cuda_stream), "sync")
+        return out
     if a.size:
         _lib.check(_lib.lib().ptk_memcpy_h2d_async(ptr(out), a.ctypes.data, a.nbytes, stream_ptr()), "h2d")
         # The source may be pageable and freed/mutated by the caller right after we return: make the copy complete.
         # (cudaMemcpyAsync from pageable memory has already staged it; for pinned memory we must wait.)
         _lib.check(_lib.lib().ptk_sync_stream(stream_ptr()), "sync")
     return out
+
+
+_side = None
+
+
+def _side_stream():
+    global _side
+    if _side is None:
+        _side = torch.cuda.Stream()
+    return _side
 
 
 def to_device_async(arr: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -143,14 +228,63 @@ def to_device_async(arr: np.ndarray, out: torch.Tensor | None = None) -> torch.T
     return out
 
 
+class _PinnedPool:
+    """Page-locked host blocks for function outputs.  A block is handed out inside a NumPy array and returns to the
+    pool when that array (and every view of it) has been garbage collected, so each call still yields a fresh object
+    (the `no_recycling` contract, pytensor/link/vm.py:860-885) without paying page faults + a pageable D2H per call."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self):
+        self.free = {}
+        self.total = 0
+
+    def take(self, nbytes):
+        cap = 1 << max(20, (int(nbytes) - 1).bit_length())
+        lst = self.free.get(cap)
+        if lst:
+            return lst.pop(), cap
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().ptk_host_alloc_pinned(ctypes.byref(p), cap), "ptk_host_alloc_pinned")
+        self.total += cap
+        return p.value, cap
+
+    def give(self, ptr, cap):
+        self.free.setdefault(cap, []).append(ptr)
+
+
+_pinned_pool = _PinnedPool()
+PINNED_POOL_LIMIT = 8 << 30
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    import weakref
+
+    dt = np.dtype(dtype)
+    n = 1
+    for s in shape:
+        n *= int(s)
+    nbytes = n * dt.itemsize
+    ptr_, cap = _pinned_pool.take(nbytes)
+    buf = (ctypes.c_char * nbytes).from_address(ptr_)
+    weakref.finalize(buf, _pinned_pool.give, ptr_, cap)
+    return np.frombuffer(buf, dtype=dt).reshape(tuple(int(s) for s in shape))
+
+
 def to_host(t, sync: bool = True) -> np.ndarray:
     """Device -> host copy into a fresh numpy array (C order)."""
     if not isinstance(t, torch.Tensor):
         return np.asarray(t)
     if t.is_meta:
         return np.zeros(tuple(t.shape), dtype=TORCH_TO_NP[t.dtype])
+    if alloc_state.capturing:
+        raise GraphUnsupported("device->host read inside a graph capture")
     src = contiguous(t)
-    out = np.empty(tuple(src.shape), dtype=TORCH_TO_NP[src.dtype])
+    nbytes = src.numel() * src.element_size()
+    if nbytes >= _PinnedPool.MIN_BYTES and _pinned_pool.total < PINNED_POOL_LIMIT and not _lib.TRACE_ONLY:
+        out = pinned_empty(tuple(src.shape), TORCH_TO_NP[src.dtype])
+    else:
+        out = np.empty(tuple(src.shape), dtype=TORCH_TO_NP[src.dtype])
     if out.size:
         _lib.check(_lib.lib().ptk_memcpy_d2h_async(out.ctypes.data, ptr(src), out.nbytes, stream_ptr()), "d2h")
     if sync:

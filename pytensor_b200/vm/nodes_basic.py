@@ -232,7 +232,7 @@ class _Region:
 
 
 def _copy_region_out(reg: _Region, dtype) -> torch.Tensor:
-    out = torch.empty(reg.shape, dtype=reg.base.dtype, device=reg.base.device)
+    out = dev.empty_t(reg.shape, reg.base.dtype)
     if out.numel():
         L = _lib.lib()
         _lib.check(L.ptk_copy_strided(dev.ptr(out), dev.i64_array(out.stride()), reg.ptr, dev.i64_array(reg.strides),
@@ -276,6 +276,10 @@ class IncSubtensorNode(Node):
     def run(self, vals):
         x = vals[0].dev()
         y = vals[1].dev()
+        if dev.TORCH_TO_NP[y.dtype] != self.dtype:  # y may be a narrower dtype than x (subtensor.py IncSubtensor.make_node)
+            from .nodes_cast import cast_to
+
+            y = cast_to(y, self.dtype)
         index = _build_index(self.idx_template, vals[2:])
         if not self.inplace:
             x = dev.clone(x)
@@ -319,7 +323,7 @@ class TakeNode(Node):
             inner *= s
         n_src = x.shape[ax]
         oshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
-        out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+        out = dev.empty_t(oshape, x.dtype)
         if out.numel():
             if n_src == 0:
                 raise IndexError("index out of bounds (taking from an empty axis)")
@@ -363,6 +367,10 @@ class PutNode(Node):
             inner *= s
         yshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
         y = vals[1].dev()
+        if dev.TORCH_TO_NP[y.dtype] != self.dtype:
+            from .nodes_cast import cast_to
+
+            y = cast_to(y, self.dtype)
         yb = _broadcast_view(y, yshape)
         yc = dev.contiguous(yb) if not yb.is_contiguous() else yb
         n = 1
@@ -382,7 +390,7 @@ _pending_flags: list = []
 
 
 def _err_flag() -> torch.Tensor:
-    t = torch.empty((1,), dtype=torch.int32, device=dev.device())
+    t = dev.empty_t((1,), torch.int32)
     _lib.check(_lib.lib().ptk_memset_async(dev.ptr(t), 0, 4, dev.stream_ptr()), "memset")
     return t
 

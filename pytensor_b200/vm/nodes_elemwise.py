@@ -234,11 +234,13 @@ class ElemwiseNode(Node):
             rows = cshape[0] if len(cshape) == 2 else 1
             cols = cshape[-1]
             col_modes = tuple(1 if st[-1] == 1 else 0 for st in csts)
-            key = ("vec", col_modes, vw)
+            flat = rows == 1
+            key = ("vec", col_modes, vw, flat)
             fn = self._kernels.get(key)
             if fn is None:
                 fn, _ = jit.get_function_gen(
-                    lambda kn: cg_ew.gen_vec_kernel(self.prog, kn, col_modes, self.inplace, vw), "ptk_ew_vec")
+                    lambda kn: cg_ew.gen_vec_kernel(self.prog, kn, col_modes, self.inplace, vw, flat=flat),
+                    "ptk_ew_vec")
                 self._kernels[key] = fn
             cpr_chunks = cols // vw
             nchunks = rows * cpr_chunks
@@ -457,3 +459,111 @@ class CAReduceNode(Node):
         args = [c_void_p(dev.ptr(t)), c_void_p(dev.ptr(out)), d, c_longlong(n_out), c_longlong(n_red)]
         grid = min(max(1, (n_out + 255) // 256), _lib.sm_count() * 16)
         jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ElemwiseReduceNode(Node):
+    """K3: Elemwise(Composite) whose output feeds a CAReduce over its trailing axes, as ONE kernel — the map result
+    stays in registers for the reduction and is written to memory only if something else needs it.
+
+    The reference cannot fuse a multi-input Elemwise into a CAReduce (pytensor/tensor/rewriting/elemwise.py:1119-1121),
+    so its C linker materialises the elementwise result and re-reads it.  Outputs of this node: the Elemwise outputs
+    (in the Elemwise's order) followed by the reduction result.  Falls back to running the two constituent nodes
+    back-to-back (still on the device) whenever the runtime layout does not fit the fused row kernel.
+    """
+
+    def __init__(self, ew: ElemwiseNode, red: CAReduceNode, which: int, store_reduced_input: bool):
+        self.ew, self.red, self.which = ew, red, which
+        self.store_reduced_input = store_reduced_input
+        self.n_out = ew.n_out + 1
+        self.destroy = dict(ew.destroy)
+        self.name = f"{ew.name}->{red.name}[fused]"
+        # program with the reduced output first (the row kernel accumulates map output 0)
+        p = ew.prog
+        order = [which] + [k for k in range(ew.n_out) if k != which]
+        self.order = order
+        self.prog = ScalarProgram(list(p.in_dtypes), [p.out_dtypes[k] for k in order], list(p.consts), list(p.insts),
+                                  [p.outputs[k] for k in order])
+        self._kernels = {}
+
+    def _unfused(self, vals):
+        outs = self.ew.run(vals)
+        return outs + self.red.run([outs[self.which]])
+
+    def run(self, vals):
+        ew, red = self.ew, self.red
+        nd = ew.ndim
+        n_red = len(red.axes)
+        if nd == 0 or n_red == 0 or tuple(red.axes) != tuple(range(nd - n_red, nd)):
+            return self._unfused(vals)
+        oshape = ew._out_shape([v.shape for v in vals])
+        rows = 1
+        for s in oshape[: nd - n_red]:
+            rows *= s
+        cols = 1
+        for s in oshape[nd - n_red:]:
+            cols *= s
+        if rows == 0 or cols == 0:
+            return self._unfused(vals)
+        ins = [v.dev() for v in vals]
+        outs = []
+        for k, dt in enumerate(ew.prog.out_dtypes):
+            outs.append(ins[ew.inplace[k]] if k in ew.inplace else dev.empty(oshape, dt))
+        # collapse kept dims -> rows and reduced dims -> cols for every operand
+        ops = ins + outs
+        strides = []
+        for k, t in enumerate(ins):
+            strides.append([0 if (ew.in_bcast[k][d] or (t.shape[d] == 1 and oshape[d] != 1)) else t.stride(d)
+                            for d in range(nd)])
+        for t in outs:
+            strides.append([t.stride(d) for d in range(nd)])
+        kshape, ksts = _collapse(oshape[: nd - n_red], [st[: nd - n_red] for st in strides])
+        cshape, csts = _collapse(oshape[nd - n_red:], [st[nd - n_red:] for st in strides])
+        if len(kshape) != 1 or len(cshape) != 1:
+            return self._unfused_given(vals, ins, outs)
+        dtypes = list(ew.prog.in_dtypes) + list(ew.prog.out_dtypes)
+        vw = cg_ew.vec_width(dtypes)
+        col_modes = []
+        for t, dt, cst, kst in zip(ops, dtypes, csts, ksts):
+            inner = cst[0]
+            if inner not in (0, 1):
+                return self._unfused_given(vals, ins, outs)
+            if inner == 1 and (dev.ptr(t) % (ITEMSIZE[dt] * vw) != 0 or kst[0] % vw != 0):
+                vw = 1
+            col_modes.append(inner)
+        if any(m != 1 for m in col_modes[len(ins):]):
+            return self._unfused_given(vals, ins, outs)
+        sms = _lib.sm_count()
+        tpr = 256 if cols >= 1024 else 32
+        rows_per_block = 256 // tpr
+        row_blocks = (rows + rows_per_block - 1) // rows_per_block
+        if row_blocks < sms:  # too few rows to fill the GPU with one CTA-row mapping: keep the two-kernel path
+            return self._unfused_given(vals, ins, outs)
+        store = tuple((k != 0 or self.store_reduced_input) for k in range(ew.n_out))  # in self.order numbering
+        in_modes = tuple(col_modes[: len(ins)])
+        key = (in_modes, vw, tpr, store)
+        fn = self._kernels.get(key)
+        if fn is None:
+            fn, _ = jit.get_function_gen(
+                lambda kn: cg_red.gen_row_kernel(self.prog, kn, in_modes, store, red.red_op, red.acc_dtype,
+                                                 red.out_dtype, red.identity, vw, tpr, inplace=ew.inplace),
+                "ptk_ew_red_row")
+            self._kernels[key] = fn
+        rout = dev.empty(oshape[: nd - n_red], red.out_dtype)
+        stored = [k for k in range(ew.n_out) if store[k]]
+        args = [c_void_p(dev.ptr(t)) for t in ins]
+        args += [c_void_p(dev.ptr(outs[self.order[k]])) for k in stored]
+        args += [c_void_p(dev.ptr(rout))]
+        args += [c_longlong(ksts[j][0]) for j in range(len(ins))]
+        args += [c_longlong(ksts[len(ins) + self.order[k]][0]) for k in stored]
+        args += [c_longlong(rows), c_longlong(cols), c_int(1)]
+        gx = min(row_blocks, sms * 16)
+        jit.launch(fn, (gx, 1), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())
+        res = [Val(d=o) for o in outs]
+        if not self.store_reduced_input:
+            res[self.which] = None  # never materialised: the fusion pass guarantees nothing reads it
+        return res + [Val(d=rout)]
+
+    def _unfused_given(self, vals, ins, outs):
+        del ins, outs
+        return self._unfused(vals)

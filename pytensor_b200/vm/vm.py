@@ -12,6 +12,8 @@ No pytensor import here: a program can be pickled and replayed on a box with onl
 from __future__ import annotations
 
 import time
+from ctypes import byref as ctypes_byref
+from ctypes import c_void_p as ctypes_void_p
 
 import numpy as np
 
@@ -61,10 +63,33 @@ class Program:
                     st.free.append(s)
 
 
-class Executor:
-    """Runs a Program.  `run(input_values) -> list of output Vals` (no host conversion)."""
+class _GraphEntry:
+    __slots__ = ("stage", "nbytes", "arena", "gexec", "static_in", "out_vals", "flags", "keep")
 
-    def __init__(self, program: Program, allow_gc=True):
+    def __init__(self, nbytes):
+        self.stage, self.nbytes = 1, nbytes
+        self.arena = self.gexec = self.out_vals = None
+        self.static_in, self.flags, self.keep = [], [], []
+
+
+class Executor:
+    """Runs a Program.  `run(input_values) -> list of output Vals` (no host conversion).
+
+    With `use_graph`, the launch list of a call signature (input shapes/dtypes, device-input addresses, values of tiny
+    host inputs) is captured once into a CUDA graph over an arena of stable addresses and replayed with one
+    cudaGraphLaunch per call afterwards — the device-side analogue of the CVM's precomputed instruction arrays
+    (pytensor/link/vm.py:1057-1168).  First call of a signature: eager run that also measures the arena; second call:
+    capture + launch; later calls: replay.  Anything that cannot live in a graph (a device->host read inside a node)
+    abandons the capture and pins that signature to eager execution.
+    """
+
+    MAX_GRAPHS = 8
+
+    def __init__(self, program: Program, allow_gc=True, use_graph=False):
+        self.use_graph = use_graph
+        self.last_from_graph = False
+        self._graphs = {}
+        self._graph_misses = 0
         self.program = program
         self.allow_gc = allow_gc
         self.vals = [None] * program.n_slots
@@ -77,7 +102,122 @@ class Executor:
         self.call_counts = [0] * n
         self.event_log = None  # when a list: (step index, start event, stop event) per executed step (no syncs)
 
+    # ---- CUDA-graph path ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _signature(inputs):
+        import torch
+
+        sig = []
+        for x in inputs:
+            if isinstance(x, Val):
+                return None
+            if isinstance(x, torch.Tensor):
+                if not x.is_cuda:
+                    return None
+                sig.append(("d", x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype))
+            else:
+                a = np.asarray(x)
+                small = tuple(a.reshape(-1).tolist()) if a.size <= 8 else None
+                sig.append(("h", a.shape, a.dtype.str, small))
+        return tuple(sig)
+
     def run(self, inputs):
+        from ..runtime import lib as _lib
+
+        self.last_from_graph = False
+        if (not self.use_graph or _lib.TRACE_ONLY or self.time_nodes or self.event_log is not None
+                or dev.alloc_state.capturing or dev.alloc_state.measuring):
+            return self._run_eager(inputs)
+        sig = self._signature(inputs)
+        if sig is None:
+            return self._run_eager(inputs)
+        e = self._graphs.get(sig)
+        if e is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graph_misses += 1
+                return self._run_eager(inputs)
+            st = dev.alloc_state
+            st.measuring, st.measured = True, 0
+            try:
+                outs = self._run_eager(inputs)
+            finally:
+                st.measuring = False
+            extra = sum(int(np.asarray(x).nbytes) + 512 for x in inputs if not hasattr(x, "is_cuda"))
+            self._graphs[sig] = _GraphEntry(st.measured + extra + 4096)
+            return outs
+        if e.stage == 1:
+            return self._capture(e, inputs)
+        if e.stage == 2:
+            L = _lib.lib()
+            sp = dev.stream_ptr()
+            for k, t in e.static_in:
+                a = np.asarray(inputs[k])
+                if not a.flags.c_contiguous:
+                    a = np.ascontiguousarray(a)
+                    e.keep.append(a)
+                if a.size:
+                    _lib.check(L.ptk_memcpy_h2d_async(dev.ptr(t), a.ctypes.data, a.nbytes, sp), "h2d")
+            _lib.check(L.ptk_graph_launch(e.gexec, sp), "graph launch")
+            nodes_basic._pending_flags.extend(e.flags)
+            e.keep.clear() if len(e.keep) > 64 else None
+            self.last_from_graph = True
+            return e.out_vals
+        return self._run_eager(inputs)
+
+    def _capture(self, e, inputs):
+        import torch
+
+        from ..runtime import lib as _lib
+
+        L = _lib.lib()
+        st = dev.alloc_state
+        sp = dev.stream_ptr()
+        e.arena = dev.Arena(e.nbytes)
+        st.arena = e.arena
+        vals_in = []
+        try:
+            for k, x in enumerate(inputs):
+                if isinstance(x, torch.Tensor):
+                    vals_in.append(Val(d=x))
+                else:
+                    a = np.ascontiguousarray(np.asarray(x))
+                    t = dev.empty(a.shape, a.dtype.name)
+                    if a.size:
+                        _lib.check(L.ptk_memcpy_h2d_async(dev.ptr(t), a.ctypes.data, a.nbytes, sp), "h2d")
+                    e.static_in.append((k, t))
+                    vals_in.append(Val(h=a if a.size <= 8 else None, d=t))
+            _lib.check(L.ptk_sync_stream(sp), "sync")
+            n_flags = len(nodes_basic._pending_flags)
+            _lib.check(L.ptk_graph_begin_capture(sp), "begin capture")
+            st.capturing = True
+            ok = True
+            try:
+                outs = self._run_eager(vals_in)
+            except dev.GraphUnsupported:
+                ok = False
+            finally:
+                st.capturing = False
+                g = ctypes_void_p()
+                rc = L.ptk_graph_end_capture(sp, ctypes_byref(g))
+            if not ok or rc != 0:
+                del nodes_basic._pending_flags[n_flags:]
+                if rc == 0 and g.value:
+                    L.ptk_graph_destroy(g)
+                e.stage, e.arena, e.static_in = -1, None, []
+                st.arena = None
+                return self._run_eager(inputs)
+            e.gexec = g.value
+            e.flags = list(nodes_basic._pending_flags[n_flags:])
+            e.out_vals = outs
+            e.stage = 2
+        finally:
+            st.arena = None
+            st.capturing = False
+        _lib.check(L.ptk_graph_launch(e.gexec, sp), "graph launch")
+        self.last_from_graph = True
+        return e.out_vals
+
+    def _run_eager(self, inputs):
         p = self.program
         vals = self.vals
         for s, x in zip(p.inputs, inputs):
@@ -108,7 +248,7 @@ class Executor:
                 self.position_of_error = st.origin if st.origin >= 0 else i
                 raise
             for j, r in zip(st.outs, res):
-                vals[j] = r
+                vals[j] = r  # a fused node may return None for a value that is never materialised (and never read)
             if self.allow_gc:
                 for j in st.free:
                     vals[j] = None
@@ -122,15 +262,16 @@ class Executor:
         return outs
 
 
-def outputs_to_host(out_vals, device_outputs=False):
-    """Val -> what Function.__call__ hands to the user: NumPy arrays (one sync) or device tensors."""
+def outputs_to_host(out_vals, device_outputs=False, copy_device=False):
+    """Val -> what Function.__call__ hands to the user: NumPy arrays (one sync) or device tensors.
+    `copy_device`: device outputs may live in a graph arena that the next call overwrites -> hand out copies."""
     res = []
     pending = []
     for v in out_vals:
         if v.h is not None and v.d is None:
             res.append(np.asarray(v.h))
         elif device_outputs:
-            res.append(v.d)
+            res.append(dev.clone(v.d) if copy_device else v.d)
         else:
             res.append(None)
             pending.append((len(res) - 1, v))

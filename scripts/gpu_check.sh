@@ -9,12 +9,12 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 ( timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 tail -2 gpurun_out/smoke.log
-( timeout 600 python bench.py --steps 30 --warmup 5 ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+( timeout 900 python bench.py --steps 30 --warmup 6 ${BENCH_ARGS:-} ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 tail -c 3000 gpurun_out/bench.json
 if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
      python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptk_ew_vec -s 4 -c 2 -o gpurun_out/prof_ew -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptk_ew -s 4 -c 2 -o gpurun_out/prof_ew -f \
      python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
 echo done

@@ -1,0 +1,67 @@
+"""The bf16 tcgen05/TMEM GEMM path (K4/K5) against the reference C linker's fp32 sgemm.
+
+Tolerance: operands are rounded to bf16 (8-bit mantissa, rel 2^-9 per operand), products accumulate in fp32, so a
+K-term dot product of O(1) values carries an absolute error ~ sqrt(K) * 2^-9 * |a||b|.  This is the reference's own
+half-precision notion of "close" (float16: atol=rtol=1e-3 relative to the output scale, pytensor/tensor/math.py:92-139)
+scaled by the output magnitude; the 1e-5 bar applies to the native fp32 path (test_gpu_blas.py)."""
+
+import numpy as np
+import pytest
+
+from helpers import pytensor
+
+import pytensor.tensor as pt
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, ref, K):
+    scale = np.abs(ref).max() + 1e-30
+    err = np.abs(got - ref).max() / scale
+    assert err < 4e-3, f"bf16 tensor-core GEMM deviates {err:.2e} of the output scale (K={K})"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (512, 768, 320), (1000, 520, 264), (384, 256, 1024)])
+def test_dot22_bf16(gpu, M, N, K):
+    rng = np.random.default_rng(41)
+    x, y = pt.fmatrix("x"), pt.fmatrix("y")
+    f = pytensor.function([x, y], pt.dot(x, y), mode="CUDA_BF16")
+    xv = rng.standard_normal((M, K)).astype("float32")
+    yv = rng.standard_normal((K, N)).astype("float32")
+    got = f(xv, yv)
+    ref = xv.astype(np.float64) @ yv.astype(np.float64)
+    _check(got, ref, K)
+    # bit-level structure: the result must equal an fp32-accumulated product of the bf16-rounded operands closely
+    import torch
+
+    xb = torch.from_numpy(xv).bfloat16().double().numpy()
+    yb = torch.from_numpy(yv).bfloat16().double().numpy()
+    np.testing.assert_allclose(got, xb @ yb, rtol=2e-5, atol=2e-4 * np.sqrt(K))
+
+
+def test_gemm_bf16_alpha_beta_and_transposes(gpu):
+    rng = np.random.default_rng(42)
+    z, x, y = pt.fmatrix("z"), pt.fmatrix("x"), pt.fmatrix("y")
+    f = pytensor.function([z, x, y], 0.5 * z + 2.0 * pt.dot(x.T, y), mode="CUDA_BF16")
+    xv = rng.standard_normal((512, 300)).astype("float32")
+    yv = rng.standard_normal((512, 260)).astype("float32")
+    zv = rng.standard_normal((300, 260)).astype("float32")
+    got = f(zv, xv, yv)
+    ref = 0.5 * zv + 2.0 * (xv.T.astype(np.float64) @ yv.astype(np.float64))
+    _check(got, ref, 512)
+
+
+def test_mlp_chain_bf16_vs_cvm(gpu):
+    # BASELINE.json configs[2] at reduced size: 3 x tanh(h @ W + b); CUDA_BF16 vs the C linker's fp32 result
+    from pytensor_b200 import workloads as W
+
+    pytensor.config.floatX = "float32"
+    ins, outs, make_args, _ = W.cfg3_mlp(512)
+    f = pytensor.function(ins, outs, mode="CUDA_BF16")
+    f_ref = pytensor.function(ins, outs, mode="CVM")
+    a = make_args()
+    got, ref = f(*a)[0], f_ref(*a)[0]
+    assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+    # and the native-precision linker meets the 1e-5 class bar on the same graph
+    f32 = pytensor.function(ins, outs, mode="CUDA")
+    np.testing.assert_allclose(f32(*a)[0], ref, rtol=1e-4, atol=1e-5)
