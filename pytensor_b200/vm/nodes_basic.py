@@ -205,6 +205,7 @@ def _build_index(idx_template, index_vals):
 def _probe(shape, strides, index):
     """NumPy-exact basic indexing on metadata only: returns (shape, strides, element offset) of x[index]."""
     base = np.empty(1, dtype=np.int8)
+    index = tuple(index) + (Ellipsis,)  # keeps an all-integer index a 0-d VIEW (a NumPy scalar would be a copy)
     if any(s == 0 for s in shape):
         v = np.lib.stride_tricks.as_strided(base, shape=tuple(shape), strides=tuple(0 for _ in shape))
         w = v[index]

@@ -39,6 +39,17 @@ class Node:
     def __repr__(self):
         return f"<{type(self).__name__} {self.name}>"
 
+    # Nodes are plain data + caches of device handles; only the data is pickled (a lowered Program can be shipped to a
+    # box that has torch + libptk but no host framework).
+    _TRANSIENT = ("_kernels", "_fn", "_const_cache", "_flag")
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            if k in d:
+                d[k] = {} if isinstance(d[k], dict) else None
+        return d
+
 
 def _collapse(shape, strides_list):
     """Merge adjacent dims that are mergeable for EVERY operand. Returns (shape, strides_list)."""

@@ -28,6 +28,12 @@ class Step:
     def __init__(self, impl, ins, outs, origin=-1):
         self.impl, self.ins, self.outs, self.free, self.origin = impl, list(ins), list(outs), [], origin
 
+    def __getstate__(self):
+        return (self.impl, self.ins, self.outs, self.free, self.origin)
+
+    def __setstate__(self, st):
+        self.impl, self.ins, self.outs, self.free, self.origin = st
+
 
 class Program:
     """Flat, pytensor-free description of a compiled graph.
@@ -84,6 +90,12 @@ class Executor:
     """
 
     MAX_GRAPHS = 8
+
+    def __getstate__(self):
+        return {"program": self.program, "allow_gc": self.allow_gc, "use_graph": self.use_graph}
+
+    def __setstate__(self, d):
+        self.__init__(d["program"], d["allow_gc"], d["use_graph"])
 
     def __init__(self, program: Program, allow_gc=True, use_graph=False):
         self.use_graph = use_graph

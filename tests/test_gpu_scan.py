@@ -22,7 +22,11 @@ def test_cfg4_elementwise_recurrence(gpu, last_only):
     from pytensor_b200 import workloads as W
 
     ins, outs, make_args, _ = W.cfg4_scan(96, 40, 57, full_trace=not last_only)
-    f, _ = compare_cuda_and_cvm(ins, outs, make_args(), rtol=2e-5, atol=2e-5)
+    args = make_args()
+    # contractive gain (|a| < 1): libm-vs-CUDA tanhf ulp differences must not be amplified step after step, otherwise the
+    # comparison measures the recurrence's Lyapunov growth instead of the kernel
+    args[1] = np.random.default_rng(5).uniform(0.3, 0.9, args[1].shape).astype("float32")
+    f, _ = compare_cuda_and_cvm(ins, outs, args, rtol=2e-5, atol=2e-5)
     assert _is_fused(f)
 
 

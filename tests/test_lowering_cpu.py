@@ -1,0 +1,154 @@
+"""CPU suite: every BASELINE.json config lowers under mode="CUDA" and its launch logic runs in trace-only mode
+(NVRTC compiles each generated kernel for sm_100a; no device, no results)."""
+
+import numpy as np
+import pytest
+
+from helpers import pytensor
+
+import pytensor.tensor as pt
+from pytensor_b200 import workloads as W
+from pytensor_b200.precompile import trace_function
+
+
+def _steps(f):
+    return [type(st.impl).__name__ for st in f.vm.executor.program.steps]
+
+
+def test_cfg2_is_one_fused_kernel():
+    pytensor.config.floatX = "float32"
+    ins, outs, mk, meta = W.cfg2_fused_elemwise(4096)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert _steps(f) == ["ElemwiseReduceNode"]
+    prog = f.vm.executor.program.steps[0].impl.ew.prog
+    assert len(prog.insts) == 32 and prog.n_transcendental() == 2  # the "32-op" graph, HBM-bound by construction
+    assert trace_function(f, mk()) == 1
+    assert meta["bytes"] == 201342976
+
+
+def test_cfg1_readme_has_gemv():
+    ins, outs, mk, _ = W.cfg1_readme(128)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert "GemvNode" in _steps(f)
+    assert trace_function(f, mk()) >= 2
+
+
+def test_cfg3_keeps_blas_ops_and_uses_the_tensor_core_mode():
+    pytensor.config.floatX = "float32"
+    ins, outs, mk, _ = W.cfg3_mlp(512)
+    f = pytensor.function(ins, outs, mode="CUDA_BF16")
+    names = _steps(f)
+    assert names.count("Dot22Node") == 3
+    assert all(st.impl.precision == 1 for st in f.vm.executor.program.steps if type(st.impl).__name__ == "Dot22Node")
+    trace_function(f, mk())
+
+
+def test_cfg4_scan_lowers_to_the_persistent_kernel():
+    pytensor.config.floatX = "float32"
+    ins, outs, mk, _ = W.cfg4_scan(256, 64, 100)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert "ScanFusedElemwiseNode" in _steps(f)
+    assert trace_function(f, mk()) == 1  # ONE launch for all 100 steps
+    ins, outs, mk, _ = W.cfg4_scan(64, 64, 10, matmul=True)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert "ScanNode" in _steps(f)
+    trace_function(f, mk())
+
+
+def test_cfg5_and_metric_graph_lower():
+    pytensor.config.floatX = "float32"
+    ins, outs, mk, _ = W.cfg5_logp_grad(B=256, n=64, J=8, K=4)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    names = _steps(f)
+    assert "TakeNode" in names and "PutNode" in names and "GemmNode" in names
+    trace_function(f, mk())
+    ins, outs, mk, _ = W.metric_graph(n=16, layers=84, scan_steps=16)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert len(f.maker.fgraph.toposort()) >= 256
+    trace_function(f, mk())
+
+
+def test_unsupported_ops_fail_at_compile_time_not_at_run_time():
+    x = pt.dmatrix("x")
+    with pytest.raises(NotImplementedError, match="no sm_100a implementation"):
+        pytensor.function([x], pt.linalg.inv(x), mode="CUDA")
+    c = pt.zmatrix("c")
+    with pytest.raises(NotImplementedError):
+        pytensor.function([c], c * 2, mode="CUDA")
+
+
+def test_running_without_a_gpu_raises():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pytensor_b200.runtime.lib import PtkError
+
+    x = pt.dvector("x")
+    f = pytensor.function([x], x * 2, mode="CUDA")
+    with pytest.raises(PtkError, match="no CPU fallback"):
+        f(np.ones(3))
+
+
+def test_scalar_table_matches_reference_through_host_emulation(tmp_path):
+    """The generated scalar body is plain C++: compile it for the host with a shim for the few device intrinsics and
+    compare against the reference C linker on the same inputs (validates the codegen table without a GPU)."""
+    import ctypes
+    import subprocess
+
+    from pytensor_b200.codegen.scalar import CTYPE, emit_body
+
+    pytensor.config.floatX = "float32"
+    a, b = pt.fvector("a"), pt.fvector("b")
+    i = pt.lvector("i")
+    out = [pt.tanh(a * b) + pt.exp(-pt.abs(b)) * pt.maximum(a, b) - pt.switch(a > b, pt.sqr(a), pt.log1p(pt.abs(b))),
+           pt.sigmoid(a) + pt.softplus(b) + pt.erf(a) + pt.cast(i // 3 + i % 5, "float32") + pt.sign(a) * pt.floor(b)]
+    f = pytensor.function([a, b, i], out, mode="CUDA")
+    f_ref = pytensor.function([a, b, i], out, mode="CVM")
+    steps = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "ElemwiseNode"]
+    assert len(steps) == 1
+    prog = steps[0].prog
+    shim = r"""
+#include <cmath>
+#include <cstring>
+#include <cstdint>
+#define __device__
+#define __forceinline__ inline
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline double __longlong_as_double(long long v) { double f; std::memcpy(&f, &v, 8); return f; }
+static inline float ptk_max_nan_f32(float a, float b) { return (b > a) ? b : ((a >= b) ? a : NAN); }
+static inline float ptk_min_nan_f32(float a, float b) { return (b < a) ? b : ((a <= b) ? a : NAN); }
+using std::isnan; using std::isinf;
+template <typename T> static inline T ptk_floordiv(T x, T y) { if (y == 0) return 0; T q = x / y; if ((x % y != 0) && ((x < 0) != (y < 0))) --q; return q; }
+template <typename T> static inline T ptk_imod_py(T x, T y) { if (y == 0) return 0; T r = x % y; if (r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
+template <typename T> static inline T ptk_fmod_py(T x, T y) { T r = std::fmod(x, y); if (r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
+"""
+    ins_decl = ", ".join(f"const {CTYPE[d]}* i{k}" for k, d in enumerate(prog.in_dtypes))
+    outs_decl = ", ".join(f"{CTYPE[d]}* o{k}" for k, d in enumerate(prog.out_dtypes))
+    call = ", ".join([f"i{k}[n]" for k in range(len(prog.in_dtypes))] + [f"o{k}[n]" for k in range(len(prog.out_dtypes))])
+    src = shim + emit_body(prog) + f'\nextern "C" void run(long long N, {ins_decl}, {outs_decl}) {{ for (long long n = 0; n < N; ++n) ptk_body({call}); }}\n'
+    cpp = tmp_path / "body.cpp"
+    cpp.write_text(src)
+    so = tmp_path / "body.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", str(cpp), "-o", str(so)], check=True)
+    L = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(91)
+    N = 4000
+    av, bv = rng.standard_normal(N).astype("float32") * 3, rng.standard_normal(N).astype("float32") * 3
+    iv = rng.integers(-40, 40, size=N)
+    order = [x.name for x in f.maker.fgraph.inputs]
+    vals = {"a": av, "b": bv, "i": iv}
+    node_inputs = [v for v in f.maker.fgraph.toposort() if type(v.op).__name__ == "Elemwise"][0].inputs
+    arrays = []
+    for v in node_inputs:
+        src_name = v.name if v.name in vals else None
+        assert src_name is not None, f"unexpected Elemwise input {v} (graph inputs {order})"
+        arrays.append(np.ascontiguousarray(vals[src_name]))
+    outs_np = [np.empty(N, dtype=d) for d in prog.out_dtypes]
+    L.run(ctypes.c_longlong(N), *[x.ctypes.data_as(ctypes.c_void_p) for x in arrays],
+          *[x.ctypes.data_as(ctypes.c_void_p) for x in outs_np])
+    ref = f_ref(av, bv, iv)
+    node_outs = [v for v in f.maker.fgraph.toposort() if type(v.op).__name__ == "Elemwise"][0].outputs
+    for k, o in enumerate(node_outs):
+        j = f.maker.fgraph.outputs.index(o)
+        np.testing.assert_allclose(outs_np[k], ref[j], rtol=2e-6, atol=2e-6)
