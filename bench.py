@@ -178,6 +178,40 @@ def extra_workloads(pytensor, W, cuda_mode, dev, torch, peaks):
     return out
 
 
+def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10, B_local=1 << 17):
+    """BASELINE.json configs[4]: hierarchical logp+grad, batch = world x 2^17 independent parameter vectors (2^20 at 8
+    GPUs), sharded along the batch axis, ONE packed NCCL all-reduce of [logp, grads] (75 floats) per evaluation."""
+    from pytensor_b200.sharded import ShardedSum
+
+    ins, outs, make_args, meta = W.cfg5_logp_grad(B=B_local * world, n=1024, J=64, K=8, dtype="float32")
+    f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True), trust_input=True)
+    local = [dev.to_device(a) for a in make_args(seed=20 + rank, B_local=B_local)]
+    sh = ShardedSum(f, batch_arg_idx=[0, 1, 2, 3])
+    for _ in range(4):
+        res = sh(*local, presharded=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = sh(*local, presharded=True)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    logp = float(dev.to_host(res[0]))
+    return {"evals_per_s": steps / (ms * 1e-3), "ms_per_eval": ms / steps, "chains_per_s": B_local * world * steps / (ms * 1e-3),
+            "global_batch": B_local * world, "per_gpu_batch": B_local, "n_rows": 1024, "allreduce_floats": 1 + meta["P"],
+            "scaling": "weak (2^17 chains per GPU; 2^20 at 8 GPUs)", "nodes": len(f.maker.fgraph.toposort()),
+            "logp_sum": logp, "graph_replay": bool(f.vm.executor.last_from_graph)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +220,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the batch-sharded logp+grad graph (configs[4])")
     ap.add_argument("--extra", action="store_true", help="also time cfg3/cfg4 and report them under 'others'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -322,8 +357,14 @@ def main():
                          "config.openmp=False)", "env": cvm.describe()}
 
     others = None
-    if args.extra and rank == 0:
+    if args.extra and rank == 0 and world == 1:
         others = extra_workloads(pytensor, W, cuda_mode, dev, torch, peaks)
+    sharded = None
+    if not args.no_sharded:
+        try:
+            sharded = sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank)
+        except Exception as e:  # noqa: BLE001
+            sharded = {"error": repr(e)[:400]}
 
     line = {
         "metric": "fn evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -339,6 +380,8 @@ def main():
     }
     if others is not None:
         line["others"] = others
+    if sharded is not None:
+        line["sharded_logp"] = sharded
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

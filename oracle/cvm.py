@@ -34,11 +34,11 @@ def configure(floatX=None):
         keys = {f.split("=")[0] for f in flags}
         if "base_compiledir" not in keys:
             flags.append("base_compiledir=" + os.environ.get("PTK_COMPILEDIR", f"/tmp/ptk_compiledir_{os.getuid()}"))
-        if "blas__ldflags" not in keys and "pytensor" not in sys.modules:
+        if "pytensor" not in sys.modules:
             d, lib = _find_blas()
             if d:
                 # the wheel's OpenBLAS needs its sibling libgfortran/libquadmath: preload them by path so that the
-                # C linker's modules resolve them by SONAME without LD_LIBRARY_PATH
+                # C linker's modules resolve them by SONAME without LD_LIBRARY_PATH (also when the flag was inherited)
                 import ctypes
 
                 ok = True
@@ -48,7 +48,7 @@ def configure(floatX=None):
                             ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
                         except OSError:
                             ok = False
-                if ok:
+                if ok and "blas__ldflags" not in keys:
                     flags.append(f"blas__ldflags=-L{d} -l:{lib}")
         os.environ["PYTENSOR_FLAGS"] = ",".join(flags)
         ref = os.path.join(REPO, "baseline", "_ref")

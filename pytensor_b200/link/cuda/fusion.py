@@ -12,7 +12,8 @@ from __future__ import annotations
 
 
 def fuse_steps(steps, output_slots, opts):
-    from pytensor_b200.link.cuda.fusion_passes import fuse_elemwise_reduce
+    from pytensor_b200.link.cuda.fusion_passes import fuse_elemwise_reduce, fuse_gemm_epilogue
 
+    steps = fuse_gemm_epilogue(steps, output_slots, opts)
     steps = fuse_elemwise_reduce(steps, output_slots, opts)
     return steps

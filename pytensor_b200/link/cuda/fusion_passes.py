@@ -2,8 +2,69 @@
 
 from __future__ import annotations
 
+from pytensor_b200.vm.nodes_blas import Dot22Node, GemmBiasActNode
 from pytensor_b200.vm.nodes_elemwise import CAReduceNode, ElemwiseNode, ElemwiseReduceNode
 from pytensor_b200.vm.vm import Step
+
+
+def _bias_act_pattern(ew: ElemwiseNode):
+    """(dot_input_idx, bias_input_idx, act) if `ew` computes act(i_dot + i_bias) with a (1,N)-broadcast bias."""
+    p = ew.prog
+    if ew.ndim != 2 or len(p.in_dtypes) != 2 or len(p.out_dtypes) != 1 or len(set(p.in_dtypes + p.out_dtypes)) != 1:
+        return None
+    ops = [i.op for i in p.insts]
+    if ops not in (["Add"], ["Add", "Tanh"]):
+        return None
+    add = p.insts[0]
+    if sorted(add.args) != [("i", 0), ("i", 1)]:
+        return None
+    if len(ops) == 2 and (p.insts[1].args != [("t", 0)] or p.outputs != [("t", 1)]):
+        return None
+    if len(ops) == 1 and p.outputs != [("t", 0)]:
+        return None
+    bc = ew.in_bcast
+    if bc[0] == (False, False) and bc[1] == (True, False):
+        d, b = 0, 1
+    elif bc[1] == (False, False) and bc[0] == (True, False):
+        d, b = 1, 0
+    else:
+        return None
+    return d, b, (1 if len(ops) == 2 else 0)
+
+
+def fuse_gemm_epilogue(steps, output_slots, opts):
+    """Dot22 -> Elemwise{act(x + bias)} (the only reader of the product) ==> one GemmBiasActNode step (K5)."""
+    readers = {}
+    for i, st in enumerate(steps):
+        for s in st.ins:
+            readers.setdefault(s, []).append(i)
+    outset = set(output_slots)
+    drop, repl = set(), {}
+    for i, st in enumerate(steps):
+        if type(st.impl) is not Dot22Node or st.impl.scalar:
+            continue
+        s = st.outs[0]
+        rd = readers.get(s, [])
+        if len(rd) != 1 or s in outset:
+            continue
+        j = rd[0]
+        ew = steps[j]
+        if type(ew.impl) is not ElemwiseNode:
+            continue
+        pat = _bias_act_pattern(ew.impl)
+        if pat is None or ew.ins[pat[0]] != s or ew.impl.prog.out_dtypes[0] != st.impl.dtype:
+            continue
+        # the Elemwise must come after the Dot22 and nothing between them may produce the bias later than the Dot22
+        bias_slot = ew.ins[pat[1]]
+        producers = {o: k for k, t in enumerate(steps) for o in t.outs}
+        if producers.get(bias_slot, -1) > i:
+            continue
+        node = GemmBiasActNode(st.impl.dtype, st.impl.precision, pat[2], name=f"{st.impl.name}+{ew.impl.name}[fused epilogue]")
+        repl[i] = Step(node, [st.ins[0], st.ins[1], bias_slot], list(ew.outs), origin=ew.origin)
+        drop.add(j)
+    if not repl:
+        return steps
+    return [repl.get(i, st) for i, st in enumerate(steps) if i not in drop]
 
 
 def fuse_elemwise_reduce(steps, output_slots, opts):

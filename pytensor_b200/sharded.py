@@ -1,0 +1,92 @@
+"""Batch-sharded evaluation across GPUs (BASELINE.json configs[4]).
+
+Independent evaluations (PyMC-style logp+grad over chains) are split along the batch axis into `world` contiguous
+shards, one process per GPU; every rank runs the SAME compiled function on its shard and produces batch-summed partials
+`[logp, grads...]`; ONE all-reduce (sum) of the packed partials makes the result valid on every rank.  The reference has
+no distributed code at all, so there is no reference interface to mirror: this is host-side plumbing
+over `torch.distributed` (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced split of range(n): the first n % world ranks get one extra item."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_args(args, batch_arg_idx, world, rank):
+    """Slice the batch-axis (dim 0) arguments for this rank; replicate the others."""
+    out = list(args)
+    n = None
+    for i in batch_arg_idx:
+        ni = args[i].shape[0]
+        if n is None:
+            n = ni
+        elif ni != n:
+            raise ValueError("batch arguments disagree on the batch size")
+        lo, hi = shard_bounds(ni, world, rank)
+        out[i] = args[i][lo:hi]
+    return out
+
+
+class ShardedSum:
+    """Callable wrapper: `f_local(*local_args) -> list of batch-summed partial outputs` on each rank, then one packed
+    all-reduce.  Works for NumPy outputs (CPU/gloo) and device tensors (NCCL)."""
+
+    def __init__(self, f_local, batch_arg_idx, group=None):
+        import torch.distributed as dist
+
+        self.f = f_local
+        self.batch_arg_idx = list(batch_arg_idx)
+        self.group = group
+        self.dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._buf = None
+
+    def local_args(self, args):
+        return shard_args(args, self.batch_arg_idx, self.world, self.rank)
+
+    def reduce(self, outs):
+        """Pack -> all_reduce(sum) -> unpack. One collective per evaluation regardless of the number of outputs."""
+        import torch
+
+        if self.world == 1:
+            return outs
+        sizes = [int(np.prod(o.shape)) if len(o.shape) else 1 for o in outs]
+        total = sum(sizes)
+        if isinstance(outs[0], torch.Tensor):
+            from pytensor_b200.runtime import device as dev
+
+            if self._buf is None or self._buf.numel() != total or self._buf.dtype != outs[0].dtype:
+                self._buf = torch.empty((total,), dtype=outs[0].dtype, device=outs[0].device)
+            pos = 0
+            for o, n in zip(outs, sizes):
+                dev.copy_strided(self._buf[pos:pos + n].view(o.shape), o)
+                pos += n
+            self.dist.all_reduce(self._buf, op=self.dist.ReduceOp.SUM, group=self.group)
+            res, pos = [], 0
+            for o, n in zip(outs, sizes):
+                res.append(self._buf[pos:pos + n].view(o.shape))
+                pos += n
+            return res
+        flat = torch.from_numpy(np.concatenate([np.asarray(o, dtype=np.float64).reshape(-1) for o in outs]))
+        self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        res, pos = [], 0
+        flat = flat.numpy()
+        for o, n in zip(outs, sizes):
+            res.append(flat[pos:pos + n].reshape(np.shape(o)).astype(np.asarray(o).dtype))
+            pos += n
+        return res
+
+    def __call__(self, *args, presharded=False):
+        local = list(args) if presharded else self.local_args(args)
+        outs = self.f(*local)
+        if not isinstance(outs, list | tuple):
+            outs = [outs]
+        return self.reduce(list(outs))

@@ -192,3 +192,25 @@ class DotNode(Node):
                 gemv(self.dtype, 1.0, Am, B, 0.0, out)
             return [Val(d=out.view(()))]
         raise NotImplementedError(f"Dot with ndims {A.dim()},{B.dim()}")
+
+
+class GemmBiasActNode(Node):
+    """K5: Dot22 followed by Elemwise{act(x + bias_row)} as ONE launch (epilogue of the GEMM kernel).  The reference
+    leaves these as two nodes (`Dot22` then `Composite{tanh(i0 + i1)}`); fused by the linker-level
+    peephole in link/cuda/fusion_passes.py.  Inputs: A, B, bias (1, N) row; act: 0 none, 1 tanh."""
+
+    def __init__(self, dtype, precision, act, name="Dot22+bias+act"):
+        self.dtype, self.precision, self.act, self.name = dtype, precision, act, name
+
+    def run(self, vals):
+        A, B, bias = vals[0].dev(), vals[1].dev(), vals[2].dev()
+        M, N = A.shape[0], B.shape[1]
+        if bias.shape[-1] != N:
+            raise ValueError(f"{self.name}: bias of shape {tuple(bias.shape)} does not match N={N}")
+        b1 = bias.reshape(-1) if bias.is_contiguous() else dev.contiguous(bias).reshape(-1)
+        out = dev.empty((M, N), self.dtype)
+        if out.numel():
+            if A.shape[1] == 0:
+                raise NotImplementedError("fused bias epilogue with K == 0")
+            gemm(self.dtype, 1.0, A, B, 0.0, out, self.precision, bias=b1, act=self.act)
+        return [Val(d=out)]

@@ -38,9 +38,13 @@ def test_cfg3_keeps_blas_ops_and_uses_the_tensor_core_mode():
     ins, outs, mk, _ = W.cfg3_mlp(512)
     f = pytensor.function(ins, outs, mode="CUDA_BF16")
     names = _steps(f)
-    assert names.count("Dot22Node") == 3
-    assert all(st.impl.precision == 1 for st in f.vm.executor.program.steps if type(st.impl).__name__ == "Dot22Node")
+    # BlasOpt kept (3 x Dot22), each fused with its bias+tanh Elemwise into one tensor-core launch (K5)
+    assert names.count("GemmBiasActNode") == 3 and "ElemwiseNode" not in names
+    assert all(st.impl.precision == 1 and st.impl.act == 1 for st in f.vm.executor.program.steps
+               if type(st.impl).__name__ == "GemmBiasActNode")
     trace_function(f, mk())
+    f2 = pytensor.function(ins, outs, mode=__import__("pytensor_b200").link.cuda.cuda_mode(fuse=False))
+    assert _steps(f2).count("Dot22Node") == 3
 
 
 def test_cfg4_scan_lowers_to_the_persistent_kernel():
