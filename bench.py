@@ -175,6 +175,26 @@ def extra_workloads(pytensor, W, cuda_mode, dev, torch, peaks):
         out["cfg4_scan_general_loop"] = {"evals_per_s": 1e3 / mse, "ms": mse}
     except Exception as e:  # noqa: BLE001
         out["cfg4_scan_persistent"] = {"error": repr(e)[:300]}
+    try:  # the metric graph of BASELINE.json: 265 compiled nodes (84 x Dot22+tanh(+bias), 16-step Scan, Sum)
+        for n, kw, steps in ((64, {}, 50), (1024, {"gemm_precision": "bf16"}, 10)):
+            ins, outs, make_args, meta = W.metric_graph(n=n)
+            f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True, **kw),
+                                  trust_input=True)
+            a = [dev.to_device(x) for x in make_args()]
+            ms = _time_dev(f, a, torch, steps, 4)
+            nn = len(f.maker.fgraph.toposort())
+            out[f"metric_graph_n{n}"] = {"evals_per_s": 1e3 / ms, "ms": ms, "compiled_nodes": nn,
+                                         "launches_per_eval_after_fusion": len(f.vm.executor.program.steps),
+                                         "us_per_compiled_node": 1e3 * ms / nn,
+                                         "cuda_graph_replay": bool(f.vm.executor.last_from_graph)}
+            if n == 64:
+                f_ref = pytensor.function(ins, outs, mode="CVM", trust_input=True)
+                from oracle import cvm as _cvm
+
+                evs, k = _cvm.time_function(f_ref, make_args(), min_seconds=2.0, min_calls=5, max_calls=2000)
+                out["metric_graph_n64"]["cpu_reference_evals_per_s"] = evs
+    except Exception as e:  # noqa: BLE001
+        out["metric_graph"] = {"error": repr(e)[:300]}
     return out
 
 

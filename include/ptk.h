@@ -96,6 +96,14 @@ ptk_status   ptk_take(void* out, const void* src, const int64_t* idx, int64_t ou
 ptk_status   ptk_put(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
                      int64_t inner, int dtype, int op, int* err_flag, void* stream);
 
+/* Row-batched scatter-ADD along the last axis with ONE index vector shared by all rows: dst[o, idx[j]] += y[o, j]
+ * (dst (outer, n_dst) and y (outer, n_idx) contiguous; float32/float64).  A deterministic segmented reduction — sources are
+ * accumulated in ascending j per destination, the same order as np.add.at (tensor/subtensor.py:2513-2531) — instead of
+ * atomics.  `workspace` (ptk_put_rows_workspace_bytes) holds the CSR of `idx` built on the device each call. */
+size_t       ptk_put_rows_workspace_bytes(int64_t n_dst, int64_t n_idx);
+ptk_status   ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
+                          int dtype, void* workspace, size_t workspace_bytes, int* err_flag, void* stream);
+
 /* ---- BLAS family (A5/A6: Gemm tensor/blas/gemm.py:76, Dot22 :248, Dot22Scalar :298, Gemv tensor/blas/gemv.py:16,
  *      Ger tensor/blas/ger.py:8; the C linker calls sgemm_/dgemm_/sgemv_/dgemv_ at blas/c_code/codegen.py:463-805) */
 /* C[M,N] = alpha * A[M,K] @ B[K,N] + beta * C, arbitrary element strides, dtype PTK_F32 | PTK_F64.
@@ -112,6 +120,17 @@ ptk_status   ptk_gemm_bias_act(int dtype, int64_t M, int64_t N, int64_t K,
                       const void* A, int64_t sa0, int64_t sa1, const void* B, int64_t sb0, int64_t sb1,
                       const void* bias, int act, void* C, int64_t sc0, int64_t sc1,
                       int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* Extended tensor-core entry point (fp32 graphs, bf16 operands, fp32 TMEM accumulation):
+ *   C = act(alpha * A @ B + beta * C + bias[N]);
+ * A comes either as fp32 (A_f32, element strides sa0/sa1; staged to bf16 in the workspace) or ALREADY staged as bf16
+ * (A_bf16: row-major [M,K], pitch lda_bf16 elements (multiple of 8), 16-byte aligned) — e.g. the C_bf16 copy a previous
+ * call emitted, so that a chain of layers re-stages only the weights.  C_bf16 (optional, row-major pitch ldc_bf16) receives
+ * a bf16 copy of the result.  Environment PTK_GEMM_CLUSTER=1 selects the single-CTA kernel instead of the 2-CTA-cluster
+ * kernel with TMA multicast of the shared B tile. */
+ptk_status   ptk_gemm_tc_ex(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0, int64_t sa1,
+                      const void* A_bf16, int64_t lda_bf16, const void* B_f32, int64_t sb0, int64_t sb1, double beta,
+                      void* C, int64_t sc0, int64_t sc1, const void* bias, int act, void* C_bf16, int64_t ldc_bf16,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

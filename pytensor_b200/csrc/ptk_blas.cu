@@ -94,11 +94,122 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int64_t M, int64_t N, in
   }
 }
 
+// ---- skinny shapes (PyMC-style regressions: (B x K)(K x n) with K ~ 8 and (B x n)(n x K)): HBM-bound on the big operand --------
+constexpr int SK_MAXK = 16;
+// K <= 16, B and C unit-stride along N: a thread keeps its K x 4 slab of B in registers and streams rows of A / C.
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
+                                                          int64_t sa0, int64_t sa1, const T* __restrict__ B, int64_t sb0,
+                                                          T beta, T* __restrict__ C, int64_t sc0) {
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
+  const int64_t n0 = ((int64_t)blockIdx.x * 64 + tx) * 4;
+  if (n0 >= N) return;
+  T b[SK_MAXK][4];
+#pragma unroll
+  for (int k = 0; k < SK_MAXK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + n0 + j] : T(0);
+  for (int64_t m = (int64_t)blockIdx.y * 4 + ty; m < M; m += (int64_t)gridDim.y * 4) {
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = 0; k < SK_MAXK; ++k) {
+      if (k < K) {
+        const T a = A[m * sa0 + k * sa1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += a * b[k][j];
+      }
+    }
+    T* c = C + m * sc0 + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + j < N) {
+        T v = alpha * acc[j];
+        if (beta != T(0)) v += beta * c[j];
+        c[j] = v;
+      }
+    }
+  }
+}
+
+constexpr int SN_MAXN = 16;
+// N <= 16, A unit-stride along K: one warp per row of A, B (K x N) staged in shared memory in K-chunks.
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int N, int64_t K, T alpha, const T* __restrict__ A,
+                                                          int64_t sa0, const T* __restrict__ B, int64_t sb0, int64_t sb1,
+                                                          T beta, T* __restrict__ C, int64_t sc0, int64_t sc1) {
+  constexpr int KC = 256;
+  __shared__ T Bs[KC][SN_MAXN + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t rows_per_block = 8 * 4;  // 8 warps x 4 rows each
+  const int64_t m_base = (int64_t)blockIdx.x * rows_per_block + warp * 4;
+  T acc[4][SN_MAXN];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) acc[r][n] = T(0);
+  for (int64_t k0 = 0; k0 < K; k0 += KC) {
+    const int kc = (int)min((int64_t)KC, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kc * N; e += blockDim.x) {
+      int k = e / N, n = e - k * N;
+      Bs[k][n] = B[(k0 + k) * sb0 + n * sb1];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t m = m_base + r;
+      if (m < M) {
+        const T* arow = A + m * sa0 + k0;
+        for (int k = lane; k < kc; k += 32) {
+          const T a = arow[k];
+#pragma unroll
+          for (int n = 0; n < SN_MAXN; ++n)
+            if (n < N) acc[r][n] += a * Bs[k][n];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t m = m_base + r;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) {
+      if (n < N) {
+        T v = acc[r][n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && m < M) {
+          T* c = C + m * sc0 + n * sc1;
+          T out = alpha * v;
+          if (beta != T(0)) out += beta * (*c);
+          *c = out;
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void* A, int64_t sa0, int64_t sa1,
                        const void* B, int64_t sb0, int64_t sb1, double beta, void* C, int64_t sc0, int64_t sc1,
                        const void* bias, int act, cudaStream_t st) {
   if (M == 0 || N == 0) return PTK_OK;
+  const int sms = std::max(1, ptk::sm_count());
+  if (bias == nullptr && act == 0 && K >= 1 && K <= SK_MAXK && sb1 == 1 && sc1 == 1 && M >= 256 && N >= 64) {
+    unsigned gx = (unsigned)((N + 255) / 256);
+    unsigned gy = (unsigned)std::min<int64_t>((M + 3) / 4, std::max<int64_t>(1, (int64_t)sms * 8 / gx));
+    gemm_smallk_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, (const T*)B, sb0,
+                                                       (T)beta, (T*)C, sc0);
+    PTK_LAUNCH_CHECK("gemm_smallk");
+    return PTK_OK;
+  }
+  if (bias == nullptr && act == 0 && N <= SN_MAXN && sa1 == 1 && M >= 256 && K >= 64) {
+    unsigned gx = (unsigned)std::min<int64_t>((M + 31) / 32, 2147483647LL);
+    gemm_smalln_kernel<T><<<gx, 256, 0, st>>>(M, (int)N, K, (T)alpha, (const T*)A, sa0, (const T*)B, sb0, sb1, (T)beta,
+                                              (T*)C, sc0, sc1);
+    PTK_LAUNCH_CHECK("gemm_smalln");
+    return PTK_OK;
+  }
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
   if (grid.y > 65535) return ptk::fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: M too large for the SIMT path");
   bool akf = (sa1 == 1) || K == 1, bnf = (sb1 == 1) || N == 1;

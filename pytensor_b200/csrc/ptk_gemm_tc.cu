@@ -9,6 +9,7 @@
 // pytensor/tensor/type.py:40-55), operands are rounded to bf16 by a conversion pass into a caller-owned workspace
 // (A as [M,K] K-major, B transposed to [N,K] K-major), products accumulate in fp32.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "ptk_common.h"
 
@@ -68,6 +69,23 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -93,6 +111,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -134,8 +158,16 @@ struct EpiParams {
   const float* bias;
   int act;
   int M, N, K;
+  __nv_bfloat16* Cbf;  // optional bf16 copy of the result, row-major [M, ldcbf] (the next layer's K-major A operand)
+  long long ldcbf;
 };
 
+// kCluster == 2: CTA pairs (cluster 2x1x1) share the B tile of a 256-row super-tile — each CTA loads HALF of it and
+// TMA-multicasts that half into both CTAs' shared memory, cutting the L2->SM traffic per CTA from 48 to 32 KiB per
+// k-block (the single-CTA kernel is L2-bandwidth bound: 1.6 GB per 4096^3 GEMM at ~12 TB/s).  A shared-memory stage
+// may be refilled only when BOTH CTAs' MMAs have drained it: the stage's "empty" barrier counts 2 arrivals and every
+// tcgen05.commit is multicast to the pair.
+template <int kCluster>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -151,8 +183,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
+  // work decomposition: a "unit" is kCluster vertically adjacent M-tiles of one N-tile; units are dealt round-robin
+  const int m_groups = (m_tiles + kCluster - 1) / kCluster;
+  const int num_units = m_groups * n_tiles;
+  const int unit0 = blockIdx.x / kCluster, unit_stride = gridDim.x / kCluster;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -161,7 +197,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCluster);
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -172,6 +208,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -180,13 +217,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int tm = t % m_tiles, tn = t / m_tiles;
+      for (int u = unit0; u < num_units; u += unit_stride) {
+        const int tm = (u % m_groups) * kCluster + (int)crank, tn = u / m_groups;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, tm * BLOCK_M);
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, tn * BLOCK_N);
+          if (kCluster == 1) {
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, tn * BLOCK_N);
+          } else {
+            constexpr uint32_t HALF = B_STAGE_BYTES / 2;  // 128 rows of the B tile
+            tma_load_2d_mc(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + crank * HALF, kb * BLOCK_K,
+                           tn * BLOCK_N + (int)crank * (BLOCK_N / 2), (uint16_t)0x3);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -199,7 +242,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = unit0; u < num_units; u += unit_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
@@ -214,7 +257,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2);
             umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in both CTAs of the pair when the B tile is shared)
+          if (kCluster == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -226,8 +271,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tm = t % m_tiles, tn = t / m_tiles;
+    for (int u = unit0; u < num_units; u += unit_stride) {
+      const int tm = (u % m_groups) * kCluster + (int)crank, tn = u / m_groups;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)tm * BLOCK_M + q * 32 + lane;
@@ -255,6 +300,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 vv[e] = x;
               }
               *reinterpret_cast<float4*>(crow + col0 + j) = v;
+              if (p.Cbf) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(p.Cbf + row * p.ldcbf + col0 + j) = pk;
+              }
             }
           } else {
 #pragma unroll
@@ -267,6 +319,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (p.bias) x += p.bias[col];
                 if (p.act == 1) x = tanhf(x);
                 *dst = x;
+                if (p.Cbf) p.Cbf[row * p.ldcbf + col] = __float2bfloat16_rn(x);
               }
             }
           }
@@ -280,6 +333,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // nobody leaves while the peer may still multicast into / signal this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -338,42 +392,98 @@ size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K) {
   return (size_t)(round_up(M * Kp * 2, 256) + round_up(N * Kp * 2, 256) + 256);
 }
 
-ptk_status gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
-                   const float* B, int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1,
-                   const float* bias, int act, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+static int g_cluster = -1;  // -1: read PTK_GEMM_CLUSTER once (default 2)
+
+// A_f32 (any strides) OR A_bf16 (row-major, pitch lda_bf16 elements, multiple of 8, 16-byte aligned base) must be given.
+ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
+                      const void* A_bf16, int64_t lda_bf16, const float* B, int64_t sb0, int64_t sb1, float beta, float* C,
+                      int64_t sc0, int64_t sc1, const float* bias, int act, void* C_bf16, int64_t ldc_bf16, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
   if (M == 0 || N == 0) return PTK_OK;
   if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) return fail(PTK_ERR_ARG, "gemm_tc: dims exceed int32");
   if (workspace == nullptr || workspace_bytes < gemm_tc_workspace(M, N, K))
     return fail(PTK_ERR_ARG, "gemm_tc: workspace too small (see ptk_gemm_workspace_bytes)");
+  if (g_cluster < 0) {
+    const char* e = getenv("PTK_GEMM_CLUSTER");
+    g_cluster = (e && e[0] == '1') ? 1 : 2;
+  }
   const long long Kp = round_up(K, 8);
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   __nv_bfloat16* Abf = reinterpret_cast<__nv_bfloat16*>(w);
   __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(w + round_up(M * Kp * 2, 256));
-  {
+  long long lda = Kp;
+  if (A_bf16 != nullptr) {
+    if (lda_bf16 % 8 != 0 || ((uintptr_t)A_bf16 & 15) != 0) return fail(PTK_ERR_ARG, "gemm_tc: misaligned bf16 A operand");
+    Abf = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(A_bf16));
+    lda = lda_bf16;
+  } else {
     dim3 ga((unsigned)((K + 31) / 32), (unsigned)((M + 31) / 32));
     convert_bf16_kernel<<<ga, 256, 0, st>>>(A, sa0, sa1, Abf, Kp, M, K);
+  }
+  {
     // B[K,N] -> Bt[N,K]: dst row index = n (source stride sb1), dst col index = k (source stride sb0)
     dim3 gb((unsigned)((K + 31) / 32), (unsigned)((N + 31) / 32));
     convert_bf16_kernel<<<gb, 256, 0, st>>>(B, sb1, sb0, Bbf, Kp, N, K);
     PTK_LAUNCH_CHECK("convert_bf16");
   }
+  const int cluster = g_cluster;
   CUtensorMap ta, tb;
   ptk_status s;
-  if ((s = make_tmap(&ta, Abf, (uint64_t)M, (uint64_t)K, (uint64_t)Kp, BLOCK_M)) != PTK_OK) return s;
-  if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, BLOCK_N)) != PTK_OK) return s;
+  if ((s = make_tmap(&ta, Abf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M)) != PTK_OK) return s;
+  if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, cluster == 2 ? BLOCK_N / 2 : BLOCK_N)) != PTK_OK) return s;
   EpiParams p;
   p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.Cbf = reinterpret_cast<__nv_bfloat16*>(C_bf16);
+  p.ldcbf = ldc_bf16;
   static bool attr_set = false;
   if (!attr_set) {
-    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = std::max(1, std::min(m_tiles * n_tiles, ptk::sm_count()));
-  gemm_bf16_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  const int sms = std::max(2, ptk::sm_count());
+  if (cluster == 2) {
+    const int units = ((m_tiles + 1) / 2) * n_tiles;
+    const int grid = 2 * std::max(1, std::min(units, sms / 2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<2>, ta, tb, p));
+  } else {
+    const int grid = std::max(1, std::min(m_tiles * n_tiles, sms));
+    gemm_bf16_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  }
   PTK_LAUNCH_CHECK("gemm_bf16_tc");
   return PTK_OK;
 }
 
+ptk_status gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
+                   const float* B, int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1,
+                   const float* bias, int act, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  return gemm_tc_ex(M, N, K, alpha, A, sa0, sa1, nullptr, 0, B, sb0, sb1, beta, C, sc0, sc1, bias, act, nullptr, 0, workspace,
+                    workspace_bytes, st);
+}
+
 }  // namespace ptk
+
+extern "C" ptk_status ptk_gemm_tc_ex(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0,
+                                     int64_t sa1, const void* A_bf16, int64_t lda_bf16, const void* B_f32, int64_t sb0,
+                                     int64_t sb1, double beta, void* C, int64_t sc0, int64_t sc1, const void* bias, int act,
+                                     void* C_bf16, int64_t ldc_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (A_f32 == nullptr && A_bf16 == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_gemm_tc_ex: no A operand");
+  return ptk::gemm_tc_ex(M, N, K, (float)alpha, (const float*)A_f32, sa0, sa1, A_bf16, lda_bf16, (const float*)B_f32, sb0, sb1,
+                         (float)beta, (float*)C, sc0, sc1, (const float*)bias, act, C_bf16, ldc_bf16, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}

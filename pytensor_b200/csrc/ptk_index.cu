@@ -145,6 +145,106 @@ __global__ void __launch_bounds__(256) put_kernel(T* __restrict__ dst, const T* 
   }
 }
 
+// take along the LAST axis (inner == 1): out[o, j] = src[o, idx[j]].  A thread owns 4 consecutive j (one 128-bit store per
+// row for 4-byte types) and reuses its 4 indices over ROWS rows; no integer division in the hot loop.
+template <typename T>
+__global__ void __launch_bounds__(256) take_lastaxis_kernel(T* __restrict__ out, const T* __restrict__ src,
+                                                            const int64_t* __restrict__ idx, int64_t outer, int64_t n_src,
+                                                            int64_t n_idx, int* err) {
+  const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j0 >= n_idx) return;
+  int64_t k[4];
+  bool ok[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    ok[e] = j0 + e < n_idx;
+    int64_t v = ok[e] ? idx[j0 + e] : 0;
+    if (v < 0) v += n_src;
+    if (v < 0 || v >= n_src) {
+      if (ok[e] && err) atomicExch(err, 1);
+      ok[e] = false;
+      v = 0;
+    }
+    k[e] = v;
+  }
+  const bool vec = ok[0] && ok[1] && ok[2] && ok[3] && (n_idx % 4 == 0) && sizeof(T) == 4 && (((uintptr_t)out & 15) == 0);
+  for (int64_t o = blockIdx.y; o < outer; o += gridDim.y) {
+    const T* s = src + o * n_src;
+    T* d = out + o * n_idx + j0;
+    if (vec) {
+      uint4 v;
+      v.x = (uint32_t)s[k[0]]; v.y = (uint32_t)s[k[1]]; v.z = (uint32_t)s[k[2]]; v.w = (uint32_t)s[k[3]];
+      *reinterpret_cast<uint4*>(d) = v;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (ok[e]) d[e] = s[k[e]];
+    }
+  }
+}
+
+// ---- scatter-add along the last axis with an index vector shared by all rows: a deterministic segmented reduction ----------
+// (1) histogram + exclusive scan of the destination bins; (2) stable fill of the permutation; (3) one warp per row.
+__global__ void __launch_bounds__(1024) put_rows_offsets_kernel(const int64_t* __restrict__ idx, int64_t n_idx, int64_t n_dst,
+                                                                int* __restrict__ offsets, int* err) {
+  extern __shared__ int cnt[];
+  for (int64_t j = threadIdx.x; j <= n_dst; j += blockDim.x) cnt[j] = 0;
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n_idx; i += blockDim.x) {
+    int64_t k = idx[i];
+    if (k < 0) k += n_dst;
+    if (k < 0 || k >= n_dst) {
+      if (err) atomicExch(err, 1);
+      continue;
+    }
+    atomicAdd(&cnt[k], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int64_t j = 0; j < n_dst; ++j) {
+      int c = cnt[j];
+      offsets[j] = run;
+      run += c;
+    }
+    offsets[n_dst] = run;
+  }
+}
+__global__ void __launch_bounds__(256) put_rows_perm_kernel(const int64_t* __restrict__ idx, int64_t n_idx, int64_t n_dst,
+                                                            const int* __restrict__ offsets, int* __restrict__ perm) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one destination bin per thread
+  if (j >= n_dst) return;
+  int p = offsets[j];
+  for (int64_t i = 0; i < n_idx; ++i) {
+    int64_t k = idx[i];
+    if (k < 0) k += n_dst;
+    if (k == j) perm[p++] = (int)i;  // ascending i: the same accumulation order as np.add.at
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) put_rows_kernel(T* __restrict__ dst, const T* __restrict__ y,
+                                                       const int* __restrict__ offsets, const int* __restrict__ perm,
+                                                       int64_t outer, int64_t n_dst, int64_t n_idx, int warps_per_block) {
+  extern __shared__ unsigned char put_smem[];
+  T* ys = reinterpret_cast<T*>(put_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= warps_per_block) return;
+  T* mine = ys + (int64_t)warp * n_idx;
+  for (int64_t o = (int64_t)blockIdx.x * warps_per_block + warp; o < outer; o += (int64_t)gridDim.x * warps_per_block) {
+    const T* yrow = y + o * n_idx;
+    for (int64_t i = lane; i < n_idx; i += 32) mine[i] = yrow[i];
+    __syncwarp();
+    T* drow = dst + o * n_dst;
+    for (int64_t j = lane; j < n_dst; j += 32) {
+      T acc = drow[j];
+      const int lo = offsets[j], hi = offsets[j + 1];
+      for (int p = lo; p < hi; ++p) acc += mine[perm[p]];
+      drow[j] = acc;
+    }
+    __syncwarp();
+  }
+}
+
 inline unsigned grid_for(int64_t total, int threads = 256) {
   int64_t blocks = (total + threads - 1) / threads;
   int64_t cap = (int64_t)ptk::sm_count() * 16;
@@ -221,6 +321,20 @@ ptk_status ptk_take(void* out, const void* src, const int64_t* idx, int64_t oute
   int64_t total = outer * n_idx * inner;
   if (total == 0) return PTK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (inner == 1 && outer >= 8 && n_idx >= 64) {
+    unsigned gx = (unsigned)((n_idx + 1023) / 1024);
+    unsigned gy = (unsigned)std::min<int64_t>(outer, std::max<int64_t>(1, (int64_t)std::max(1, ptk::sm_count()) * 16 / gx));
+    dim3 grid(gx, gy);
+    switch (itemsize) {
+      case 1: take_lastaxis_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)out, (const uint8_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+      case 2: take_lastaxis_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)out, (const uint16_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+      case 4: take_lastaxis_kernel<uint32_t><<<grid, 256, 0, st>>>((uint32_t*)out, (const uint32_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+      case 8: take_lastaxis_kernel<uint64_t><<<grid, 256, 0, st>>>((uint64_t*)out, (const uint64_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+      default: return fail(PTK_ERR_ARG, "ptk_take: itemsize must be 1, 2, 4 or 8");
+    }
+    PTK_LAUNCH_CHECK("take_lastaxis");
+    return PTK_OK;
+  }
   unsigned g = grid_for(total);
 #define PTK_TAKE(T) \
   take_kernel<T><<<g, 256, 0, st>>>((T*)out, (const T*)src, idx, outer, n_src, n_idx, inner, err_flag); break;
@@ -258,6 +372,34 @@ ptk_status ptk_put(void* dst, const void* y, const int64_t* idx, int64_t outer, 
   }
 #undef PTK_PUT
   PTK_LAUNCH_CHECK("put");
+  return PTK_OK;
+}
+
+size_t ptk_put_rows_workspace_bytes(int64_t n_dst, int64_t n_idx) { return (size_t)(n_dst + 1 + n_idx) * sizeof(int) + 64; }
+
+ptk_status ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx, int dtype,
+                        void* workspace, size_t workspace_bytes, int* err_flag, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (outer == 0 || n_idx == 0) return PTK_OK;
+  if (dtype != PTK_F32 && dtype != PTK_F64) return fail(PTK_ERR_UNSUPPORTED, "ptk_put_rows: dtype must be float32 or float64");
+  const int isz = dtype_size(dtype);
+  if (n_dst + 1 > 12000 || n_idx * isz > 48 * 1024 || n_dst < 1)
+    return fail(PTK_ERR_UNSUPPORTED, "ptk_put_rows: n_dst <= 11999 and n_idx * itemsize <= 48 KiB required");
+  if (workspace == nullptr || workspace_bytes < ptk_put_rows_workspace_bytes(n_dst, n_idx))
+    return fail(PTK_ERR_ARG, "ptk_put_rows: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* offsets = reinterpret_cast<int*>(workspace);
+  int* perm = offsets + (n_dst + 1);
+  put_rows_offsets_kernel<<<1, 1024, (size_t)(n_dst + 1) * sizeof(int), st>>>(idx, n_idx, n_dst, offsets, err_flag);
+  put_rows_perm_kernel<<<(unsigned)((n_dst + 255) / 256), 256, 0, st>>>(idx, n_idx, n_dst, offsets, perm);
+  int wpb = (int)std::max<int64_t>(1, std::min<int64_t>(8, (48 * 1024) / (n_idx * isz)));
+  size_t smem = (size_t)wpb * n_idx * isz;
+  unsigned grid = (unsigned)std::min<int64_t>((outer + wpb - 1) / wpb, (int64_t)std::max(1, ptk::sm_count()) * 8);
+  if (dtype == PTK_F32)
+    put_rows_kernel<float><<<grid, 256, smem, st>>>((float*)dst, (const float*)y, offsets, perm, outer, n_dst, n_idx, wpb);
+  else
+    put_rows_kernel<double><<<grid, 256, smem, st>>>((double*)dst, (const double*)y, offsets, perm, outer, n_dst, n_idx, wpb);
+  PTK_LAUNCH_CHECK("put_rows");
   return PTK_OK;
 }
 

@@ -62,9 +62,22 @@ def fuse_gemm_epilogue(steps, output_slots, opts):
         node = GemmBiasActNode(st.impl.dtype, st.impl.precision, pat[2], name=f"{st.impl.name}+{ew.impl.name}[fused epilogue]")
         repl[i] = Step(node, [st.ins[0], st.ins[1], bias_slot], list(ew.outs), origin=ew.origin)
         drop.add(j)
-    if not repl:
-        return steps
-    return [repl.get(i, st) for i, st in enumerate(steps) if i not in drop]
+    if repl:
+        steps = [repl.get(i, st) for i, st in enumerate(steps) if i not in drop]
+    return mark_bf16_chains(steps)
+
+
+def mark_bf16_chains(steps):
+    """A tensor-core GEMM whose result is the A operand of another tensor-core GEMM also emits a bf16 copy of it
+    (carried as `Val.aux`), so the chain re-stages only the weights (SURVEY.md §8d cfg 3)."""
+    tc = (Dot22Node, GemmBiasActNode)
+    producers = {o: st for st in steps for o in st.outs}
+    for st in steps:
+        if isinstance(st.impl, tc) and st.impl.precision == 1:
+            src = producers.get(st.ins[0])
+            if src is not None and isinstance(src.impl, tc) and src.impl.precision == 1:
+                src.impl.emit_bf16 = True
+    return steps
 
 
 def fuse_elemwise_reduce(steps, output_slots, opts):

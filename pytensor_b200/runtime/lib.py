@@ -67,12 +67,18 @@ SIGNATURES = {
                          c_void_p]),
     "ptk_put": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
                         c_void_p]),
+    "ptk_put_rows_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ptk_put_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p,
+                             c_void_p]),
     "ptk_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "ptk_gemm": (c_int, [c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                          c_int64, c_double, c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "ptk_gemm_bias_act": (c_int, [c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                   c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t,
                                   c_void_p]),
+    "ptk_gemm_tc_ex": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                               c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
+                               c_void_p, c_size_t, c_void_p]),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -98,6 +104,8 @@ class _TraceLib:
             return lambda: 148
         if name == "ptk_gemm_workspace_bytes":
             return lambda M, N, K, p: 2 * (M * K + N * K) + 1024
+        if name == "ptk_put_rows_workspace_bytes":
+            return lambda n_dst, n_idx: 4 * (n_dst + 1 + n_idx) + 64
         if name == "ptk_last_error":
             return lambda: b""
         return lambda *a, **k: 0

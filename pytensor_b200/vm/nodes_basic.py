@@ -377,6 +377,19 @@ class PutNode(Node):
         n = 1
         for s in yshape:
             n *= s
+        isz = x.element_size()
+        if (n and inner == 1 and it.dim() == 1 and not self.set_instead_of_inc and self.dtype in ("float32", "float64")
+                and outer >= 64 and x.shape[ax] + 1 <= 12000 and it.numel() * isz <= 48 * 1024):
+            # many rows share one index vector: deterministic segmented reduction instead of atomics
+            L = _lib.lib()
+            wsb = int(L.ptk_put_rows_workspace_bytes(x.shape[ax], it.numel()))
+            ws = dev.empty_t((wsb,), torch.uint8)
+            flag = _err_flag()
+            _lib.check(L.ptk_put_rows(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, x.shape[ax], it.numel(),
+                                      _lib.DTYPE_CODE[self.dtype], dev.ptr(ws), wsb, dev.ptr(flag), dev.stream_ptr()),
+                       "ptk_put_rows")
+            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
+            return [Val(d=x)]
         if n:
             flag = _err_flag()
             _lib.check(_lib.lib().ptk_put(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, x.shape[ax], it.numel(), inner,

@@ -31,30 +31,43 @@ def _scalar(v: Val) -> float:
     return float(np.asarray(v.host()).reshape(-1)[0])
 
 
-def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0):
-    """C = alpha*A@B + beta*C (or act(A@B + bias) when bias/act given) through the C-ABI."""
+def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None, want_bf16=False):
+    """C = alpha*A@B + beta*C (or act(A@B + bias) when bias/act given) through the C-ABI.
+    Tensor-core path extras: `a_bf16` = an already staged bf16 copy of A (skips the staging pass); `want_bf16` returns a
+    bf16 copy of C (torch.bfloat16 container) for the next layer, else None."""
     M, K = A.shape
     K2, N = B.shape
     if K != K2 or tuple(C.shape) != (M, N):
         raise ValueError(f"gemm: shape mismatch {tuple(A.shape)} @ {tuple(B.shape)} -> {tuple(C.shape)}")
     L = _lib.lib()
     use_tc = precision == 1 and dtype == "float32" and min(M, N, K) >= TC_MIN_DIM
-    ws_ptr, ws_bytes = None, 0
+    code = _lib.DTYPE_CODE[dtype]
+    st = dev.stream_ptr()
     if use_tc:
         ws_bytes = int(L.ptk_gemm_workspace_bytes(M, N, K, 1))
         ws = _get_workspace(ws_bytes)
-        ws_ptr = dev.ptr(ws)
-    code = _lib.DTYPE_CODE[dtype]
-    st = dev.stream_ptr()
+        cbf = None
+        if want_bf16:
+            Np = (N + 7) // 8 * 8
+            cbf = dev.empty_t((M, Np), torch.bfloat16)
+        abf_ptr, lda = None, 0
+        if a_bf16 is not None and a_bf16.shape[0] == M and a_bf16.shape[1] >= K and a_bf16.stride(1) == 1:
+            abf_ptr, lda = dev.ptr(a_bf16), a_bf16.stride(0)
+        _lib.check(L.ptk_gemm_tc_ex(M, N, K, float(alpha), dev.ptr(A), A.stride(0), A.stride(1), abf_ptr, lda, dev.ptr(B),
+                                    B.stride(0), B.stride(1), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
+                                    dev.ptr(bias) if bias is not None else None, act,
+                                    dev.ptr(cbf) if cbf is not None else None, cbf.stride(0) if cbf is not None else 0,
+                                    dev.ptr(ws), ws_bytes, st), "ptk_gemm_tc_ex")
+        return cbf
     if bias is not None or act:
         _lib.check(L.ptk_gemm_bias_act(code, M, N, K, dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B), B.stride(0),
                                        B.stride(1), dev.ptr(bias) if bias is not None else None, act, dev.ptr(C),
-                                       C.stride(0), C.stride(1), 1 if use_tc else 0, ws_ptr, ws_bytes, st),
-                   "ptk_gemm_bias_act")
+                                       C.stride(0), C.stride(1), 0, None, 0, st), "ptk_gemm_bias_act")
     else:
         _lib.check(L.ptk_gemm(code, M, N, K, float(alpha), dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B),
                               B.stride(0), B.stride(1), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
-                              1 if use_tc else 0, ws_ptr, ws_bytes, st), "ptk_gemm")
+                              0, None, 0, st), "ptk_gemm")
+    return None
 
 
 def gemv(dtype, alpha, A, x, beta, y):
@@ -67,6 +80,8 @@ def gemv(dtype, alpha, A, x, beta, y):
 
 
 class Dot22Node(Node):
+    emit_bf16 = False  # set by the fusion pass when the only consumer is another tensor-core GEMM taking this as A
+
     def __init__(self, dtype, precision=0, scalar=False, name="Dot22"):
         self.dtype, self.precision, self.scalar, self.name = dtype, precision, scalar, name
 
@@ -74,13 +89,15 @@ class Dot22Node(Node):
         A, B = vals[0].dev(), vals[1].dev()
         alpha = _scalar(vals[2]) if self.scalar else 1.0
         out = dev.empty((A.shape[0], B.shape[1]), self.dtype)
+        aux = None
         if out.numel():
             if A.shape[1] == 0:
                 _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(),
                                                        dev.stream_ptr()), "memset")
             else:
-                gemm(self.dtype, alpha, A, B, 0.0, out, self.precision)
-        return [Val(d=out)]
+                aux = gemm(self.dtype, alpha, A, B, 0.0, out, self.precision, a_bf16=vals[0].aux,
+                           want_bf16=self.emit_bf16)
+        return [Val(d=out, aux=aux)]
 
 
 class GemmNode(Node):
@@ -199,6 +216,8 @@ class GemmBiasActNode(Node):
     leaves these as two nodes (`Dot22` then `Composite{tanh(i0 + i1)}`); fused by the linker-level
     peephole in link/cuda/fusion_passes.py.  Inputs: A, B, bias (1, N) row; act: 0 none, 1 tanh."""
 
+    emit_bf16 = False
+
     def __init__(self, dtype, precision, act, name="Dot22+bias+act"):
         self.dtype, self.precision, self.act, self.name = dtype, precision, act, name
 
@@ -212,5 +231,7 @@ class GemmBiasActNode(Node):
         if out.numel():
             if A.shape[1] == 0:
                 raise NotImplementedError("fused bias epilogue with K == 0")
-            gemm(self.dtype, 1.0, A, B, 0.0, out, self.precision, bias=b1, act=self.act)
+            aux = gemm(self.dtype, 1.0, A, B, 0.0, out, self.precision, bias=b1, act=self.act, a_bf16=vals[0].aux,
+                       want_bf16=self.emit_bf16)
+            return [Val(d=out, aux=aux)]
         return [Val(d=out)]

@@ -16,11 +16,12 @@ from ..runtime import device as dev
 
 
 class Val:
-    __slots__ = ("h", "d")
+    __slots__ = ("h", "d", "aux")
 
-    def __init__(self, h=None, d=None):
+    def __init__(self, h=None, d=None, aux=None):
         self.h = h
         self.d = d
+        self.aux = aux  # optional device-side companion of `d` (e.g. the bf16 copy a tensor-core GEMM emitted)
 
     # ---- metadata without forcing a transfer ----
     @property

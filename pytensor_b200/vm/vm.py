@@ -192,7 +192,9 @@ class Executor:
                 if isinstance(x, torch.Tensor):
                     vals_in.append(Val(d=x))
                 else:
-                    a = np.ascontiguousarray(np.asarray(x))
+                    a = np.asarray(x)
+                    if not a.flags.c_contiguous:  # (np.ascontiguousarray would also turn a 0-d array into 1-d)
+                        a = np.ascontiguousarray(a)
                     t = dev.empty(a.shape, a.dtype.name)
                     if a.size:
                         _lib.check(L.ptk_memcpy_h2d_async(dev.ptr(t), a.ctypes.data, a.nbytes, sp), "h2d")

@@ -87,3 +87,17 @@ def test_ger(gpu):
     y = pt.dvector("y")
     compare_cuda_and_cvm([A, x, y], [A + 0.3 * pt.outer(x, y)],
                          [rng.standard_normal((40, 50)), rng.standard_normal(40), rng.standard_normal(50)])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_skinny_gemm_shapes(gpu, dtype):
+    # cfg-5 regression shapes: (B x K)(K x n) with K = 8 and (B x n)(n x K) with N = 8 take the HBM-bound skinny kernels
+    rng = np.random.default_rng(27)
+    beta = pt.tensor("beta", dtype=dtype, shape=(None, None))
+    X = pt.tensor("X", dtype=dtype, shape=(None, None))
+    R = pt.tensor("R", dtype=dtype, shape=(None, None))
+    bv = rng.standard_normal((1500, 8)).astype(dtype)
+    Xv = rng.standard_normal((1030, 8)).astype(dtype)
+    Rv = rng.standard_normal((1500, 1030)).astype(dtype)
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == "float32" else dict(rtol=1e-9, atol=1e-9)
+    compare_cuda_and_cvm([beta, X, R], [pt.dot(beta, X.T), pt.dot(R, X), 0.5 * R + 2.0 * pt.dot(beta, X.T)], [bv, Xv, Rv], **tol)

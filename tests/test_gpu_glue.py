@@ -114,3 +114,52 @@ def test_cholesky_and_solve_triangular(gpu):
     f = pytensor.function([A], L, mode="CUDA")
     assert np.all(np.isnan(f(-np.eye(4))))
     del scipy
+
+
+@pytest.mark.parametrize("n,nrhs", [(129, 3), (300, 70), (512, 1)])
+def test_blocked_cholesky_and_solve_triangular(gpu, n, nrhs):
+    # n > 128 takes the blocked (64-wide panel + GEMM trailing update) path
+    rng = np.random.default_rng(36)
+    A = pt.dmatrix("A")
+    b = pt.dmatrix("b")
+    Av = rng.standard_normal((n, n))
+    Av = Av @ Av.T / n + np.eye(n)
+    bv = rng.standard_normal((n, nrhs))
+    L = pt.linalg.cholesky(A)
+    U = pt.linalg.cholesky(A, lower=False)
+    outs = [L, U, pt.linalg.solve_triangular(L, b, lower=True), pt.linalg.solve_triangular(U, b, lower=False),
+            pt.linalg.solve_triangular(L.T, b, lower=False), pt.linalg.solve_triangular(L, b, lower=True,
+                                                                                         unit_diagonal=True)]
+    compare_cuda_and_cvm([A, b], outs, [Av, bv], rtol=1e-7, atol=1e-8)
+    f = pytensor.function([A], L, mode="CUDA")
+    bad = Av.copy()
+    bad[n // 2, n // 2] = -5.0
+    assert np.all(np.isnan(f(bad)))
+
+
+def test_batched_cholesky_blockwise(gpu):
+    rng = np.random.default_rng(37)
+    A = pt.dtensor3("A")
+    Av = rng.standard_normal((6, 9, 9))
+    Av = Av @ Av.transpose(0, 2, 1) + 9 * np.eye(9)
+    compare_cuda_and_cvm([A], [pt.linalg.cholesky(A)], [Av], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_row_batched_gather_and_deterministic_scatter_add(gpu, dtype):
+    # cfg-5 pattern: theta[:, g] (B,J)->(B,n) and its transpose, zeros(B,J)[:, g] += r(B,n); the scatter-add is a
+    # segmented reduction in ascending-index order => equal to np.add.at up to the last bit for float64
+    rng = np.random.default_rng(38)
+    theta = pt.tensor("theta", dtype=dtype, shape=(None, None))
+    r = pt.tensor("r", dtype=dtype, shape=(None, None))
+    g = pt.lvector("g")
+    tv = rng.standard_normal((300, 64)).astype(dtype)
+    rv = rng.standard_normal((300, 1024)).astype(dtype)
+    gv = rng.integers(0, 64, size=1024)
+    compare_cuda_and_cvm([theta, g], [theta[:, g]], [tv, gv], exact=True)
+    out = pt.inc_subtensor(pt.zeros_like(theta)[:, g], r)
+    f, got = compare_cuda_and_cvm([theta, r, g], [out], [tv, rv, gv], rtol=1e-6 if dtype == "float32" else 1e-13,
+                                  atol=1e-5 if dtype == "float32" else 1e-12)
+    ref = np.zeros_like(tv)
+    np.add.at(ref, (slice(None), gv), rv)
+    np.testing.assert_array_equal(got[0], ref)  # deterministic: same accumulation order as np.add.at
