@@ -100,7 +100,7 @@ constexpr int SK_MAXK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
                                                           int64_t sa0, int64_t sa1, const T* __restrict__ B, int64_t sb0,
-                                                          T beta, T* __restrict__ C, int64_t sc0) {
+                                                          int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
   const int64_t n0 = ((int64_t)blockIdx.x * 64 + tx) * 4;
   if (n0 >= N) return;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, 
 #pragma unroll
   for (int k = 0; k < SK_MAXK; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + n0 + j] : T(0);
+    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + (n0 + j) * sb1] : T(0);
   for (int64_t m = (int64_t)blockIdx.y * 4 + ty; m < M; m += (int64_t)gridDim.y * 4) {
     T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
@@ -132,61 +132,81 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, 
 }
 
 constexpr int SN_MAXN = 16;
-// N <= 16, A unit-stride along K: one warp per row of A, B (K x N) staged in shared memory in K-chunks.
-template <typename T>
-__global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int N, int64_t K, T alpha, const T* __restrict__ A,
+// N <= 16, A unit-stride along K: one warp per row of A; each lane streams 16-byte vectors of the row (4 in flight) and
+// multiplies them with B, which is staged TRANSPOSED in shared memory (Bs[n][k], k contiguous -> conflict-free LDS.128).
+template <typename T, int N>
+__global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int n_act, int64_t K, T alpha, const T* __restrict__ A,
                                                           int64_t sa0, const T* __restrict__ B, int64_t sb0, int64_t sb1,
                                                           T beta, T* __restrict__ C, int64_t sc0, int64_t sc1) {
-  constexpr int KC = 256;
-  __shared__ T Bs[KC][SN_MAXN + 1];
+  constexpr int V = 16 / sizeof(T);         // elements per 16-byte vector
+  constexpr int KC = 32 * V * 4;            // k-chunk: every lane handles 4 vectors per chunk (512 fp32 / 256 fp64)
+  __shared__ __align__(16) T Bs[N][KC + V];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t rows_per_block = 8 * 4;  // 8 warps x 4 rows each
-  const int64_t m_base = (int64_t)blockIdx.x * rows_per_block + warp * 4;
-  T acc[4][SN_MAXN];
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  const bool vec_ok = (sa0 % V == 0) && ((((uintptr_t)A) & 15) == 0);
+  // every warp of the block owns the rows m = gw, gw + warps_total, ...; all warps walk the K chunks together
+  const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t rounds = (M + warps_total - 1) / warps_total;
+  for (int64_t round = 0; round < rounds; ++round) {
+    const int64_t m = gw + round * warps_total;
+    T acc[N];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int n = 0; n < SN_MAXN; ++n) acc[r][n] = T(0);
-  for (int64_t k0 = 0; k0 < K; k0 += KC) {
-    const int kc = (int)min((int64_t)KC, K - k0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < kc * N; e += blockDim.x) {
-      int k = e / N, n = e - k * N;
-      Bs[k][n] = B[(k0 + k) * sb0 + n * sb1];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t m = m_base + r;
+    for (int n = 0; n < N; ++n) acc[n] = T(0);
+    for (int64_t k0 = 0; k0 < K; k0 += KC) {
+      const int kc = (int)min((int64_t)KC, K - k0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < N * KC; e += blockDim.x) {
+        const int n = e / KC, k = e - n * KC;
+        Bs[n][k] = (k < kc && n < n_act) ? B[(k0 + k) * sb0 + n * sb1] : T(0);
+      }
+      __syncthreads();
       if (m < M) {
         const T* arow = A + m * sa0 + k0;
-        for (int k = lane; k < kc; k += 32) {
-          const T a = arow[k];
+        if (vec_ok && kc == KC) {
+          T a[4][V];
 #pragma unroll
-          for (int n = 0; n < SN_MAXN; ++n)
-            if (n < N) acc[r][n] += a * Bs[k][n];
+          for (int u = 0; u < 4; ++u) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(arow + (u * 32 + lane) * V);
+            *reinterpret_cast<uint4*>(a[u]) = raw;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              T bv[V];
+              *reinterpret_cast<uint4*>(bv) = *reinterpret_cast<const uint4*>(&Bs[n][(u * 32 + lane) * V]);
+#pragma unroll
+              for (int e = 0; e < V; ++e) acc[n] += a[u][e] * bv[e];
+            }
+          }
+        } else {
+          for (int k = lane; k < kc; k += 32) {
+            const T av = arow[k];
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[n] += av * Bs[n][k];
+          }
         }
       }
     }
-  }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t m = m_base + r;
+    for (int n = 0; n < N; ++n) {
+      T v = acc[n];
 #pragma unroll
-    for (int n = 0; n < SN_MAXN; ++n) {
-      if (n < N) {
-        T v = acc[r][n];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && m < M) {
-          T* c = C + m * sc0 + n * sc1;
-          T out = alpha * v;
-          if (beta != T(0)) out += beta * (*c);
-          *c = out;
-        }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && m < M && n < n_act) {
+        T* c = C + m * sc0 + n * sc1;
+        T out = alpha * v;
+        if (beta != T(0)) out += beta * (*c);
+        *c = out;
       }
     }
   }
+}
+
+template <typename T, int N>
+void launch_smalln(int64_t M, int n_act, int64_t K, T alpha, const T* A, int64_t sa0, const T* B, int64_t sb0, int64_t sb1, T beta, T* C,
+                   int64_t sc0, int64_t sc1, unsigned grid, cudaStream_t st) {
+  gemm_smalln_kernel<T, N><<<grid, 256, 0, st>>>(M, n_act, K, alpha, A, sa0, B, sb0, sb1, beta, C, sc0, sc1);
 }
 
 template <typename T>
@@ -195,18 +215,23 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
                        const void* bias, int act, cudaStream_t st) {
   if (M == 0 || N == 0) return PTK_OK;
   const int sms = std::max(1, ptk::sm_count());
-  if (bias == nullptr && act == 0 && K >= 1 && K <= SK_MAXK && sb1 == 1 && sc1 == 1 && M >= 256 && N >= 64) {
+  if (bias == nullptr && act == 0 && K >= 1 && K <= SK_MAXK && sc1 == 1 && M >= 256 && N >= 64) {
     unsigned gx = (unsigned)((N + 255) / 256);
     unsigned gy = (unsigned)std::min<int64_t>((M + 3) / 4, std::max<int64_t>(1, (int64_t)sms * 8 / gx));
     gemm_smallk_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, (const T*)B, sb0,
-                                                       (T)beta, (T*)C, sc0);
+                                                       sb1, (T)beta, (T*)C, sc0);
     PTK_LAUNCH_CHECK("gemm_smallk");
     return PTK_OK;
   }
   if (bias == nullptr && act == 0 && N <= SN_MAXN && sa1 == 1 && M >= 256 && K >= 64) {
-    unsigned gx = (unsigned)std::min<int64_t>((M + 31) / 32, 2147483647LL);
-    gemm_smalln_kernel<T><<<gx, 256, 0, st>>>(M, (int)N, K, (T)alpha, (const T*)A, sa0, (const T*)B, sb0, sb1, (T)beta,
-                                              (T*)C, sc0, sc1);
+    unsigned gx = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)sms * 6);
+#define PTK_SN(NN) launch_smalln<T, NN>(M, (int)N, K, (T)alpha, (const T*)A, sa0, (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0, sc1, gx, st)
+    if (N <= 1) PTK_SN(1);
+    else if (N <= 2) PTK_SN(2);
+    else if (N <= 4) PTK_SN(4);
+    else if (N <= 8) PTK_SN(8);
+    else PTK_SN(16);
+#undef PTK_SN
     PTK_LAUNCH_CHECK("gemm_smalln");
     return PTK_OK;
   }

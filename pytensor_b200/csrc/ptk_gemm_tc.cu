@@ -345,28 +345,43 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src, long long sr, long long sc,
                                                            __nv_bfloat16* __restrict__ dst, long long ld, long long R,
                                                            long long Cc) {
-  __shared__ float tile[32][33];
-  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  // 64 x 64 tile: reads walk the source's unit-stride direction (128 B per warp), writes are packed bf16x2 along c
+  // (128 B per warp-row).  ld is even and dst 4-byte aligned (workspace rows are padded to 8 elements).
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const bool col_fast = (sc == 1) || (sr != 1);
   if (col_fast) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      long long r = r0 + ty + 8 * i, c = c0 + tx;
-      tile[ty + 8 * i][tx] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
-    }
-  } else {  // source is row-fast (sr == 1): read with threads along r, transpose in smem
+    for (int i = 0; i < 8; ++i) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      long long r = r0 + tx, c = c0 + ty + 8 * i;
-      tile[tx][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + ty + 8 * i, c = c0 + tx + 32 * h;
+        tile[ty + 8 * i][tx + 32 * h] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
+    }
+  } else {  // source is row-fast (sr == 1): read with threads along r, transpose through shared memory
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + tx + 32 * h, c = c0 + ty + 8 * i;
+        tile[tx + 32 * h][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    long long r = r0 + ty + 8 * i, c = c0 + tx;
-    if (r < R && c < Cc) dst[r * ld + c] = __float2bfloat16_rn(tile[ty + 8 * i][tx]);
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    if (r < R && c < Cc) {
+      const float lo = tile[ty + 8 * i][2 * tx], hi = tile[ty + 8 * i][2 * tx + 1];
+      if (c + 1 < Cc || c + 1 < ld) {
+        *reinterpret_cast<__nv_bfloat162*>(dst + r * ld + c) = __floats2bfloat162_rn(lo, (c + 1 < Cc) ? hi : 0.0f);
+      } else {
+        dst[r * ld + c] = __float2bfloat16_rn(lo);
+      }
+    }
   }
 }
 
@@ -417,12 +432,12 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     Abf = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(A_bf16));
     lda = lda_bf16;
   } else {
-    dim3 ga((unsigned)((K + 31) / 32), (unsigned)((M + 31) / 32));
+    dim3 ga((unsigned)((K + 63) / 64), (unsigned)((M + 63) / 64));
     convert_bf16_kernel<<<ga, 256, 0, st>>>(A, sa0, sa1, Abf, Kp, M, K);
   }
   {
     // B[K,N] -> Bt[N,K]: dst row index = n (source stride sb1), dst col index = k (source stride sb0)
-    dim3 gb((unsigned)((K + 31) / 32), (unsigned)((N + 31) / 32));
+    dim3 gb((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64));
     convert_bf16_kernel<<<gb, 256, 0, st>>>(B, sb1, sb0, Bbf, Kp, N, K);
     PTK_LAUNCH_CHECK("convert_bf16");
   }

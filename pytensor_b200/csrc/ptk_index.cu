@@ -212,14 +212,18 @@ __global__ void __launch_bounds__(1024) put_rows_offsets_kernel(const int64_t* _
 }
 __global__ void __launch_bounds__(256) put_rows_perm_kernel(const int64_t* __restrict__ idx, int64_t n_idx, int64_t n_dst,
                                                             const int* __restrict__ offsets, int* __restrict__ perm) {
+  extern __shared__ int sidx[];  // normalised indices, shared by the block
+  for (int64_t i = threadIdx.x; i < n_idx; i += blockDim.x) {
+    int64_t k = idx[i];
+    if (k < 0) k += n_dst;
+    sidx[i] = (k >= 0 && k < n_dst) ? (int)k : -1;
+  }
+  __syncthreads();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one destination bin per thread
   if (j >= n_dst) return;
   int p = offsets[j];
-  for (int64_t i = 0; i < n_idx; ++i) {
-    int64_t k = idx[i];
-    if (k < 0) k += n_dst;
-    if (k == j) perm[p++] = (int)i;  // ascending i: the same accumulation order as np.add.at
-  }
+  for (int i = 0; i < (int)n_idx; ++i)
+    if (sidx[i] == (int)j) perm[p++] = i;  // ascending i: the same accumulation order as np.add.at
 }
 template <typename T>
 __global__ void __launch_bounds__(256) put_rows_kernel(T* __restrict__ dst, const T* __restrict__ y,
@@ -391,7 +395,7 @@ ptk_status ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t ou
   int* offsets = reinterpret_cast<int*>(workspace);
   int* perm = offsets + (n_dst + 1);
   put_rows_offsets_kernel<<<1, 1024, (size_t)(n_dst + 1) * sizeof(int), st>>>(idx, n_idx, n_dst, offsets, err_flag);
-  put_rows_perm_kernel<<<(unsigned)((n_dst + 255) / 256), 256, 0, st>>>(idx, n_idx, n_dst, offsets, perm);
+  put_rows_perm_kernel<<<(unsigned)((n_dst + 255) / 256), 256, (size_t)n_idx * sizeof(int), st>>>(idx, n_idx, n_dst, offsets, perm);
   int wpb = (int)std::max<int64_t>(1, std::min<int64_t>(8, (48 * 1024) / (n_idx * isz)));
   size_t smem = (size_t)wpb * n_idx * isz;
   unsigned grid = (unsigned)std::min<int64_t>((outer + wpb - 1) / wpb, (int64_t)std::max(1, ptk::sm_count()) * 8);
