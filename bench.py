@@ -43,6 +43,27 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def _ncu_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture summary of the same command (profiles/*_prof_ew_ncu_summary.csv); None when no capture is committed."""
+    import csv
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*prof_ew*_ncu_summary.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+                    for r in rows[2:] if r[kn].startswith(kernel_prefix)]
+            if vals:
+                return sum(vals) / len(vals)
+        except Exception:  # noqa: BLE001
+            continue
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -298,6 +319,13 @@ def main():
             f_dev(*dev_args[i % 2])
         e1.record()
         barrier()
+        # the timed region lasts ~1 ms: keep the SAME work running for ~1.2 s more (untimed) so that nvidia-smi (200 ms
+        # period) sees the clocks / throttle reasons of this workload under sustained load
+        t_end = time.perf_counter() + 1.2
+        while time.perf_counter() < t_end:
+            for i in range(64):
+                f_dev(*dev_args[i % 2])
+            torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     replayed = bool(ex.last_from_graph)
     if dist is not None:
@@ -358,7 +386,8 @@ def main():
     alg_bytes = meta["bytes"] if fused else 3 * 4 * args.n * args.n
     achieved = alg_bytes / (step_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": dom_name,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic("ptk_ew_red_row" if fused else "ptk_ew_vec"),
+                "kernel": dom_name,
                 "kernel_ms": step_ms[dom], "algorithmic_bytes": alg_bytes, "peak_source": peaks["source"],
                 "how": "median CUDA-event duration of the node's launch over 12 eager evaluations queued behind device "
                        "work (no host gaps); whole_graph = all bytes / graph-replayed step time of the timed region",

@@ -125,8 +125,8 @@ ptk_status   ptk_gemm_bias_act(int dtype, int64_t M, int64_t N, int64_t K,
  * A comes either as fp32 (A_f32, element strides sa0/sa1; staged to bf16 in the workspace) or ALREADY staged as bf16
  * (A_bf16: row-major [M,K], pitch lda_bf16 elements (multiple of 8), 16-byte aligned) — e.g. the C_bf16 copy a previous
  * call emitted, so that a chain of layers re-stages only the weights.  C_bf16 (optional, row-major pitch ldc_bf16) receives
- * a bf16 copy of the result.  Environment PTK_GEMM_CLUSTER=1 selects the single-CTA kernel instead of the 2-CTA-cluster
- * kernel with TMA multicast of the shared B tile. */
+ * a bf16 copy of the result.  Environment PTK_GEMM_MODE selects the kernel: 1 = single CTA per tile,
+ * 2 = 2-CTA cluster sharing the B tile by TMA multicast, 3 = cta_group::2 UMMA (one 256x256 tile per CTA pair). */
 ptk_status   ptk_gemm_tc_ex(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0, int64_t sa1,
                       const void* A_bf16, int64_t lda_bf16, const void* B_f32, int64_t sb0, int64_t sb1, double beta,
                       void* C, int64_t sc0, int64_t sc1, const void* bias, int act, void* C_bf16, int64_t ldc_bf16,

@@ -340,6 +340,221 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ====================================================================================================================
+// cta_group::2 ("pair") kernel: two CTAs of a 2x1x1 cluster (one TPC) run ONE 256 x 256 UMMA tile.  Each CTA stages only
+// its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows), so per k-block a CTA writes 32 KiB into shared
+// memory instead of 48 KiB and the MMA reads 8 KiB instead of 12 KiB per k16 step: shared-memory traffic drops from
+// ~192 B/clk (above the 128 B/clk port, the limiter of the single-CTA kernel at ~60-67 % tensor-pipe) to ~128 B/clk, and
+// the ring deepens from 4 to 6 stages.  Only the leader CTA (cluster rank 0) issues tcgen05.mma; both CTAs' TMA loads
+// complete on the LEADER's "full" barrier; tcgen05.commit is multicast to both CTAs ("empty" + accumulator-ready
+// barriers); both CTAs' epilogue warps arrive on the leader's "accumulator drained" barrier.
+// ====================================================================================================================
+constexpr int P_STAGES = 6;
+constexpr uint32_t P_A_BYTES = BLOCK_M * BLOCK_K * 2;         // 16 KiB: this CTA's 128 rows of A
+constexpr uint32_t P_B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;   // 16 KiB: this CTA's half of the B tile
+constexpr uint32_t P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;     // 32 KiB
+constexpr uint32_t P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                // shared::cluster address of the same offset in CTA rank 0
+
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* smem_dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;                                // P_STAGES x 16 KiB
+  uint8_t* smem_b = smem + P_STAGES * P_A_BYTES;         // P_STAGES x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* full_bar = bars;                             // [P_STAGES]   (used in the leader only)
+  uint64_t* empty_bar = bars + P_STAGES;                 // [P_STAGES]   (one per CTA, signalled by the leader's commits)
+  uint64_t* tmem_full = bars + 2 * P_STAGES;             // [ACC_STAGES] (one per CTA)
+  uint64_t* tmem_empty = bars + 2 * P_STAGES + ACC_STAGES;  // [ACC_STAGES] (leader only; 8 arrivals = 4 warps x 2 CTAs)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);  // 256-row tiles
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_units = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of B, completion counted on the LEADER's full barrier =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = unit0; u < num_units; u += unit_stride) {
+        const int tm = u % m_tiles, tn = u / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * P_A_BYTES, kb * BLOCK_K,
+                          tm * 2 * BLOCK_M + (int)crank * BLOCK_M);
+          tma_load_2d_2sm(&tmap_b, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
+                          tn * BLOCK_N + (int)crank * (BLOCK_N / 2));
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: ONE thread of the leader CTA drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = unit0; u < num_units; u += unit_stride) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * P_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_f16_2sm(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free again in BOTH CTAs
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);      // accumulator complete in both CTAs' TMEM
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the 256-row tile =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = unit0; u < num_units; u += unit_stride) {
+      const int tm = u % m_tiles, tn = u / m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)tm * 2 * BLOCK_M + (long long)crank * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + row * p.sc0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const long long col0 = (long long)tn * BLOCK_N + c0;
+        if (row_ok && col0 < p.N) {
+          const bool full = (col0 + 32 <= p.N);
+          if (full && p.sc1 == 1 && p.beta == 0.0f && ((((uintptr_t)(crow + col0)) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = p.alpha * __uint_as_float(r[j + e]);
+                if (p.bias) x += p.bias[col0 + j + e];
+                if (p.act == 1) x = tanhf(x);
+                vv[e] = x;
+              }
+              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+              if (p.Cbf) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(p.Cbf + row * p.ldcbf + col0 + j) = pk;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long col = col0 + j;
+              if (col < p.N) {
+                float* dst = crow + col * p.sc1;
+                float x = p.alpha * __uint_as_float(r[j]);
+                if (p.beta != 0.0f) x += p.beta * (*dst);
+                if (p.bias) x += p.bias[col];
+                if (p.act == 1) x = tanhf(x);
+                *dst = x;
+                if (p.Cbf) p.Cbf[row * p.ldcbf + col] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);  // 8 arrivals (4 warps x 2 CTAs) free the accumulator
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---- fp32 -> bf16 operand staging: dst[r][c] (row-major, pitch ld) = bf16(src[r*sr + c*sc]) ----------------------------
 // Tiled through shared memory so that both the read (along whichever source stride is 1) and the write (along c) coalesce.
 __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src, long long sr, long long sc,
@@ -419,8 +634,8 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
   if (workspace == nullptr || workspace_bytes < gemm_tc_workspace(M, N, K))
     return fail(PTK_ERR_ARG, "gemm_tc: workspace too small (see ptk_gemm_workspace_bytes)");
   if (g_cluster < 0) {
-    const char* e = getenv("PTK_GEMM_CLUSTER");
-    g_cluster = (e && e[0] == '1') ? 1 : 2;
+    const char* e = getenv("PTK_GEMM_MODE");  // 1 = single CTA, 2 = CTA pair sharing B by TMA multicast, 3 = cta_group::2 UMMA
+    g_cluster = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
   }
   const long long Kp = round_up(K, 8);
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
@@ -445,7 +660,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
   CUtensorMap ta, tb;
   ptk_status s;
   if ((s = make_tmap(&ta, Abf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M)) != PTK_OK) return s;
-  if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, cluster == 2 ? BLOCK_N / 2 : BLOCK_N)) != PTK_OK) return s;
+  if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, cluster >= 2 ? BLOCK_N / 2 : BLOCK_N)) != PTK_OK) return s;
   EpiParams p;
   p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -455,17 +670,18 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   const int sms = std::max(2, ptk::sm_count());
-  if (cluster == 2) {
+  if (cluster >= 2) {
     const int units = ((m_tiles + 1) / 2) * n_tiles;
     const int grid = 2 * std::max(1, std::min(units, sms / 2));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = cluster == 3 ? P_SMEM_BYTES : SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -474,7 +690,8 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<2>, ta, tb, p));
+    if (cluster == 3) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, p));
+    else PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<2>, ta, tb, p));
   } else {
     const int grid = std::max(1, std::min(m_tiles * n_tiles, sms));
     gemm_bf16_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);

@@ -45,7 +45,11 @@ def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None
     st = dev.stream_ptr()
     if use_tc:
         ws_bytes = int(L.ptk_gemm_workspace_bytes(M, N, K, 1))
-        ws = _get_workspace(ws_bytes)
+        if dev.alloc_state.arena is not None or dev.alloc_state.measuring:
+            # inside a captured graph GEMMs may run concurrently on different streams: each gets its own staging area
+            ws = dev.empty_t((ws_bytes,), torch.uint8)
+        else:
+            ws = _get_workspace(ws_bytes)
         cbf = None
         if want_bf16:
             Np = (N + 7) // 8 * 8

@@ -10,6 +10,8 @@ from .values import Val
 
 
 class CholeskyNode(Node):
+    serial_group = "linalg"  # the blocked kernels share one device status word: never overlap two of them
+
     def __init__(self, dtype, lower=True, name="Cholesky"):
         self.dtype, self.lower, self.name = dtype, lower, name
 
@@ -28,6 +30,8 @@ class CholeskyNode(Node):
 
 class SolveTriangularNode(Node):
     """x = solve(op(A), b): lower/upper, trans, unit_diagonal, b_ndim 1|2 (triangular.py:16-21)."""
+
+    serial_group = "linalg"
 
     def __init__(self, dtype, lower, unit_diagonal, b_ndim, trans=0, name="SolveTriangular"):
         self.dtype, self.lower, self.unit_diagonal, self.b_ndim, self.trans, self.name = (

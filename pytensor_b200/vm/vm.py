@@ -48,6 +48,90 @@ class Program:
         self.steps = list(steps)
         self._plan_gc()
 
+    # ---- dependency structure for multi-stream execution ------------------------------------------------------------
+    def plan_streams(self, max_streams=4):
+        """Static stream assignment for the captured (graph) execution: `self.stream_of[i]` and `self.deps[i]`.
+
+        Hazards honoured (the role `fgraph.orderings()` / `get_destroy_dependencies` play for the reference's VMs,
+        pytensor/link/utils.py:831-847): true dependencies through slots, and — conservatively — any pair of steps where
+        one WRITES into an alias group (views + in-place outputs share a group) that the other touches."""
+        n = len(self.steps)
+        parent = {}
+
+        def find(x):
+            while parent.setdefault(x, x) != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+
+        def union(a, b):
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[ra] = rb
+
+        VIEW = ("DimShuffleNode", "ViewNode", "SubtensorNode", "ReshapeNode", "AssertNode")
+        writers = [False] * n
+        for i, st in enumerate(self.steps):
+            name = type(st.impl).__name__
+            if name in VIEW and st.ins and st.outs:
+                union(st.ins[0], st.outs[0])
+            destroy = getattr(st.impl, "destroy", None) or {}
+            for o, k in destroy.items():
+                if o < len(st.outs) and k < len(st.ins):
+                    union(st.outs[o], st.ins[k])
+                    writers[i] = True
+            if name in ("ScanNode", "ScanFusedElemwiseNode"):
+                writers[i] = writers[i] or bool(destroy)
+        producer = {}
+        for i, st in enumerate(self.steps):
+            for o in st.outs:
+                producer[o] = i
+        group_touch = {}   # group -> list of (step, is_write)
+        deps = [set() for _ in range(n)]
+        last_serial = {}
+        for i, st in enumerate(self.steps):
+            sg = getattr(st.impl, "serial_group", None)
+            if sg is not None:
+                if sg in last_serial:
+                    deps[i].add(last_serial[sg])
+                last_serial[sg] = i
+            for sl in st.ins:
+                if sl in producer and producer[sl] < i:
+                    deps[i].add(producer[sl])
+            groups_r = {find(sl) for sl in st.ins}
+            groups_w = {find(st.ins[k]) for k in (getattr(st.impl, "destroy", None) or {}).values() if k < len(st.ins)}
+            for g in groups_r | groups_w:
+                for j, was_write in group_touch.get(g, []):
+                    if was_write or g in groups_w:
+                        deps[i].add(j)
+            for g in groups_r | groups_w:
+                group_touch.setdefault(g, []).append((i, g in groups_w))
+        # greedy assignment: continue on the stream of a dependency whose last op is that dependency; else a free stream
+        stream_of = [0] * n
+        last_on = {}   # stream -> last step index
+        for i in range(n):
+            cand = None
+            for d in sorted(deps[i], reverse=True):
+                sd = stream_of[d]
+                if last_on.get(sd) == d:
+                    cand = sd
+                    break
+            if cand is None:
+                used = set(last_on)
+                free = [k for k in range(max_streams) if k not in used]
+                if not deps[i] and free:
+                    cand = free[0]
+                elif free and deps[i]:
+                    cand = free[0]
+                else:
+                    # reuse the stream whose last op is oldest
+                    cand = min(range(max_streams), key=lambda k: last_on.get(k, -1))
+            stream_of[i] = cand
+            last_on[cand] = i
+        self.deps = [sorted(d) for d in deps]
+        self.stream_of = stream_of
+        self.n_streams = max(stream_of) + 1 if stream_of else 1
+
     def _plan_gc(self):
         last = {}
         for i, st in enumerate(self.steps):
@@ -99,6 +183,8 @@ class Executor:
 
     def __init__(self, program: Program, allow_gc=True, use_graph=False):
         self.use_graph = use_graph
+        self.multi_stream = True   # independent branches on side streams inside captured graphs
+        self._side_streams = []
         self.last_from_graph = False
         self._graphs = {}
         self._graph_misses = 0
@@ -206,7 +292,7 @@ class Executor:
             st.capturing = True
             ok = True
             try:
-                outs = self._run_eager(vals_in)
+                outs = self._run_streams(vals_in) if self.multi_stream else self._run_eager(vals_in)
             except dev.GraphUnsupported:
                 ok = False
             finally:
@@ -230,6 +316,57 @@ class Executor:
         _lib.check(L.ptk_graph_launch(e.gexec, sp), "graph launch")
         self.last_from_graph = True
         return e.out_vals
+
+    def _run_streams(self, inputs):
+        """Capture-time execution with independent branches on side streams: the cross-stream event waits recorded here
+        become the dependency edges of the CUDA graph, so replays run independent nodes concurrently."""
+        import torch
+
+        p = self.program
+        if not hasattr(p, "stream_of"):
+            p.plan_streams()
+        if p.n_streams <= 1:
+            return self._run_eager(inputs)
+        main = torch.cuda.current_stream()
+        while len(self._side_streams) < p.n_streams - 1:
+            self._side_streams.append(torch.cuda.Stream())
+        streams = [main] + self._side_streams[: p.n_streams - 1]
+        vals = self.vals
+        for s, x in zip(p.inputs, inputs):
+            vals[s] = wrap(x)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for sd in streams[1:]:
+            sd.wait_event(fork)
+        done = [None] * len(p.steps)
+        try:
+            for i, st in enumerate(p.steps):
+                S = streams[p.stream_of[i]]
+                for d in p.deps[i]:
+                    if p.stream_of[d] != p.stream_of[i]:
+                        S.wait_event(done[d])
+                torch.cuda.set_stream(S)
+                try:
+                    res = st.impl.run([vals[j] for j in st.ins])
+                except Exception:
+                    self.position_of_error = st.origin if st.origin >= 0 else i
+                    raise
+                ev = torch.cuda.Event()
+                ev.record(S)
+                done[i] = ev
+                for j, r in zip(st.outs, res):
+                    vals[j] = r
+        finally:
+            torch.cuda.set_stream(main)
+            for sd in streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(sd)
+                main.wait_event(ev)
+        outs = [vals[s] for s in p.outputs]
+        for s in range(len(vals)):
+            if s not in p.constants:
+                vals[s] = None
+        return outs
 
     def _run_eager(self, inputs):
         p = self.program
