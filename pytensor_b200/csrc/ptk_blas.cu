@@ -120,12 +120,19 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, 
       }
     }
     T* c = C + m * sc0 + n0;
+    if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
+      struct __align__(4 * sizeof(T)) V4 { T v[4]; } out;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (n0 + j < N) {
-        T v = alpha * acc[j];
-        if (beta != T(0)) v += beta * c[j];
-        c[j] = v;
+      for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
+      *reinterpret_cast<V4*>(c) = out;  // one 128-bit (fp32) / 256-bit (fp64) store: full 32-byte sectors
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n0 + j < N) {
+          T v = alpha * acc[j];
+          if (beta != T(0)) v += beta * c[j];
+          c[j] = v;
+        }
       }
     }
   }
@@ -133,80 +140,101 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, 
 
 constexpr int SN_MAXN = 16;
 // N <= 16, A unit-stride along K: one warp per row of A; each lane streams 16-byte vectors of the row (4 in flight) and
-// multiplies them with B, which is staged TRANSPOSED in shared memory (Bs[n][k], k contiguous -> conflict-free LDS.128).
+// multiplies them with B, which is staged TRANSPOSED in shared memory ONCE per CTA and K-chunk (Bs[n][k], k contiguous ->
+// conflict-free LDS.128).  The CTA's warps then walk all their rows without further synchronisation.
 template <typename T, int N>
-__global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int n_act, int64_t K, T alpha, const T* __restrict__ A,
-                                                          int64_t sa0, const T* __restrict__ B, int64_t sb0, int64_t sb1,
-                                                          T beta, T* __restrict__ C, int64_t sc0, int64_t sc1) {
-  constexpr int V = 16 / sizeof(T);         // elements per 16-byte vector
-  constexpr int KC = 32 * V * 4;            // k-chunk: every lane handles 4 vectors per chunk (512 fp32 / 256 fp64)
-  __shared__ __align__(16) T Bs[N][KC + V];
+__global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int n_act, int64_t K, int kchunk, T alpha,
+                                                          const T* __restrict__ A, int64_t sa0, const T* __restrict__ B,
+                                                          int64_t sb0, int64_t sb1, T beta, T* __restrict__ C, int64_t sc0,
+                                                          int64_t sc1) {
+  constexpr int V = 16 / sizeof(T);  // elements per 16-byte vector
+  extern __shared__ __align__(16) unsigned char sn_smem[];
+  T* Bs = reinterpret_cast<T*>(sn_smem);  // [N][kchunk + V]
+  const int ldb = kchunk + V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * 8;
-  const bool vec_ok = (sa0 % V == 0) && ((((uintptr_t)A) & 15) == 0);
-  // every warp of the block owns the rows m = gw, gw + warps_total, ...; all warps walk the K chunks together
   const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
-  const int64_t rounds = (M + warps_total - 1) / warps_total;
-  for (int64_t round = 0; round < rounds; ++round) {
-    const int64_t m = gw + round * warps_total;
-    T acc[N];
+  const bool vec_ok = (sa0 % V == 0) && ((((uintptr_t)A) & 15) == 0) && (kchunk % (32 * V) == 0);
+  for (int64_t k0 = 0; k0 < K; k0 += kchunk) {
+    const int kc = (int)min((int64_t)kchunk, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * kchunk; e += blockDim.x) {
+      const int n = e / kchunk, k = e - n * kchunk;
+      Bs[n * ldb + k] = (k < kc && n < n_act) ? B[(k0 + k) * sb0 + n * sb1] : T(0);
+    }
+    __syncthreads();
+    const bool first = k0 == 0;
+    for (int64_t m = gw; m < M; m += warps_total) {
+      T acc[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) acc[n] = T(0);
-    for (int64_t k0 = 0; k0 < K; k0 += KC) {
-      const int kc = (int)min((int64_t)KC, K - k0);
-      __syncthreads();
-      for (int e = threadIdx.x; e < N * KC; e += blockDim.x) {
-        const int n = e / KC, k = e - n * KC;
-        Bs[n][k] = (k < kc && n < n_act) ? B[(k0 + k) * sb0 + n * sb1] : T(0);
-      }
-      __syncthreads();
-      if (m < M) {
-        const T* arow = A + m * sa0 + k0;
-        if (vec_ok && kc == KC) {
+      for (int n = 0; n < N; ++n) acc[n] = T(0);
+      const T* arow = A + m * sa0 + k0;
+      if (vec_ok && ((k0 % V) == 0)) {
+        // kc is padded with zeros in Bs up to kchunk, but A must not be read past K: guard the vector index
+        for (int kb = 0; kb < kchunk; kb += 32 * V * 4) {
           T a[4][V];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(arow + (u * 32 + lane) * V);
-            *reinterpret_cast<uint4*>(a[u]) = raw;
+            const int kk = kb + (u * 32 + lane) * V;
+            if (kk + V <= kc) *reinterpret_cast<uint4*>(a[u]) = *reinterpret_cast<const uint4*>(arow + kk);
+            else {
+#pragma unroll
+              for (int e = 0; e < V; ++e) a[u][e] = (kk + e < kc) ? arow[kk + e] : T(0);
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
+            const int kk = kb + (u * 32 + lane) * V;
+            if (kk < kchunk) {
 #pragma unroll
-            for (int n = 0; n < N; ++n) {
-              T bv[V];
-              *reinterpret_cast<uint4*>(bv) = *reinterpret_cast<const uint4*>(&Bs[n][(u * 32 + lane) * V]);
+              for (int n = 0; n < N; ++n) {
+                T bv[V];
+                *reinterpret_cast<uint4*>(bv) = *reinterpret_cast<const uint4*>(&Bs[n * ldb + kk]);
 #pragma unroll
-              for (int e = 0; e < V; ++e) acc[n] += a[u][e] * bv[e];
+                for (int e = 0; e < V; ++e) acc[n] += a[u][e] * bv[e];
+              }
             }
           }
-        } else {
-          for (int k = lane; k < kc; k += 32) {
-            const T av = arow[k];
+        }
+      } else {
+        for (int k = lane; k < kc; k += 32) {
+          const T av = arow[k];
 #pragma unroll
-            for (int n = 0; n < N; ++n) acc[n] += av * Bs[n][k];
-          }
+          for (int n = 0; n < N; ++n) acc[n] += av * Bs[n * ldb + k];
         }
       }
-    }
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      T v = acc[n];
+      for (int n = 0; n < N; ++n) {
+        T v = acc[n];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && m < M && n < n_act) {
-        T* c = C + m * sc0 + n * sc1;
-        T out = alpha * v;
-        if (beta != T(0)) out += beta * (*c);
-        *c = out;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && n < n_act) {
+          T* c = C + m * sc0 + n * sc1;
+          T out = alpha * v;
+          if (first) { if (beta != T(0)) out += beta * (*c); }
+          else out += *c;
+          *c = out;
+        }
       }
     }
   }
 }
 
 template <typename T, int N>
-void launch_smalln(int64_t M, int n_act, int64_t K, T alpha, const T* A, int64_t sa0, const T* B, int64_t sb0, int64_t sb1, T beta, T* C,
-                   int64_t sc0, int64_t sc1, unsigned grid, cudaStream_t st) {
-  gemm_smalln_kernel<T, N><<<grid, 256, 0, st>>>(M, n_act, K, alpha, A, sa0, B, sb0, sb1, beta, C, sc0, sc1);
+ptk_status launch_smalln(int64_t M, int n_act, int64_t K, T alpha, const T* A, int64_t sa0, const T* B, int64_t sb0,
+                         int64_t sb1, T beta, T* C, int64_t sc0, int64_t sc1, unsigned grid, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  const int unit = 32 * V * 4;  // one unrolled sweep of a warp
+  int64_t kchunk = (K + unit - 1) / unit * unit;
+  const int64_t max_elems = (96 * 1024) / ((int64_t)sizeof(T) * N) - V;
+  if (kchunk > max_elems) kchunk = std::max<int64_t>(unit, max_elems / unit * unit);
+  const size_t smem = (size_t)N * (kchunk + V) * sizeof(T);
+  static bool attr_done = false;
+  (void)attr_done;
+  cudaError_t e = cudaFuncSetAttribute(gemm_smalln_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) return ptk::check_cuda(e, "cudaFuncSetAttribute(gemm_smalln)");
+  gemm_smalln_kernel<T, N><<<grid, 256, smem, st>>>(M, n_act, K, (int)kchunk, alpha, A, sa0, B, sb0, sb1, beta, C, sc0, sc1);
+  return PTK_OK;
 }
 
 template <typename T>
@@ -224,14 +252,16 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
     return PTK_OK;
   }
   if (bias == nullptr && act == 0 && N <= SN_MAXN && sa1 == 1 && M >= 256 && K >= 64) {
-    unsigned gx = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)sms * 6);
+    unsigned gx = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)sms * 2);
 #define PTK_SN(NN) launch_smalln<T, NN>(M, (int)N, K, (T)alpha, (const T*)A, sa0, (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0, sc1, gx, st)
-    if (N <= 1) PTK_SN(1);
-    else if (N <= 2) PTK_SN(2);
-    else if (N <= 4) PTK_SN(4);
-    else if (N <= 8) PTK_SN(8);
-    else PTK_SN(16);
+    ptk_status sn;
+    if (N <= 1) sn = PTK_SN(1);
+    else if (N <= 2) sn = PTK_SN(2);
+    else if (N <= 4) sn = PTK_SN(4);
+    else if (N <= 8) sn = PTK_SN(8);
+    else sn = PTK_SN(16);
 #undef PTK_SN
+    if (sn != PTK_OK) return sn;
     PTK_LAUNCH_CHECK("gemm_smalln");
     return PTK_OK;
   }

@@ -635,7 +635,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     return fail(PTK_ERR_ARG, "gemm_tc: workspace too small (see ptk_gemm_workspace_bytes)");
   if (g_cluster < 0) {
     const char* e = getenv("PTK_GEMM_MODE");  // 1 = single CTA, 2 = CTA pair sharing B by TMA multicast, 3 = cta_group::2 UMMA
-    g_cluster = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
+    g_cluster = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
   }
   const long long Kp = round_up(K, 8);
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;

@@ -168,7 +168,21 @@ __global__ void __launch_bounds__(256) take_lastaxis_kernel(T* __restrict__ out,
     k[e] = v;
   }
   const bool vec = ok[0] && ok[1] && ok[2] && ok[3] && (n_idx % 4 == 0) && sizeof(T) == 4 && (((uintptr_t)out & 15) == 0);
-  for (int64_t o = blockIdx.y; o < outer; o += gridDim.y) {
+  int64_t o = blockIdx.y;
+  if (vec) {
+    for (; o + 3 * (int64_t)gridDim.y < outer; o += 4 * (int64_t)gridDim.y) {  // 4 rows = 16 independent gathers in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* s = src + (o + u * (int64_t)gridDim.y) * n_src;
+        v[u].x = (uint32_t)s[k[0]]; v[u].y = (uint32_t)s[k[1]]; v[u].z = (uint32_t)s[k[2]]; v[u].w = (uint32_t)s[k[3]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(out + (o + u * (int64_t)gridDim.y) * n_idx + j0) = v[u];
+    }
+  }
+  for (; o < outer; o += gridDim.y) {
     const T* s = src + o * n_src;
     T* d = out + o * n_idx + j0;
     if (vec) {
@@ -236,7 +250,15 @@ __global__ void __launch_bounds__(256) put_rows_kernel(T* __restrict__ dst, cons
   T* mine = ys + (int64_t)warp * n_idx;
   for (int64_t o = (int64_t)blockIdx.x * warps_per_block + warp; o < outer; o += (int64_t)gridDim.x * warps_per_block) {
     const T* yrow = y + o * n_idx;
-    for (int64_t i = lane; i < n_idx; i += 32) mine[i] = yrow[i];
+    int64_t i = lane;
+    for (; i + 7 * 32 < n_idx; i += 8 * 32) {  // 8 independent 128-byte warp loads in flight before the first smem store
+      T t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = yrow[i + u * 32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mine[i + u * 32] = t[u];
+    }
+    for (; i < n_idx; i += 32) mine[i] = yrow[i];
     __syncwarp();
     T* drow = dst + o * n_dst;
     for (int64_t j = lane; j < n_dst; j += 32) {
