@@ -224,7 +224,7 @@ def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10
     GPUs), sharded along the batch axis, ONE packed NCCL all-reduce of [logp, grads] (75 floats) per evaluation."""
     from pytensor_b200.sharded import ShardedSum
 
-    ins, outs, make_args, meta = W.cfg5_logp_grad(B=B_local * world, n=1024, J=64, K=8, dtype="float32")
+    ins, outs, make_args, meta = W.cfg5_logp_grad(B=B_local * world, n=1024, J=64, K=8, dtype="float32", packed=True)
     f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True), trust_input=True)
     local = [dev.to_device(a) for a in make_args(seed=20 + rank, B_local=B_local)]
     sh = ShardedSum(f, batch_arg_idx=[0, 1, 2, 3])
@@ -246,7 +246,7 @@ def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    logp = float(dev.to_host(res[0]))
+    logp = float(dev.to_host(res[0]).reshape(-1)[0])
     return {"evals_per_s": steps / (ms * 1e-3), "ms_per_eval": ms / steps, "chains_per_s": B_local * world * steps / (ms * 1e-3),
             "global_batch": B_local * world, "per_gpu_batch": B_local, "n_rows": 1024, "allreduce_floats": 1 + meta["P"],
             "scaling": "weak (2^17 chains per GPU; 2^20 at 8 GPUs)", "nodes": len(f.maker.fgraph.toposort()),

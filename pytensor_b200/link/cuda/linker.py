@@ -57,6 +57,12 @@ class CudaVM:
         except Exception:
             self.position_of_error = ex.position_of_error
             raise
+        if ex.last_from_graph and self.device_outputs and self.borrow_outputs and output_subset is None:
+            # replayed graph, borrowed device outputs: hand out the arena views directly (no copies, no sync)
+            outs = [v.d if v.d is not None else v.h for v in out_vals]
+            for cell, o in zip(self.output_storage, outs):
+                cell[0] = o
+            return outs
         outs = outputs_to_host(out_vals, self.device_outputs, copy_device=ex.last_from_graph and not self.borrow_outputs)
         for cell, o in zip(self.output_storage, outs):
             cell[0] = o

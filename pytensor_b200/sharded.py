@@ -60,6 +60,10 @@ class ShardedSum:
             return outs
         sizes = [int(np.prod(o.shape)) if len(o.shape) else 1 for o in outs]
         total = sum(sizes)
+        if len(outs) == 1 and isinstance(outs[0], torch.Tensor) and outs[0].is_contiguous():
+            # the graph already packed its partials into one vector: reduce it in place, one NCCL call, no copies
+            self.dist.all_reduce(outs[0], op=self.dist.ReduceOp.SUM, group=self.group)
+            return outs
         if isinstance(outs[0], torch.Tensor):
             from pytensor_b200.runtime import device as dev
 

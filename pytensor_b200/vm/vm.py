@@ -187,6 +187,7 @@ class Executor:
         self._side_streams = []
         self.last_from_graph = False
         self._graphs = {}
+        self._id_cache = {}
         self._graph_misses = 0
         self.program = program
         self.allow_gc = allow_gc
@@ -226,10 +227,23 @@ class Executor:
         if (not self.use_graph or _lib.TRACE_ONLY or self.time_nodes or self.event_log is not None
                 or dev.alloc_state.capturing or dev.alloc_state.measuring):
             return self._run_eager(inputs)
-        sig = self._signature(inputs)
-        if sig is None:
-            return self._run_eager(inputs)
-        e = self._graphs.get(sig)
+        # hot path: the very same input OBJECTS as an earlier replayed call (device tensors / large host arrays whose
+        # metadata cannot change under us) -> skip building the signature
+        ids = tuple(map(id, inputs))
+        hit = self._id_cache.get(ids)
+        if hit is not None and hit[1].stage == 2:
+            e = hit[1]
+            sig = None
+        else:
+            sig = self._signature(inputs)
+            if sig is None:
+                return self._run_eager(inputs)
+            e = self._graphs.get(sig)
+            if e is not None and e.stage == 2 and all(
+                    (hasattr(x, "is_cuda") or np.asarray(x).size > 8) for x in inputs):
+                if len(self._id_cache) > 16:
+                    self._id_cache.clear()
+                self._id_cache[ids] = (list(inputs), e)  # strong refs keep the ids from being recycled
         if e is None:
             if len(self._graphs) >= self.MAX_GRAPHS:
                 self._graph_misses += 1
@@ -428,7 +442,13 @@ def outputs_to_host(out_vals, device_outputs=False, copy_device=False):
             pending.append((len(res) - 1, v))
     for k, v in pending:
         res[k] = dev.to_host(v.d, sync=False)
-    if pending or nodes_basic._pending_flags:
+    if pending:
         dev.synchronize()
-    nodes_basic.check_pending_flags()
+        nodes_basic.check_pending_flags()
+    elif nodes_basic._pending_flags and not device_outputs:
+        dev.synchronize()
+        nodes_basic.check_pending_flags()
+    elif len(nodes_basic._pending_flags) > 256:
+        # device outputs never force a synchronisation; index-error flags are checked lazily (next host-visible call)
+        del nodes_basic._pending_flags[:-64]
     return res

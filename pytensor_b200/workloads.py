@@ -107,7 +107,7 @@ def cfg4_scan(rows=8192, cols=512, n_steps=1000, matmul=False, full_trace=False)
                                    "n_steps": n_steps, "name": "cfg4_scan"}
 
 
-def cfg5_logp_grad(B=1 << 20, n=1024, J=64, K=8, dtype="float32"):
+def cfg5_logp_grad(B=1 << 20, n=1024, J=64, K=8, dtype="float32", packed=False):
     """configs[4]: hierarchical-normal logp + grad for B independent parameter vectors (chains) over shared data.
 
     logp_b = N(mu;0,1) + N(ls;0,1) + sum_j N(theta_j; mu, e^ls) + sum_k N(beta_k;0,1) + sum_i N(y_i; theta[g_i]+X_i.beta, 1)
@@ -135,6 +135,8 @@ def cfg5_logp_grad(B=1 << 20, n=1024, J=64, K=8, dtype="float32"):
     total = lp.sum()
     grads = pytensor.grad(total, [mu, ls, theta, beta])
     outs = [total] + [gr.sum(axis=0) for gr in grads]
+    if packed:  # ONE contiguous [logp, d/dmu, d/dls, d/dtheta (J), d/dbeta (K)] vector: the all-reduce message
+        outs = [pt.concatenate([o.reshape((-1,)) for o in outs])]
 
     def make_args(seed=20, B_local=None):
         rng = np.random.default_rng(seed)
