@@ -72,43 +72,46 @@ __global__ void __launch_bounds__(512) potrf_small_kernel(T* __restrict__ Aall, 
 }
 
 // ---- blocked path ----------------------------------------------------------------------------------------------------
-// (1) factor the kb x kb diagonal block in shared memory (right-looking, one CTA); sets *flag when not positive definite
+// (1) factor the kb x kb diagonal block in shared memory: left-looking, ONE thread per row, ONE barrier per column.  Every
+// thread recomputes the pivot column's dot product (row j . row j) itself, so no thread waits for another one's sqrt.
 template <typename T>
-__global__ void __launch_bounds__(256) potrf_diag_kernel(T* __restrict__ A, int64_t rs, int64_t cs, int kb, int* flag) {
+__global__ void __launch_bounds__(64) potrf_diag_kernel(T* __restrict__ A, int64_t rs, int64_t cs, int kb, int* flag) {
   __shared__ T s[NB][NB + 1];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < kb * kb; e += blockDim.x) {
+  const int i = threadIdx.x;
+  for (int e = i; e < kb * kb; e += blockDim.x) {
     int r = e / kb, c = e - r * kb;
     s[r][c] = (c <= r) ? A[r * rs + c * cs] : T(0);
   }
   __syncthreads();
+  bool bad = false;
   for (int j = 0; j < kb; ++j) {
-    if (tid == 0) {
-      T d = s[j][j];
-      if (!(d > T(0))) *flag = 1;
-      s[j][j] = sqrt(d);
+    T sj = T(0), si = T(0);
+    for (int k = 0; k < j; ++k) {
+      const T ljk = s[j][k];
+      sj += ljk * ljk;
+      if (i > j && i < kb) si += s[i][k] * ljk;
     }
-    __syncthreads();
-    const T inv = T(1) / s[j][j];
-    for (int i = j + 1 + tid; i < kb; i += blockDim.x) s[i][j] *= inv;
-    __syncthreads();
-    // trailing update of the block: s[i][c] -= s[i][j] * s[c][j] for j < c <= i
-    const int m = kb - j - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      int i = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= i) s[i][c] -= s[i][j] * s[c][j];
-    }
+    const T d = s[j][j] - sj;
+    if (!(d > T(0))) bad = true;
+    const T ljj = sqrt(d);
+    T mine = T(0);
+    if (i > j && i < kb) mine = (s[i][j] - si) / ljj;
+    __syncthreads();  // everyone has read column j / row j before it is overwritten
+    if (i == j) s[j][j] = ljj;
+    else if (i > j && i < kb) s[i][j] = mine;
     __syncthreads();
   }
-  for (int e = tid; e < kb * kb; e += blockDim.x) {
+  if (bad && i == 0) *flag = 1;
+  for (int e = i; e < kb * kb; e += blockDim.x) {
     int r = e / kb, c = e - r * kb;
     if (c <= r) A[r * rs + c * cs] = s[r][c];
   }
 }
 
-// (2) panel: rows below the diagonal block: X * L11^T = A21  (one thread per row, L11 broadcast from shared memory)
+// (2) panel: rows below the diagonal block solve X * L11^T = A21.  One WARP per row: lane l owns columns l and l+32; the
+// forward substitution broadcasts each finished x_j with a shuffle and every lane updates its two pending columns.
 template <typename T>
-__global__ void __launch_bounds__(128) potrf_panel_kernel(const T* __restrict__ L11, T* __restrict__ A21, int64_t rs,
+__global__ void __launch_bounds__(256) potrf_panel_kernel(const T* __restrict__ L11, T* __restrict__ A21, int64_t rs,
                                                           int64_t cs, int kb, int64_t m) {
   __shared__ T s[NB][NB + 1];
   for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) {
@@ -116,17 +119,25 @@ __global__ void __launch_bounds__(128) potrf_panel_kernel(const T* __restrict__ 
     s[r][c] = (c <= r) ? L11[r * rs + c * cs] : T(0);
   }
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  T x[NB];
-  T* row = A21 + i * rs;
-#pragma unroll 1
-  for (int j = 0; j < kb; ++j) {
-    T v = row[j * cs];
-    for (int p = 0; p < j; ++p) v -= x[p] * s[j][p];
-    x[j] = v / s[j][j];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < m; i += nwarps) {
+    T* row = A21 + i * rs;
+    T a0 = (lane < kb) ? row[lane * cs] : T(0);
+    T a1 = (lane + 32 < kb) ? row[(lane + 32) * cs] : T(0);
+    for (int j = 0; j < kb; ++j) {
+      const int owner = j & 31;
+      T x = (j < 32) ? a0 : a1;
+      x = x / s[j][j];                       // only the owner lane's value is used
+      const T xj = __shfl_sync(0xffffffffu, x, owner);
+      if (lane == owner) { if (j < 32) a0 = xj; else a1 = xj; }
+      if (lane > j && lane < kb) a0 -= xj * s[lane][j];
+      if (lane + 32 > j && lane + 32 < kb) a1 -= xj * s[lane + 32][j];
+    }
+    if (lane < kb) row[lane * cs] = a0;
+    if (lane + 32 < kb) row[(lane + 32) * cs] = a1;
   }
-  for (int j = 0; j < kb; ++j) row[j * cs] = x[j];
 }
 
 template <typename T>
@@ -239,11 +250,11 @@ ptk_status potrf_blocked(int dtype, T* A, int64_t n, int64_t rs, int64_t cs, int
   for (int64_t k0 = 0; k0 < n; k0 += NB) {
     const int kb = (int)std::min<int64_t>(NB, n - k0);
     T* A11 = A + k0 * rs + k0 * cs;
-    potrf_diag_kernel<T><<<1, 256, 0, st>>>(A11, rs, cs, kb, flag);
+    potrf_diag_kernel<T><<<1, 64, 0, st>>>(A11, rs, cs, kb, flag);
     const int64_t m = n - k0 - kb;
     if (m > 0) {
       T* A21 = A + (k0 + kb) * rs + k0 * cs;
-      potrf_panel_kernel<T><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(A11, A21, rs, cs, kb, m);
+      potrf_panel_kernel<T><<<(unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)std::max(1, ptk::sm_count()) * 4), 256, 0, st>>>(A11, A21, rs, cs, kb, m);
       T* A22 = A + (k0 + kb) * rs + (k0 + kb) * cs;
       // A22 -= A21 * A21^T on the GEMM kernel (full square; only the lower triangle is read afterwards)
       ptk_status s = ptk_gemm(dtype, m, m, kb, -1.0, A21, rs, cs, A21, cs, rs, 1.0, A22, rs, cs, 0, nullptr, 0, (void*)st);
