@@ -96,28 +96,30 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int64_t M, int64_t N, in
 
 // ---- skinny shapes (PyMC-style regressions: (B x K)(K x n) with K ~ 8 and (B x n)(n x K)): HBM-bound on the big operand --------
 constexpr int SK_MAXK = 16;
-// K <= 16, B and C unit-stride along N: a thread keeps its K x 4 slab of B in registers and streams rows of A / C.
-template <typename T>
-__global__ void __launch_bounds__(256) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
+// K <= KMAX (4 / 8 / 16), C unit-stride along N: a thread keeps its K x 4 slab of B in registers and streams rows of A / C
+// (two rows per iteration for memory-level parallelism).  Register budget matters here: the K <= 8 instance must keep
+// >= 3 CTAs per SM resident or the kernel turns latency-bound.
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256, (KMAX <= 8 ? 3 : 1)) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
                                                           int64_t sa0, int64_t sa1, const T* __restrict__ B, int64_t sb0,
                                                           int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
   const int64_t n0 = ((int64_t)blockIdx.x * 64 + tx) * 4;
   if (n0 >= N) return;
-  T b[SK_MAXK][4];
+  T b[KMAX][4];
 #pragma unroll
-  for (int k = 0; k < SK_MAXK; ++k)
+  for (int k = 0; k < KMAX; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + (n0 + j) * sb1] : T(0);
   for (int64_t m = (int64_t)blockIdx.y * 4 + ty; m < M; m += (int64_t)gridDim.y * 4) {
+    T av[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) av[k] = (k < K) ? A[m * sa0 + k * sa1] : T(0);  // all loads first, then the FMAs
     T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-    for (int k = 0; k < SK_MAXK; ++k) {
-      if (k < K) {
-        const T a = A[m * sa0 + k * sa1];
+    for (int k = 0; k < KMAX; ++k) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += a * b[k][j];
-      }
+      for (int j = 0; j < 4; ++j) acc[j] += av[k] * b[k][j];
     }
     T* c = C + m * sc0 + n0;
     if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
@@ -245,9 +247,13 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
   const int sms = std::max(1, ptk::sm_count());
   if (bias == nullptr && act == 0 && K >= 1 && K <= SK_MAXK && sc1 == 1 && M >= 256 && N >= 64) {
     unsigned gx = (unsigned)((N + 255) / 256);
-    unsigned gy = (unsigned)std::min<int64_t>((M + 3) / 4, std::max<int64_t>(1, (int64_t)sms * 8 / gx));
-    gemm_smallk_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, (const T*)B, sb0,
-                                                       sb1, (T)beta, (T*)C, sc0);
+    unsigned gy = (unsigned)std::min<int64_t>((M + 3) / 4, std::max<int64_t>(1, (int64_t)sms * 12 / gx));
+#define PTK_SK(KM) gemm_smallk_kernel<T, KM><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, \
+                                                                      (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0)
+    if (K <= 4) PTK_SK(4);
+    else if (K <= 8) PTK_SK(8);
+    else PTK_SK(16);
+#undef PTK_SK
     PTK_LAUNCH_CHECK("gemm_smallk");
     return PTK_OK;
   }

@@ -85,12 +85,24 @@ __global__ void __launch_bounds__(64) potrf_diag_kernel(T* __restrict__ A, int64
   __syncthreads();
   bool bad = false;
   for (int j = 0; j < kb; ++j) {
-    T sj = T(0), si = T(0);
-    for (int k = 0; k < j; ++k) {
-      const T ljk = s[j][k];
-      sj += ljk * ljk;
-      if (i > j && i < kb) si += s[i][k] * ljk;
+    T sj0 = T(0), sj1 = T(0), si0 = T(0), si1 = T(0);  // two partial sums each: break the serial FMA dependency
+    const bool below = i > j && i < kb;
+    int k = 0;
+    for (; k + 1 < j; k += 2) {
+      const T l0 = s[j][k], l1 = s[j][k + 1];
+      sj0 += l0 * l0;
+      sj1 += l1 * l1;
+      if (below) {
+        si0 += s[i][k] * l0;
+        si1 += s[i][k + 1] * l1;
+      }
     }
+    if (k < j) {
+      const T l0 = s[j][k];
+      sj0 += l0 * l0;
+      if (below) si0 += s[i][k] * l0;
+    }
+    const T sj = sj0 + sj1, si = si0 + si1;
     const T d = s[j][j] - sj;
     if (!(d > T(0))) bad = true;
     const T ljj = sqrt(d);
