@@ -1,0 +1,94 @@
+
+// ---- ptk scalar helpers ----
+__device__ __forceinline__ float ptk_max_nan_f32(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float ptk_min_nan_f32(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+// Python floor-division / modulo semantics of IntDiv / Mod
+template <typename T> __device__ __forceinline__ T ptk_floordiv(T x, T y) {
+  if (y == 0) return 0;
+  T q = x / y;
+  if ((x % y != 0) && ((x < 0) != (y < 0))) --q;
+  return q;
+}
+template <typename T> __device__ __forceinline__ T ptk_imod_py(T x, T y) {
+  if (y == 0) return 0;
+  T r = x % y;
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+template <typename T> __device__ __forceinline__ T ptk_fmod_py(T x, T y) {
+  if (y == 0) return x - x + (T)__int_as_float(0x7fc00000);
+  T r = fmod(x, y);
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+
+
+template <typename T, int N> struct __align__(sizeof(T) * N) PVec { T v[N]; };
+template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv(const T* p) {
+  return *reinterpret_cast<const PVec<T, N>*>(p);
+}
+template <typename T, int N> __device__ __forceinline__ void ptk_stv(T* p, const PVec<T, N>& v) {
+  *reinterpret_cast<PVec<T, N>*>(p) = v;
+}
+
+__device__ __forceinline__ void ptk_body(const double i0, const double i1, double& o0, double& o1, double& o2) {
+  const double t0 = (double)(exp((double)(i1)));
+  const double t1 = (double)(((t0) + (i0)));
+  const double t2 = (double)(((t1) - (i1)));
+  const double t3 = (double)(tanh((double)(t1)));
+  const double t4 = (double)(((0x1.0000000000000p+1) * (t1)));
+  o0 = (double)(t4);
+  o1 = (double)(t3);
+  o2 = (double)(t2);
+}
+
+#define VW 4
+#define U 4
+extern "C" __global__ void __launch_bounds__(256) ptk_ew_vec_0cad919afbc4f61c(const double* __restrict__ pi0, const double* __restrict__ pi1, double* __restrict__ po0, double* __restrict__ po1, double* __restrict__ po2, long long rsi0, long long rsi1, long long rso0, long long rso1, long long rso2, long long nchunks, unsigned int cpr, long long tail_start, long long n_total) {
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long base = gtid; base < nchunks; base += gstride * U) {
+      PVec<double, VW> vi0[U];
+      PVec<double, VW> vi1[U];
+      long long rr[U]; long long cc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {
+          long long r, c;
+          if (nchunks < 0x7fffffffLL) { unsigned int qq = (unsigned int)q; unsigned int r32 = qq / cpr; r = r32; c = (long long)(qq - r32 * cpr) * VW; }
+          else { r = q / cpr; c = (q - r * cpr) * VW; }
+          rr[u] = r; cc[u] = c;
+          vi0[u] = ptk_ldv<double, VW>(pi0 + r * rsi0 + c);
+          vi1[u] = ptk_ldv<double, VW>(pi1 + r * rsi1 + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = base + (long long)u * gstride;
+        if (q < nchunks) {
+          const long long r = rr[u], c = cc[u];
+          PVec<double, VW> vo0;
+          PVec<double, VW> vo1;
+          PVec<double, VW> vo2;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            ptk_body(vi0[u].v[e], vi1[u].v[e], vo0.v[e], vo1.v[e], vo2.v[e]);
+          }
+          ptk_stv<double, VW>(po0 + r * rso0 + c, vo0);
+          ptk_stv<double, VW>(po1 + r * rso1 + c, vo1);
+          ptk_stv<double, VW>(po2 + r * rso2 + c, vo2);
+        }
+      }
+  }
+  // flat tail (rows == 1 only): the last n_total % VW elements
+  for (long long i = tail_start + gtid; i < n_total; i += gstride) {
+      double to0;
+      double to1;
+      double to2;
+      ptk_body(pi0[i], pi1[i], to0, to1, to2);
+      po0[i] = to0;
+      po1[i] = to1;
+      po2[i] = to2;
+  }
+}

@@ -100,7 +100,7 @@ constexpr int SK_MAXK = 16;
 // (two rows per iteration for memory-level parallelism).  Register budget matters here: the K <= 8 instance must keep
 // >= 3 CTAs per SM resident or the kernel turns latency-bound.
 template <typename T, int KMAX>
-__global__ void __launch_bounds__(256, (KMAX <= 8 ? 3 : 1)) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
+__global__ void __launch_bounds__(256, (KMAX <= 8 ? (sizeof(T) == 4 ? 3 : 2) : 1)) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
                                                           int64_t sa0, int64_t sa1, const T* __restrict__ B, int64_t sb0,
                                                           int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
@@ -111,29 +111,41 @@ __global__ void __launch_bounds__(256, (KMAX <= 8 ? 3 : 1)) gemm_smallk_kernel(i
   for (int k = 0; k < KMAX; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + (n0 + j) * sb1] : T(0);
-  for (int64_t m = (int64_t)blockIdx.y * 4 + ty; m < M; m += (int64_t)gridDim.y * 4) {
-    T av[KMAX];
+  // R rows per iteration: all A loads of the R rows are issued before the first FMA (memory-level parallelism)
+  constexpr int R = (KMAX <= 8 && sizeof(T) == 4) ? 4 : 2;
+  const int64_t mstep = (int64_t)gridDim.y * 4;
+  for (int64_t mb = (int64_t)blockIdx.y * 4 + ty; mb < M; mb += mstep * R) {
+    T av[R][KMAX];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) av[k] = (k < K) ? A[m * sa0 + k * sa1] : T(0);  // all loads first, then the FMAs
-    T acc[4] = {T(0), T(0), T(0), T(0)};
+    for (int r = 0; r < R; ++r) {
+      const int64_t m = mb + r * mstep;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] += av[k] * b[k][j];
+      for (int k = 0; k < KMAX; ++k) av[r][k] = (k < K && m < M) ? A[m * sa0 + k * sa1] : T(0);
     }
-    T* c = C + m * sc0 + n0;
-    if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
-      struct __align__(4 * sizeof(T)) V4 { T v[4]; } out;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
-      *reinterpret_cast<V4*>(c) = out;  // one 128-bit (fp32) / 256-bit (fp64) store: full 32-byte sectors
-    } else {
+    for (int r = 0; r < R; ++r) {
+      const int64_t m = mb + r * mstep;
+      if (m >= M) continue;
+      T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (n0 + j < N) {
-          T v = alpha * acc[j];
-          if (beta != T(0)) v += beta * c[j];
-          c[j] = v;
+      for (int k = 0; k < KMAX; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += av[r][k] * b[k][j];
+      }
+      T* c = C + m * sc0 + n0;
+      if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
+        struct __align__(4 * sizeof(T)) V4 { T v[4]; } out;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
+        *reinterpret_cast<V4*>(c) = out;  // one 128-bit (fp32) / 256-bit (fp64) store: full 32-byte sectors
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + j < N) {
+            T v = alpha * acc[j];
+            if (beta != T(0)) v += beta * c[j];
+            c[j] = v;
+          }
         }
       }
     }
@@ -258,7 +270,7 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
     return PTK_OK;
   }
   if (bias == nullptr && act == 0 && N <= SN_MAXN && sa1 == 1 && M >= 256 && K >= 64) {
-    unsigned gx = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)sms * 2);
+    unsigned gx = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)sms * 4);
 #define PTK_SN(NN) launch_smalln<T, NN>(M, (int)N, K, (T)alpha, (const T*)A, sa0, (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0, sc1, gx, st)
     ptk_status sn;
     if (N <= 1) sn = PTK_SN(1);

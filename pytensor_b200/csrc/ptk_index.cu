@@ -197,6 +197,52 @@ __global__ void __launch_bounds__(256) take_lastaxis_kernel(T* __restrict__ out,
   }
 }
 
+// take along the last axis when the source rows are small: a CTA stages ROWS source rows in shared memory (coalesced), then
+// every thread gathers 4 consecutive j for each staged row from shared memory and stores 128-bit — no global-memory
+// latency inside the gather, fully coalesced writes (the kernel is bound by the output write).
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(256) take_lastaxis_smem_kernel(T* __restrict__ out, const T* __restrict__ src,
+                                                                 const int64_t* __restrict__ idx, int64_t outer, int64_t n_src,
+                                                                 int64_t n_idx, int* err) {
+  extern __shared__ unsigned char take_smem[];
+  T* rows = reinterpret_cast<T*>(take_smem);  // [ROWS][n_src]
+  const int64_t o0 = (int64_t)blockIdx.y * ROWS;
+  const int nrows = (int)min((int64_t)ROWS, outer - o0);
+  const T* s0 = src + o0 * n_src;
+  for (int64_t e = threadIdx.x; e < (int64_t)nrows * n_src; e += blockDim.x) rows[e] = s0[e];
+  __syncthreads();
+  for (int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < n_idx; j0 += (int64_t)gridDim.x * blockDim.x * 4) {
+    int k[4];
+    bool ok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ok[e] = j0 + e < n_idx;
+      int64_t v = ok[e] ? idx[j0 + e] : 0;
+      if (v < 0) v += n_src;
+      if (v < 0 || v >= n_src) {
+        if (ok[e] && err) atomicExch(err, 1);
+        ok[e] = false;
+        v = 0;
+      }
+      k[e] = (int)v;
+    }
+    const bool vec = ok[0] && ok[1] && ok[2] && ok[3] && (n_idx % 4 == 0) && sizeof(T) == 4 && (((uintptr_t)out & 15) == 0);
+    for (int r = 0; r < nrows; ++r) {
+      const T* sr = rows + (int64_t)r * n_src;
+      T* d = out + (o0 + r) * n_idx + j0;
+      if (vec) {
+        uint4 v;
+        v.x = (uint32_t)sr[k[0]]; v.y = (uint32_t)sr[k[1]]; v.z = (uint32_t)sr[k[2]]; v.w = (uint32_t)sr[k[3]];
+        *reinterpret_cast<uint4*>(d) = v;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ok[e]) d[e] = sr[k[e]];
+      }
+    }
+  }
+}
+
 // ---- scatter-add along the last axis with an index vector shared by all rows: a deterministic segmented reduction ----------
 // (1) histogram + exclusive scan of the destination bins; (2) stable fill of the permutation; (3) one warp per row.
 __global__ void __launch_bounds__(1024) put_rows_offsets_kernel(const int64_t* __restrict__ idx, int64_t n_idx, int64_t n_dst,
@@ -244,7 +290,12 @@ __global__ void __launch_bounds__(256) put_rows_kernel(T* __restrict__ dst, cons
                                                        const int* __restrict__ offsets, const int* __restrict__ perm,
                                                        int64_t outer, int64_t n_dst, int64_t n_idx, int warps_per_block) {
   extern __shared__ unsigned char put_smem[];
-  T* ys = reinterpret_cast<T*>(put_smem);
+  int* s_off = reinterpret_cast<int*>(put_smem);            // [n_dst + 1]
+  int* s_perm = s_off + (n_dst + 1);                        // [n_idx]
+  T* ys = reinterpret_cast<T*>(s_perm + n_idx + ((n_dst + 1 + n_idx) & 1));  // 8-byte aligned rows
+  for (int64_t i = threadIdx.x; i <= n_dst; i += blockDim.x) s_off[i] = offsets[i];
+  for (int64_t i = threadIdx.x; i < n_idx; i += blockDim.x) s_perm[i] = perm[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= warps_per_block) return;
   T* mine = ys + (int64_t)warp * n_idx;
@@ -261,11 +312,18 @@ __global__ void __launch_bounds__(256) put_rows_kernel(T* __restrict__ dst, cons
     for (; i < n_idx; i += 32) mine[i] = yrow[i];
     __syncwarp();
     T* drow = dst + o * n_dst;
-    for (int64_t j = lane; j < n_dst; j += 32) {
-      T acc = drow[j];
-      const int lo = offsets[j], hi = offsets[j + 1];
-      for (int p = lo; p < hi; ++p) acc += mine[perm[p]];
-      drow[j] = acc;
+    for (int64_t j = lane; j < n_dst; j += 64) {   // two destination bins per lane, their chains interleaved
+      const int64_t j2 = j + 32;
+      const bool has2 = j2 < n_dst;
+      T acc0 = drow[j], acc1 = has2 ? drow[j2] : T(0);
+      int p0 = s_off[j], e0 = s_off[j + 1];
+      int p1 = has2 ? s_off[j2] : 0, e1 = has2 ? s_off[j2 + 1] : 0;
+      while (p0 < e0 || p1 < e1) {
+        if (p0 < e0) acc0 += mine[s_perm[p0++]];
+        if (p1 < e1) acc1 += mine[s_perm[p1++]];
+      }
+      drow[j] = acc0;
+      if (has2) drow[j2] = acc1;
     }
     __syncwarp();
   }
@@ -347,6 +405,24 @@ ptk_status ptk_take(void* out, const void* src, const int64_t* idx, int64_t oute
   int64_t total = outer * n_idx * inner;
   if (total == 0) return PTK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (inner == 1 && outer >= 64 && n_idx >= 64 && n_src * 16 * itemsize <= 40 * 1024 && outer / 16 <= 65535 * 16LL) {
+    constexpr int ROWS = 16;
+    unsigned gx = (unsigned)std::min<int64_t>((n_idx + 1023) / 1024, 8);
+    dim3 grid(gx, (unsigned)((outer + ROWS - 1) / ROWS));
+    if (grid.y <= 65535u * 16u && grid.y <= 2147483647u) {
+      size_t smem = (size_t)ROWS * n_src * itemsize;
+      if (grid.y > 65535) grid = dim3(gx, 65535);  // (guarded above; kept for clarity)
+      switch (itemsize) {
+        case 1: take_lastaxis_smem_kernel<uint8_t, ROWS><<<dim3(gx, (unsigned)((outer + ROWS - 1) / ROWS)), 256, smem, st>>>((uint8_t*)out, (const uint8_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+        case 2: take_lastaxis_smem_kernel<uint16_t, ROWS><<<dim3(gx, (unsigned)((outer + ROWS - 1) / ROWS)), 256, smem, st>>>((uint16_t*)out, (const uint16_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+        case 4: take_lastaxis_smem_kernel<uint32_t, ROWS><<<dim3(gx, (unsigned)((outer + ROWS - 1) / ROWS)), 256, smem, st>>>((uint32_t*)out, (const uint32_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+        case 8: take_lastaxis_smem_kernel<uint64_t, ROWS><<<dim3(gx, (unsigned)((outer + ROWS - 1) / ROWS)), 256, smem, st>>>((uint64_t*)out, (const uint64_t*)src, idx, outer, n_src, n_idx, err_flag); break;
+        default: return fail(PTK_ERR_ARG, "ptk_take: itemsize must be 1, 2, 4 or 8");
+      }
+      PTK_LAUNCH_CHECK("take_lastaxis_smem");
+      return PTK_OK;
+    }
+  }
   if (inner == 1 && outer >= 8 && n_idx >= 64) {
     unsigned gx = (unsigned)((n_idx + 1023) / 1024);
     unsigned gy = (unsigned)std::min<int64_t>(outer, std::max<int64_t>(1, (int64_t)std::max(1, ptk::sm_count()) * 16 / gx));
@@ -418,8 +494,12 @@ ptk_status ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t ou
   int* perm = offsets + (n_dst + 1);
   put_rows_offsets_kernel<<<1, 1024, (size_t)(n_dst + 1) * sizeof(int), st>>>(idx, n_idx, n_dst, offsets, err_flag);
   put_rows_perm_kernel<<<(unsigned)((n_dst + 255) / 256), 256, (size_t)n_idx * sizeof(int), st>>>(idx, n_idx, n_dst, offsets, perm);
-  int wpb = (int)std::max<int64_t>(1, std::min<int64_t>(8, (48 * 1024) / (n_idx * isz)));
-  size_t smem = (size_t)wpb * n_idx * isz;
+  const size_t meta = (size_t)(n_dst + 1 + n_idx + 1) * sizeof(int);
+  if (meta + (size_t)n_idx * isz > 96 * 1024) return fail(PTK_ERR_UNSUPPORTED, "ptk_put_rows: index set too large for shared memory");
+  int wpb = (int)std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)(96 * 1024 - meta) / (n_idx * isz)));
+  size_t smem = meta + (size_t)wpb * n_idx * isz;
+  PTK_CUDA(cudaFuncSetAttribute(put_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  PTK_CUDA(cudaFuncSetAttribute(put_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   unsigned grid = (unsigned)std::min<int64_t>((outer + wpb - 1) / wpb, (int64_t)std::max(1, ptk::sm_count()) * 8);
   if (dtype == PTK_F32)
     put_rows_kernel<float><<<grid, 256, smem, st>>>((float*)dst, (const float*)y, offsets, perm, outer, n_dst, n_idx, wpb);

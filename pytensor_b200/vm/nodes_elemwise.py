@@ -18,12 +18,6 @@ from ..runtime import jit
 from ..runtime import lib as _lib
 from .values import Val
 
-_uid = [0]
-
-
-def _kname(prefix: str) -> str:
-    _uid[0] += 1
-    return f"{prefix}_{_uid[0]}"
 
 
 class Node:
@@ -41,7 +35,7 @@ class Node:
 
     # Nodes are plain data + caches of device handles; only the data is pickled (a lowered Program can be shipped to a
     # box that has torch + libptk but no host framework).
-    _TRANSIENT = ("_kernels", "_fn", "_const_cache", "_flag")
+    _TRANSIENT = ("_kernels", "_fn", "_const_cache", "_flag", "_plans")
 
     def __getstate__(self):
         d = dict(self.__dict__)
@@ -167,6 +161,7 @@ class ElemwiseNode(Node):
         self.n_out = len(prog.out_dtypes)
         self.name = name
         self._kernels = {}
+        self._plans = {}
         self._host_ok = all((not is_float(d)) for d in list(prog.in_dtypes) + list(prog.out_dtypes))
 
     # -- shape logic -------------------------------------------------------------------------------------------------
@@ -198,30 +193,53 @@ class ElemwiseNode(Node):
                 if res is not None:
                     return [Val(h=np.broadcast_to(r, oshape).copy() if tuple(np.shape(r)) != tuple(oshape) else r)
                             for r in res]
-        oshape = self._out_shape([v.shape for v in vals])  # shape errors surface before any transfer
+        if any(v.d is None for v in vals):
+            self._out_shape([v.shape for v in vals])  # shape errors surface before any host->device transfer
         ins = [v.dev() for v in vals]
-        # output layout follows a dense full-shape input (elemwise.py:935-961) so that the pair collapses together
-        order = None
-        for k, t in enumerate(ins):
-            if tuple(t.shape) == tuple(oshape) and not any(self.in_bcast[k]):
-                order = _dense_order(t)
-                break
+        # launch-plan cache: same operand layouts (shape, strides, 16-byte alignment class) => same kernel, grid and
+        # argument block; only the pointers change.  Keeps the eager per-node host cost at allocation + one ctypes call.
+        pkey = tuple((tuple(t.shape), t.stride(), t.data_ptr() & 31) for t in ins)
+        plan = self._plans.get(pkey)
+        if plan is None:
+            oshape = self._out_shape([tuple(t.shape) for t in ins])  # raises on runtime broadcasting
+            order = None
+            for k, t in enumerate(ins):
+                if tuple(t.shape) == tuple(oshape) and not any(self.in_bcast[k]):
+                    order = _dense_order(t)
+                    break
+            total = 1
+            for s_ in oshape:
+                total *= s_
+            plan = [oshape, order, total, None]
+            if len(self._plans) > 64:
+                self._plans.clear()
+            self._plans[pkey] = plan
+        oshape, order, total, launch = plan
         outs = []
         for k, dt in enumerate(self.prog.out_dtypes):
             if k in self.inplace:
                 outs.append(ins[self.inplace[k]])
             else:
                 outs.append(dev.empty_like_layout(oshape, dt, order))
-        total = 1
-        for s in oshape:
-            total *= s
         if total == 0:
             return [Val(d=o) for o in outs]
-        self._launch(ins, outs, oshape)
+        if launch is None or (outs and (outs[0].data_ptr() & 31)):
+            launch = self._plan_launch(ins, outs, oshape)
+            plan[3] = launch
+            fn, grid, kargs, nptr = launch
+        else:
+            fn, grid, kargs, nptr = launch
+            ptrs = kargs._vals
+            for j, t in enumerate(ins):
+                ptrs[j].value = t.data_ptr()
+            for j, t in enumerate(outs):
+                ptrs[len(ins) + j].value = t.data_ptr()
+        jit.launch(fn, (grid,), (256,), kargs, 0, dev.stream_ptr())
         return [Val(d=o) for o in outs]
 
     # -- launch --------------------------------------------------------------------------------------------------------
-    def _launch(self, ins, outs, oshape):
+    def _plan_launch(self, ins, outs, oshape):
+        """Kernel selection + argument block for these operand layouts: (fn, grid, KernelArgs, n_pointer_slots)."""
         nd = self.ndim
         ops = ins + outs
         strides = []
@@ -264,8 +282,7 @@ class ElemwiseNode(Node):
             per_block = 256 * cg_ew.VEC_UNROLL
             want = max(1, (max(nchunks, n_total - tail_start) + per_block - 1) // per_block)
             grid = min(want, _lib.sm_count() * 8)
-            jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, stream)
-            return
+            return fn, grid, jit.KernelArgs(args), len(ops)
         if len(cshape) > cg_ew.MAX_DIMS:
             raise NotImplementedError(f"{self.name}: more than {cg_ew.MAX_DIMS} non-collapsible dims")
         key = ("gen",)
@@ -290,7 +307,7 @@ class ElemwiseNode(Node):
                 d.st[j][i] = s
         args = [c_void_p(dev.ptr(t)) for t in ops] + [d, c_longlong(total)]
         grid = min(max(1, (total + 255) // 256), _lib.sm_count() * 16)
-        jit.launch(fn, (grid,), (256,), jit.KernelArgs(args), 0, stream)
+        return fn, grid, jit.KernelArgs(args), len(ops)
 
     @staticmethod
     def _vec_ok(ops, dtypes, cshape, csts, vw):

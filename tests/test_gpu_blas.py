@@ -101,3 +101,25 @@ def test_skinny_gemm_shapes(gpu, dtype):
     Rv = rng.standard_normal((1500, 1030)).astype(dtype)
     tol = dict(rtol=2e-4, atol=2e-4) if dtype == "float32" else dict(rtol=1e-9, atol=1e-9)
     compare_cuda_and_cvm([beta, X, R], [pt.dot(beta, X.T), pt.dot(R, X), 0.5 * R + 2.0 * pt.dot(beta, X.T)], [bv, Xv, Rv], **tol)
+
+
+def test_gemm_zero_sized_and_broadcast_z(gpu):
+    # zero-size operands (tests/tensor/test_blas.py:185-191) and a row-broadcast Z (gemm.py:194-198)
+    rng = np.random.default_rng(28)
+    x, y = pt.dmatrix("x"), pt.dmatrix("y")
+    zrow = pt.drow("zrow")
+    compare_cuda_and_cvm([x, y], [pt.dot(x, y)], [np.zeros((0, 5)), rng.standard_normal((5, 7))])
+    compare_cuda_and_cvm([x, y], [pt.dot(x, y)], [rng.standard_normal((4, 0)), np.zeros((0, 7))])
+    compare_cuda_and_cvm([zrow, x, y], [zrow + 2.0 * pt.dot(x, y)],
+                         [rng.standard_normal((1, 7)), rng.standard_normal((4, 5)), rng.standard_normal((5, 7))])
+
+
+def test_gemv_beta_zero_ignores_nan_y(gpu):
+    # contract: beta == 0 => y's contents (possibly NaN from AllocEmpty) are never read (gemv.py:79-86)
+    rng = np.random.default_rng(29)
+    A, x = pt.dmatrix("A"), pt.dvector("x")
+    Av, xv = rng.standard_normal((33, 17)), rng.standard_normal(17)
+    f, got = compare_cuda_and_cvm([A, x], [pt.dot(A, x)], [Av, xv])
+    assert np.all(np.isfinite(got[0]))
+    for _ in range(3):  # repeated calls reuse NaN-poisoned allocator blocks; result must stay finite
+        assert np.all(np.isfinite(f(Av, xv)[0]))

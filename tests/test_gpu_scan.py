@@ -110,3 +110,44 @@ def test_known_answer_two_mit_mots(gpu):
     touts = [o.sum() for o in op(*tins)]
     f = pytensor.function(tins, touts, mode="CUDA")
     np.testing.assert_allclose(f(*vals), [44, 38])
+
+
+def test_nested_scan_with_until_known_answer(gpu):
+    # nested Scan whose inner Scan stops early (tests/scan/test_basic.py:3852-3898 expects [3, 1, 0])
+    from pytensor.scan.utils import until
+
+    def fn(n):
+        s_in_y = scan(fn=lambda z: (z + 1, until(z > 2)),
+                      outputs_info=[{"taps": [-1], "initial": pt.as_tensor(0.0, dtype=np.float64)}],
+                      n_steps=n - 1, return_updates=False)
+        return s_in_y.sum()
+
+    s_y = scan(fn=fn, outputs_info=[None], sequences=[pt.as_tensor([3, 2, 1], dtype=np.int64)], return_updates=False)
+    f = pytensor.function([], s_y, mode="CUDA")
+    np.testing.assert_array_equal(f(), np.array([3, 1, 0]))
+
+
+def test_truncated_trace_buffers_and_taps(gpu):
+    # save-mem rewrites shrink trace buffers to the taps actually used (circular buffers + final rotation)
+    rng = np.random.default_rng(53)
+    x0 = pt.dmatrix("x0")  # (3, n) initial taps
+    u = pt.dmatrix("u")
+
+    def step(u_t, x3, x1):
+        return 0.3 * x1 + 0.2 * x3 + pt.sin(u_t)
+
+    xs = scan(step, sequences=[u], outputs_info=[dict(initial=x0, taps=[-3, -1])], return_updates=False)
+    uv = rng.standard_normal((40, 9))
+    x0v = rng.standard_normal((3, 9))
+    compare_cuda_and_cvm([u, x0], [xs[-1], xs[-2] + xs[-4], xs[::7]], [uv, x0v], rtol=1e-10, atol=1e-12)
+
+
+def test_scan_with_shared_non_sequence_and_sum_of_nit_sot(gpu):
+    rng = np.random.default_rng(54)
+    W = pytensor.shared(rng.standard_normal((6, 6)) * 0.3, name="W")
+    v = pt.dvector("v")
+    seq = pt.dmatrix("seq")
+    hs, ys = scan(lambda s_t, h: (pt.tanh(pt.dot(h, W) + s_t), (h ** 2).sum()), sequences=[seq],
+                  outputs_info=[v, None], return_updates=False)
+    compare_cuda_and_cvm([v, seq], [hs[-1], ys, ys.sum()], [rng.standard_normal(6), rng.standard_normal((11, 6))],
+                         rtol=1e-9, atol=1e-10)
