@@ -96,41 +96,43 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int64_t M, int64_t N, in
 
 // ---- skinny shapes (PyMC-style regressions: (B x K)(K x n) with K ~ 8 and (B x n)(n x K)): HBM-bound on the big operand --------
 constexpr int SK_MAXK = 16;
-// K <= KMAX (4 / 8 / 16), C unit-stride along N: a thread keeps its K x 4 slab of B in registers and streams rows of A / C
-// (two rows per iteration for memory-level parallelism).  Register budget matters here: the K <= 8 instance must keep
-// >= 3 CTAs per SM resident or the kernel turns latency-bound.
+// K <= KMAX (4 / 8 / 16), C unit-stride along N.  A CTA owns 256 output columns; every thread keeps its K x 4 slab of B in
+// registers.  Rows are processed in tiles of 64: the tile's 64 x K block of A is staged in shared memory with ONE coalesced
+// global load per thread (latency paid once per 64 rows, hidden by the other resident CTAs), then each thread produces
+// 16 rows x 4 columns from broadcast LDS + FMAs and writes them with 128-bit stores.  Bound by the write of C.
 template <typename T, int KMAX>
-__global__ void __launch_bounds__(256, (KMAX <= 8 ? (sizeof(T) == 4 ? 3 : 2) : 1)) gemm_smallk_kernel(int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A,
-                                                          int64_t sa0, int64_t sa1, const T* __restrict__ B, int64_t sb0,
-                                                          int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2)) gemm_smallk_kernel(
+    int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t sa0, int64_t sa1, const T* __restrict__ B,
+    int64_t sb0, int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
+  constexpr int TR = 64;
+  __shared__ T As[TR][KMAX + 1];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
   const int64_t n0 = ((int64_t)blockIdx.x * 64 + tx) * 4;
-  if (n0 >= N) return;
   T b[KMAX][4];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + (n0 + j) * sb1] : T(0);
-  // R rows per iteration: all A loads of the R rows are issued before the first FMA (memory-level parallelism)
-  constexpr int R = (KMAX <= 8 && sizeof(T) == 4) ? 4 : 2;
-  const int64_t mstep = (int64_t)gridDim.y * 4;
-  for (int64_t mb = (int64_t)blockIdx.y * 4 + ty; mb < M; mb += mstep * R) {
-    T av[R][KMAX];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t m = mb + r * mstep;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) av[r][k] = (k < K && m < M) ? A[m * sa0 + k * sa1] : T(0);
+  const bool col_ok = n0 < N;
+  for (int64_t m0 = (int64_t)blockIdx.y * TR; m0 < M; m0 += (int64_t)gridDim.y * TR) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TR * KMAX; e += blockDim.x) {
+      const int r = e / KMAX, k = e - r * KMAX;
+      As[r][k] = (m0 + r < M && k < K) ? A[(m0 + r) * sa0 + k * sa1] : T(0);
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t m = mb + r * mstep;
-      if (m >= M) continue;
+    __syncthreads();
+    if (!col_ok) continue;
+#pragma unroll 4
+    for (int rr = 0; rr < TR / 4; ++rr) {
+      const int r = rr * 4 + ty;
+      const int64_t m = m0 + r;
+      if (m >= M) break;
       T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
+        const T a = As[r][k];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += av[r][k] * b[k][j];
+        for (int j = 0; j < 4; ++j) acc[j] += a * b[k][j];
       }
       T* c = C + m * sc0 + n0;
       if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
@@ -259,7 +261,7 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
   const int sms = std::max(1, ptk::sm_count());
   if (bias == nullptr && act == 0 && K >= 1 && K <= SK_MAXK && sc1 == 1 && M >= 256 && N >= 64) {
     unsigned gx = (unsigned)((N + 255) / 256);
-    unsigned gy = (unsigned)std::min<int64_t>((M + 3) / 4, std::max<int64_t>(1, (int64_t)sms * 12 / gx));
+    unsigned gy = (unsigned)std::min<int64_t>((M + 63) / 64, std::max<int64_t>(1, (int64_t)sms * 12 / gx));
 #define PTK_SK(KM) gemm_smallk_kernel<T, KM><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, \
                                                                       (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0)
     if (K <= 4) PTK_SK(4);
