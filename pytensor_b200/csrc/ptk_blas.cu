@@ -135,11 +135,17 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2)) gemm_smallk_ker
         for (int j = 0; j < 4; ++j) acc[j] += a * b[k][j];
       }
       T* c = C + m * sc0 + n0;
-      if (n0 + 3 < N && beta == T(0) && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
+      if (n0 + 3 < N && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0)) {
         struct __align__(4 * sizeof(T)) V4 { T v[4]; } out;
+        if (beta != T(0)) {  // Gemm accumulating into Z: vector read-modify-write, never touched when beta == 0
+          const V4 old = *reinterpret_cast<const V4*>(c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
-        *reinterpret_cast<V4*>(c) = out;  // one 128-bit (fp32) / 256-bit (fp64) store: full 32-byte sectors
+          for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j] + beta * old.v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
+        }
+        *reinterpret_cast<V4*>(c) = out;  // one 128-bit (fp32) / 256-bit (fp64) access: full 32-byte sectors
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
