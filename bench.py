@@ -219,7 +219,7 @@ def extra_workloads(pytensor, W, cuda_mode, dev, torch, peaks):
     return out
 
 
-def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10, B_local=1 << 17):
+def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10, B_local=1 << 17, collective="nccl"):
     """BASELINE.json configs[4]: hierarchical logp+grad, batch = world x 2^17 independent parameter vectors (2^20 at 8
     GPUs), sharded along the batch axis, ONE packed NCCL all-reduce of [logp, grads] (75 floats) per evaluation."""
     from pytensor_b200.sharded import ShardedSum
@@ -227,7 +227,7 @@ def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10
     ins, outs, make_args, meta = W.cfg5_logp_grad(B=B_local * world, n=1024, J=64, K=8, dtype="float32", packed=True)
     f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True), trust_input=True)
     local = [dev.to_device(a) for a in make_args(seed=20 + rank, B_local=B_local)]
-    sh = ShardedSum(f, batch_arg_idx=[0, 1, 2, 3])
+    sh = ShardedSum(f, batch_arg_idx=[0, 1, 2, 3], collective=collective)
     for _ in range(4):
         res = sh(*local, presharded=True)
     if dist is not None:
@@ -250,7 +250,7 @@ def sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, steps=10
     return {"evals_per_s": steps / (ms * 1e-3), "ms_per_eval": ms / steps, "chains_per_s": B_local * world * steps / (ms * 1e-3),
             "global_batch": B_local * world, "per_gpu_batch": B_local, "n_rows": 1024, "allreduce_floats": 1 + meta["P"],
             "scaling": "weak (2^17 chains per GPU; 2^20 at 8 GPUs)", "nodes": len(f.maker.fgraph.toposort()),
-            "logp_sum": logp, "graph_replay": bool(f.vm.executor.last_from_graph)}
+            "logp_sum": logp, "graph_replay": bool(f.vm.executor.last_from_graph), "collective": collective if world > 1 else None}
 
 
 def main():
@@ -414,6 +414,12 @@ def main():
             sharded = sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank)
         except Exception as e:  # noqa: BLE001
             sharded = {"error": repr(e)[:400]}
+        if world > 1 and "error" not in sharded:
+            try:  # the same evaluation with the hand-written one-shot NVLink all-reduce instead of NCCL
+                alt = sharded_logp(pytensor, W, cuda_mode, dev, torch, dist, world, rank, collective="oneshot")
+                sharded["oneshot_nvlink"] = {k: alt[k] for k in ("evals_per_s", "ms_per_eval", "logp_sum")}
+            except Exception as e:  # noqa: BLE001
+                sharded["oneshot_nvlink"] = {"error": repr(e)[:300]}
 
     line = {
         "metric": "fn evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,

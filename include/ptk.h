@@ -148,6 +148,15 @@ ptk_status   ptk_potrf(int dtype, void* A, int64_t n, int64_t batch, int lower, 
 ptk_status   ptk_trsm(int dtype, const void* A, void* B, int64_t n, int64_t nrhs, int64_t batch,
                       int lower, int trans, int unit_diag, void* stream);
 
+/* ---- multi-GPU exchange (no counterpart in the reference, which has no collectives) ----------------------
+ * One-shot all-reduce (sum) of a small vector (n <= nmax) over NVLink peer memory.  `peer_ptrs[world]` (host array) are the
+ * addresses of every rank's symmetric buffer of ptk_allreduce_oneshot_buffer_bytes() bytes, zero-initialised once;
+ * `epoch_ctr` is a zero-initialised device uint32 owned by this rank.  Collective: every rank must call it the same number of
+ * times.  The result (sum in rank order, identical on all ranks) lands in `out`; no host synchronisation. */
+size_t       ptk_allreduce_oneshot_buffer_bytes(int world, int64_t nmax, int itemsize);
+ptk_status   ptk_allreduce_oneshot(int dtype, const void* in, void* out, int64_t n, const uint64_t* peer_ptrs, int rank,
+                                   int world, int64_t nmax, void* epoch_ctr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,9 @@ SIGNATURES = {
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                         c_int64, c_void_p]),
+    "ptk_allreduce_oneshot_buffer_bytes": (c_size_t, [c_int, c_int64, c_int]),
+    "ptk_allreduce_oneshot": (c_int, [c_int, c_void_p, c_void_p, c_int64, POINTER(ctypes.c_uint64), c_int, c_int, c_int64,
+                                      c_void_p, c_void_p]),
     "ptk_potrf": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "ptk_trsm": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
 }

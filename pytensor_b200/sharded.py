@@ -34,13 +34,74 @@ def shard_args(args, batch_arg_idx, world, rank):
     return out
 
 
+class PeerAllReduce:
+    """One-shot all-reduce of a small vector over NVLink peer memory (libptk `ptk_allreduce_oneshot`).
+
+    torch.distributed's symmetric-memory rendezvous is used ONLY to obtain peer-mapped pointers to every rank's buffer;
+    the data movement and the reduction are one hand-written kernel per rank (push to all peers, flag, wait, sum)."""
+
+    def __init__(self, group=None, nmax=1024, dtype="float32"):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from pytensor_b200.runtime import device as dev
+        from pytensor_b200.runtime import lib as _lib
+
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.nmax = int(nmax)
+        self.dtype = dtype
+        isz = 4 if dtype == "float32" else 8
+        L = _lib.lib()
+        nbytes = int(L.ptk_allreduce_oneshot_buffer_bytes(self.world, self.nmax, isz))
+        dev.device()
+        self.buf = symm.empty((nbytes + 3) // 4, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        _lib.check(L.ptk_memset_async(self.buf.data_ptr(), 0, self.buf.numel() * 4, dev.stream_ptr()), "memset")
+        dev.synchronize()
+        try:  # needed by older torch releases, a no-op / deprecated in newer ones
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:  # noqa: BLE001
+            pass
+        self.handle = symm.rendezvous(self.buf, self.group.group_name)
+        ptrs = list(self.handle.buffer_ptrs)
+        self.peer_ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in ptrs])
+        self.epoch = dev.empty((1,), "int32")
+        _lib.check(L.ptk_memset_async(self.epoch.data_ptr(), 0, 4, dev.stream_ptr()), "memset")
+        dev.synchronize()
+        dist.barrier(self.group)  # every rank's buffer is zeroed before the first push can land
+        self._L, self._lib, self._dev = L, _lib, dev
+
+    def __call__(self, x, out=None):
+        """x: contiguous device vector (n <= nmax). Returns the element-wise sum over ranks (in `out` or in place)."""
+        n = x.numel()
+        if out is None:
+            out = x
+        self._lib.check(
+            self._L.ptk_allreduce_oneshot(self._lib.DTYPE_CODE[self.dtype], x.data_ptr(), out.data_ptr(), n, self.peer_ptrs,
+                                          self.rank, self.world, self.nmax, self.epoch.data_ptr(), self._dev.stream_ptr()),
+            "ptk_allreduce_oneshot")
+        return out
+
+
 class ShardedSum:
     """Callable wrapper: `f_local(*local_args) -> list of batch-summed partial outputs` on each rank, then one packed
     all-reduce.  Works for NumPy outputs (CPU/gloo) and device tensors (NCCL)."""
 
-    def __init__(self, f_local, batch_arg_idx, group=None):
+    def __init__(self, f_local, batch_arg_idx, group=None, collective="nccl"):
+        """collective: "nccl" (torch.distributed all_reduce) or "oneshot" (PeerAllReduce; packed device outputs only)."""
         import torch.distributed as dist
 
+        self.collective = collective
+        self._peer = None
         self.f = f_local
         self.batch_arg_idx = list(batch_arg_idx)
         self.group = group
@@ -61,7 +122,12 @@ class ShardedSum:
         sizes = [int(np.prod(o.shape)) if len(o.shape) else 1 for o in outs]
         total = sum(sizes)
         if len(outs) == 1 and isinstance(outs[0], torch.Tensor) and outs[0].is_contiguous():
-            # the graph already packed its partials into one vector: reduce it in place, one NCCL call, no copies
+            # the graph already packed its partials into one vector: reduce it in place, ONE collective, no copies
+            if self.collective == "oneshot" and outs[0].numel() <= 1024 and outs[0].dtype in (torch.float32, torch.float64):
+                if self._peer is None:
+                    self._peer = PeerAllReduce(self.group, 1024, "float32" if outs[0].dtype == torch.float32 else "float64")
+                self._peer(outs[0])
+                return outs
             self.dist.all_reduce(outs[0], op=self.dist.ReduceOp.SUM, group=self.group)
             return outs
         if isinstance(outs[0], torch.Tensor):
