@@ -242,6 +242,22 @@ def lower_node(node, opts):
         return nlin.SolveTriangularNode(node.outputs[0].type.dtype, bool(core.lower), bool(core.unit_diagonal),
                                         int(core.b_ndim), name=str(op))
 
+    if cname == "BatchedDot":
+        dt = node.outputs[0].type.dtype
+        if dt not in ("float32", "float64"):
+            raise UnsupportedOp(f"BatchedDot with dtype {dt}")
+        return nblas.BatchedDotNode(dt, prec, name=str(op))
+
+    from pytensor.compile.builders import OpFromGraph
+
+    if isinstance(op, OpFromGraph):
+        from pytensor_b200.link.cuda.linker import build_program
+        from pytensor_b200.vm.nodes_inner import InnerProgramNode
+
+        inner = op.fgraph
+        program, _ = build_program(inner, list(inner.toposort()), dict(opts), storage_map=None)
+        return InnerProgramNode(program, len(node.outputs), name=str(op))
+
     if cname == "Scan":
         from pytensor_b200.link.cuda.lower_scan import lower_scan
 

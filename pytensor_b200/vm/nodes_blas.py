@@ -239,3 +239,27 @@ class GemmBiasActNode(Node):
                        want_bf16=self.emit_bf16)
             return [Val(d=out, aux=aux)]
         return [Val(d=out)]
+
+
+class BatchedDotNode(Node):
+    """out[i] = dot(a[i], b[i]) over the leading batch axis (reference: BatchedDot, pytensor/tensor/blas/batched.py:18).
+    One GEMM launch per batch element on the current stream (strided views, no copies)."""
+
+    def __init__(self, dtype, precision=0, name="BatchedDot"):
+        self.dtype, self.precision, self.name = dtype, precision, name
+
+    def run(self, vals):
+        A, B = vals[0].dev(), vals[1].dev()
+        if A.shape[0] != B.shape[0] or A.shape[2] != B.shape[1]:
+            raise ValueError(f"{self.name}: shape mismatch {tuple(A.shape)} x {tuple(B.shape)}")
+        nb, M, K = A.shape
+        N = B.shape[2]
+        out = dev.empty((nb, M, N), self.dtype)
+        if out.numel():
+            if K == 0:
+                _lib.check(_lib.lib().ptk_memset_async(dev.ptr(out), 0, out.numel() * out.element_size(),
+                                                       dev.stream_ptr()), "memset")
+            else:
+                for i in range(nb):
+                    gemm(self.dtype, 1.0, A[i], B[i], 0.0, out[i], self.precision)
+        return [Val(d=out)]

@@ -80,3 +80,18 @@ def test_cfg5_logp_grad_small(gpu):
         compare_cuda_and_cvm(ins, outs, make_args(), rtol=1e-8, atol=1e-8)
     finally:
         pytensor.config.floatX = "float32"
+
+
+def test_op_from_graph_and_batched_dot(gpu):
+    from pytensor.compile.builders import OpFromGraph
+
+    rng = np.random.default_rng(62)
+    x, y = pt.dmatrix("x"), pt.dmatrix("y")
+    ofg = OpFromGraph([x, y], [pt.tanh(pt.dot(x, y)) + x.sum(), pt.exp(-x)], inline=False)
+    a, b = pt.dmatrix("a"), pt.dmatrix("b")
+    o1, o2 = ofg(a, b)
+    compare_cuda_and_cvm([a, b], [o1 * 2, o2.sum(axis=0)], [rng.standard_normal((5, 5)), rng.standard_normal((5, 5))],
+                         rtol=1e-9, atol=1e-10)
+    A3, B3 = pt.dtensor3("A3"), pt.dtensor3("B3")
+    compare_cuda_and_cvm([A3, B3], [pt.matmul(A3, B3)], [rng.standard_normal((4, 6, 7)), rng.standard_normal((4, 7, 3))],
+                         rtol=1e-9, atol=1e-10)
