@@ -160,6 +160,7 @@ struct EpiParams {
   int M, N, K;
   __nv_bfloat16* Cbf;  // optional bf16 copy of the result, row-major [M, ldcbf] (the next layer's K-major A operand)
   long long ldcbf;
+  int split_tail;      // pair kernel: split the units of the last partial round into 256 x 128 halves (PTK_GEMM_SPLIT=0: off)
 };
 
 // kCluster == 2: CTA pairs (cluster 2x1x1) share the B tile of a 256-row super-tile — each CTA loads HALF of it and
@@ -391,7 +392,8 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_m
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_bh, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                // P_STAGES x 16 KiB
@@ -411,10 +413,31 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int num_units = m_tiles * n_tiles;
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
+  // Wave-quantisation fix: the units of the last, partially filled round are split into two 256 x 128 HALF units when
+  // that fills the idle CTA pairs (e.g. 4096^2: 256 units on 74 pairs = 3 full rounds + 34 -> 68 half units, 3.5 rounds
+  // instead of 4).  The work list is: full units [0, full_units), then half units; all roles walk the same sequence.
+  // (Measured: a half unit costs ~0.9 of a full one because it re-reads the whole A tile for half the flops, so the gain
+  // is 1-7 %; splitting K instead, with the two partial tiles combined through global memory, measured slower.)
+  const int rem = num_units % unit_stride;
+  const bool split_tail = p.split_tail && rem > 0 && 2 * rem <= unit_stride && num_units > unit_stride;
+  const int full_units = split_tail ? num_units - rem : num_units;
+  const int seq_len = full_units + (split_tail ? 2 * rem : 0);
 
+  // work item `seq` -> tile row, first column, half-unit flag
+#define PTK_DECODE_UNIT(seq, tm, ncol0, half)                                     \
+  int tm, ncol0;                                                                  \
+  bool half;                                                                      \
+  {                                                                               \
+    half = (seq) >= full_units;                                                   \
+    const int h_ = ((seq) - full_units) & 1;                                      \
+    const int u_ = half ? full_units + ((seq) - full_units) / 2 : (seq);          \
+    tm = u_ % m_tiles;                                                            \
+    ncol0 = (u_ / m_tiles) * BLOCK_N + (half ? h_ * (BLOCK_N / 2) : 0);           \
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_bh);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -439,15 +462,19 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = unit0; u < num_units; u += unit_stride) {
-        const int tm = u % m_tiles, tn = u / m_tiles;
+      for (int sq = unit0; sq < seq_len; sq += unit_stride) {
+        PTK_DECODE_UNIT(sq, tm, ncol0, half)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full_bar[stage], half ? 2 * (P_A_BYTES + P_B_BYTES / 2) : 2 * P_STAGE_BYTES);
           tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * P_A_BYTES, kb * BLOCK_K,
                           tm * 2 * BLOCK_M + (int)crank * BLOCK_M);
-          tma_load_2d_2sm(&tmap_b, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
-                          tn * BLOCK_N + (int)crank * (BLOCK_N / 2));
+          if (half)  // this CTA's 64 of the 128 B rows of a half unit
+            tma_load_2d_2sm(&tmap_bh, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
+                            ncol0 + (int)crank * (BLOCK_N / 4));
+          else
+            tma_load_2d_2sm(&tmap_b, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
+                            ncol0 + (int)crank * (BLOCK_N / 2));
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -455,12 +482,14 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===== MMA issuer: ONE thread of the leader CTA drives both SMs' tensor cores =====
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_full = make_idesc(2 * BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_half = make_idesc(2 * BLOCK_M, BLOCK_N / 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = unit0; u < num_units; u += unit_stride) {
+      for (int sq = unit0; sq < seq_len; sq += unit_stride) {
+        const uint32_t idesc = (sq >= full_units) ? idesc_half : idesc_full;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
@@ -486,20 +515,21 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = unit0; u < num_units; u += unit_stride) {
-      const int tm = u % m_tiles, tn = u / m_tiles;
+    for (int sq = unit0; sq < seq_len; sq += unit_stride) {
+      PTK_DECODE_UNIT(sq, tm, ncol0, half)
+      const int ncols = half ? BLOCK_N / 2 : BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)tm * 2 * BLOCK_M + (long long)crank * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       float* crow = p.C + row * p.sc0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
         tmem_ld_32x32b_x32(taddr, r);
         tmem_ld_wait();
-        const long long col0 = (long long)tn * BLOCK_N + c0;
+        const long long col0 = (long long)ncol0 + c0;
         if (row_ok && col0 < p.N) {
           const bool full = (col0 + 32 <= p.N);
           if (full && p.sc1 == 1 && p.beta == 0.0f && ((((uintptr_t)(crow + col0)) & 15) == 0)) {
@@ -546,6 +576,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
+#undef PTK_DECODE_UNIT
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -657,15 +688,22 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     PTK_LAUNCH_CHECK("convert_bf16");
   }
   const int cluster = g_cluster;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbh;
   ptk_status s;
   if ((s = make_tmap(&ta, Abf, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M)) != PTK_OK) return s;
+  if ((s = make_tmap(&tbh, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, BLOCK_N / 4)) != PTK_OK) return s;
   if ((s = make_tmap(&tb, Bbf, (uint64_t)N, (uint64_t)K, (uint64_t)Kp, cluster >= 2 ? BLOCK_N / 2 : BLOCK_N)) != PTK_OK) return s;
   EpiParams p;
   p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Cbf = reinterpret_cast<__nv_bfloat16*>(C_bf16);
   p.ldcbf = ldc_bf16;
+  static int g_split = -1;
+  if (g_split < 0) {
+    const char* e = getenv("PTK_GEMM_SPLIT");
+    g_split = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.split_tail = g_split;
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -690,7 +728,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cluster == 3) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, p));
+    if (cluster == 3) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
     else PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<2>, ta, tb, p));
   } else {
     const int grid = std::max(1, std::min(m_tiles * n_tiles, sms));

@@ -52,6 +52,7 @@ class CudaVM:
     def __call__(self, output_subset=None):
         ex = self.executor
         ex.time_nodes = self.time_thunks
+        ex.host_outputs = not self.device_outputs
         try:
             out_vals = ex.run([cell[0] for cell in self.input_storage])
         except Exception:

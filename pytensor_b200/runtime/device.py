@@ -271,6 +271,20 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     return np.frombuffer(buf, dtype=dt).reshape(tuple(int(s) for s in shape))
 
 
+def host_empty(shape, dtype, always_pinned: bool = False) -> np.ndarray:
+    """Host array for a function output: page-locked (pooled) when large enough to matter, else plain NumPy.
+    `always_pinned`: also pin small arrays — a device->host copy into pageable memory blocks the calling thread until the
+    copy has run, which would stall a software pipeline that wants to keep enqueueing work."""
+    dt = np.dtype(dtype)
+    nbytes = dt.itemsize
+    for s in shape:
+        nbytes *= int(s)
+    if ((nbytes >= _PinnedPool.MIN_BYTES or (always_pinned and nbytes > 0)) and _pinned_pool.total < PINNED_POOL_LIMIT
+            and not _lib.TRACE_ONLY):
+        return pinned_empty(tuple(shape), dt)
+    return np.empty(tuple(int(s) for s in shape), dtype=dt)
+
+
 def to_host(t, sync: bool = True) -> np.ndarray:
     """Device -> host copy into a fresh numpy array (C order)."""
     if not isinstance(t, torch.Tensor):
@@ -280,11 +294,7 @@ def to_host(t, sync: bool = True) -> np.ndarray:
     if alloc_state.capturing:
         raise GraphUnsupported("device->host read inside a graph capture")
     src = contiguous(t)
-    nbytes = src.numel() * src.element_size()
-    if nbytes >= _PinnedPool.MIN_BYTES and _pinned_pool.total < PINNED_POOL_LIMIT and not _lib.TRACE_ONLY:
-        out = pinned_empty(tuple(src.shape), TORCH_TO_NP[src.dtype])
-    else:
-        out = np.empty(tuple(src.shape), dtype=TORCH_TO_NP[src.dtype])
+    out = host_empty(tuple(src.shape), TORCH_TO_NP[src.dtype])
     if out.size:
         _lib.check(_lib.lib().ptk_memcpy_d2h_async(out.ctypes.data, ptr(src), out.nbytes, stream_ptr()), "d2h")
     if sync:

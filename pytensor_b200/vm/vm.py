@@ -132,6 +132,42 @@ class Program:
         self.stream_of = stream_of
         self.n_streams = max(stream_of) + 1 if stream_of else 1
 
+    def streamable(self):
+        """True when every step is row-independent along axis 0: fused Elemwise over non-broadcast operands, and
+        reductions that keep axis 0.  Such a program can be run chunk by chunk along axis 0, which lets the executor
+        overlap the host->device copy of chunk c+1 and the device->host copy of chunk c-1 with the kernels of chunk c
+        (PCIe is full duplex; see Executor._run_chunked)."""
+        ok = getattr(self, "_streamable", None)
+        if ok is None:
+            from .nodes_elemwise import CAReduceNode, ElemwiseNode, ElemwiseReduceNode
+
+            def ew_ok(n):
+                return n.ndim >= 1 and not any(any(b) for b in n.in_bcast)
+
+            def red_ok(n):
+                return n.ndim >= 2 and 0 not in n.axes
+
+            ok = bool(self.steps) and bool(self.inputs)
+            produced = set()
+            for st in self.steps:
+                t = type(st.impl)
+                if t is ElemwiseNode:
+                    good = ew_ok(st.impl)
+                elif t is CAReduceNode:
+                    good = red_ok(st.impl)
+                elif t is ElemwiseReduceNode:
+                    good = ew_ok(st.impl.ew) and red_ok(st.impl.red)
+                else:
+                    good = False
+                if not good or any(j in self.constants for j in st.ins):
+                    ok = False
+                    break
+                produced.update(st.outs)
+            if ok:
+                ok = all(s in produced for s in self.outputs) and len(set(self.outputs)) == len(self.outputs)
+            self._streamable = ok
+        return ok
+
     def _plan_gc(self):
         last = {}
         for i, st in enumerate(self.steps):
@@ -161,6 +197,16 @@ class _GraphEntry:
         self.arena = self.gexec = self.out_vals = None
         self.static_in, self.flags, self.keep = [], [], []
 
+    def __del__(self):
+        g, self.gexec = self.gexec, None
+        if g:
+            try:
+                from ..runtime import lib as _lib
+
+                _lib.lib().ptk_graph_destroy(g)
+            except Exception:
+                pass
+
 
 class Executor:
     """Runs a Program.  `run(input_values) -> list of output Vals` (no host conversion).
@@ -174,6 +220,9 @@ class Executor:
     """
 
     MAX_GRAPHS = 8
+    STREAM_MIN_BYTES = 24 << 20   # host inputs smaller than this are not worth pipelining over PCIe
+    STREAM_CHUNKS = 16            # at most this many chunks ...
+    STREAM_CHUNK_BYTES = 8 << 20  # ... of about this many input bytes each
 
     def __getstate__(self):
         return {"program": self.program, "allow_gc": self.allow_gc, "use_graph": self.use_graph}
@@ -184,6 +233,10 @@ class Executor:
     def __init__(self, program: Program, allow_gc=True, use_graph=False):
         self.use_graph = use_graph
         self.multi_stream = True   # independent branches on side streams inside captured graphs
+        self.host_outputs = False  # set by the caller when results go back to NumPy (enables the chunked PCIe pipeline)
+        self._d2h_stream = self._h2d_stream = None
+        self.chunked_calls = 0
+        self._chunk_plan = None
         self._side_streams = []
         self.last_from_graph = False
         self._graphs = {}
@@ -227,6 +280,10 @@ class Executor:
         if (not self.use_graph or _lib.TRACE_ONLY or self.time_nodes or self.event_log is not None
                 or dev.alloc_state.capturing or dev.alloc_state.measuring):
             return self._run_eager(inputs)
+        if self.host_outputs and self._chunkable(inputs):
+            outs = self._run_chunked(inputs)
+            if outs is not None:
+                return outs
         # hot path: the very same input OBJECTS as an earlier replayed call (device tensors / large host arrays whose
         # metadata cannot change under us) -> skip building the signature
         ids = tuple(map(id, inputs))
@@ -275,6 +332,105 @@ class Executor:
             self.last_from_graph = True
             return e.out_vals
         return self._run_eager(inputs)
+
+    # ---- chunked host pipeline --------------------------------------------------------------------------------------
+    def _chunkable(self, inputs):
+        if not inputs:
+            return False
+        a0 = inputs[0]
+        if type(a0) is not np.ndarray or a0.ndim < 1 or a0.shape[0] < 2 or not self.program.streamable():
+            return False
+        rows = a0.shape[0]
+        nbytes = 0
+        for a in inputs:
+            if type(a) is not np.ndarray or a.ndim < 1 or a.shape[0] != rows or not a.flags.c_contiguous:
+                return False
+            nbytes += a.nbytes
+        return nbytes >= self.STREAM_MIN_BYTES
+
+    def _run_chunked(self, inputs):
+        """Host arrays in, host arrays out, row-independent program: split axis 0 into chunks and pipeline
+        H2D(c+1) | kernels(c) | D2H(c-1).  Uploads run back to back on their own stream (the static input buffers are
+        full size, so they never wait for a kernel), the kernels of chunk c wait on the VM stream for upload c, and
+        downloads run on a third stream behind the kernels: both PCIe directions stay busy and a call costs about
+        max(upload, download) plus one chunk of latency instead of their sum.
+
+        The per-chunk device work runs through a private Executor over STATIC device input buffers: with `use_graph` its
+        kernels are captured once per chunk and replayed with a single cudaGraphLaunch, which keeps the host cost per
+        chunk (2 copies + 1 launch + 1 event) far below the chunk's DMA time.  Returns host Vals (pinned-pool arrays),
+        or None if the first chunk shows the program does not keep axis 0 (the caller then takes the normal path)."""
+        import torch
+
+        from ..runtime import lib as _lib
+
+        L = _lib.lib()
+        main = torch.cuda.current_stream()
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream()
+            self._h2d_stream = torch.cuda.Stream()
+        side, up = self._d2h_stream, self._h2d_stream
+        sp_up, sp2 = up.cuda_stream, side.cuda_stream
+        key = tuple((a.shape, a.dtype.str) for a in inputs)
+        plan = self._chunk_plan
+        if plan is None or plan["key"] != key:
+            rows = inputs[0].shape[0]
+            in_bytes = sum(a.nbytes for a in inputs)
+            nch = max(2, min(self.STREAM_CHUNKS, rows, in_bytes // self.STREAM_CHUNK_BYTES))
+            bounds = [(rows * c // nch, rows * (c + 1) // nch) for c in range(nch)]
+            static = [dev.empty(a.shape, a.dtype.name) for a in inputs]
+            ev0 = torch.cuda.Event()  # the allocator may hand out blocks with work still queued on the VM stream
+            ev0.record(main)
+            up.wait_event(ev0)
+            sub = Executor(self.program, self.allow_gc, self.use_graph)
+            sub.MAX_GRAPHS = nch + 1
+            sub.multi_stream = False
+            plan = self._chunk_plan = {
+                "key": key, "rows": rows, "bounds": bounds, "static": static, "sub": sub,
+                "views": [[t[r0:r1] for t in static] for r0, r1 in bounds],
+                "rowbytes": [a.nbytes // rows for a in inputs],
+                "events": [torch.cuda.Event() for _ in bounds],
+                "up_events": [torch.cuda.Event() for _ in bounds],
+                "out_meta": None,
+            }
+        rows, sub = plan["rows"], plan["sub"]
+        hbase = [a.ctypes.data for a in inputs]
+        rowbytes = plan["rowbytes"]
+        host_out = obase = None
+        for c, (r0, r1) in enumerate(plan["bounds"]):
+            views = plan["views"][c]
+            for k, t in enumerate(views):
+                nb = (r1 - r0) * rowbytes[k]
+                if nb:
+                    _lib.check(L.ptk_memcpy_h2d_async(t.data_ptr(), hbase[k] + r0 * rowbytes[k], nb, sp_up), "h2d")
+            uev = plan["up_events"][c]
+            uev.record(up)
+            main.wait_event(uev)
+            outs = sub.run(views)
+            if host_out is None:
+                meta = plan["out_meta"]
+                if meta is None:
+                    if any(v is None or v.d is None or v.d.dim() < 1 or v.d.shape[0] != r1 - r0
+                           or not v.d.is_contiguous() for v in outs):
+                        self.program._streamable = False
+                        self._chunk_plan = None
+                        return None
+                    meta = plan["out_meta"] = [(tuple(v.d.shape[1:]), dev.TORCH_TO_NP[v.d.dtype]) for v in outs]
+                host_out = [dev.host_empty((rows,) + tail, dt, always_pinned=True) for tail, dt in meta]
+                obase = [(h.ctypes.data, h.nbytes // rows) for h in host_out]
+            ev = plan["events"][c]
+            ev.record(main)
+            side.wait_event(ev)
+            for v, (base, rb) in zip(outs, obase):
+                nb = (r1 - r0) * rb
+                if nb:
+                    _lib.check(L.ptk_memcpy_d2h_async(base + r0 * rb, v.d.data_ptr(), nb, sp2), "d2h")
+            if not sub.last_from_graph:
+                # eagerly allocated results: keep them until the download stream is done with them
+                plan.setdefault("keep", []).append(outs)
+        _lib.check(L.ptk_sync_stream(sp2), "sync")
+        plan.pop("keep", None)
+        self.chunked_calls += 1
+        return [Val(h=h) for h in host_out]
 
     def _capture(self, e, inputs):
         import torch

@@ -21,7 +21,13 @@ def _check(got, ref, K):
     assert err < 4e-3, f"bf16 tensor-core GEMM deviates {err:.2e} of the output scale (K={K})"
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (512, 768, 320), (1000, 520, 264), (384, 256, 1024)])
+# the last three shapes have more 256x256 units than CTA pairs (148 SMs -> 74 pairs) with a remainder that is split into
+# 256x128 half units (wave-quantisation path of gemm_bf16_tc_pair_kernel): 80 units (6 -> 12 halves), ragged 80 units,
+# and 12 x 13 = 156 units (8 -> 16 halves, two full rounds before the tail); the last two have >= 8 k-blocks, which the
+# split-K variant of the tail (PTK_GEMM_SPLIT=2) requires
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (512, 768, 320), (1000, 520, 264), (384, 256, 1024),
+                                   (2560, 2048, 256), (2500, 2000, 264), (3072, 3328, 320),
+                                   (2500, 2000, 520), (2560, 2048, 1032)])
 def test_dot22_bf16(gpu, M, N, K):
     rng = np.random.default_rng(41)
     x, y = pt.fmatrix("x"), pt.fmatrix("y")

@@ -95,3 +95,68 @@ def test_op_from_graph_and_batched_dot(gpu):
     A3, B3 = pt.dtensor3("A3"), pt.dtensor3("B3")
     compare_cuda_and_cvm([A3, B3], [pt.matmul(A3, B3)], [rng.standard_normal((4, 6, 7)), rng.standard_normal((4, 7, 3))],
                          rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("shape,dtype", [((1030, 4099), "float32"), ((3_000_001,), "float64"), ((37, 129, 515), "float32"),
+                                         ((2048, 2048), "int64")])
+def test_chunked_host_pipeline_matches_cvm(gpu, shape, dtype):
+    # large host-resident elementwise call: the executor pipelines H2D | kernel | D2H chunk by chunk along axis 0
+    # (Executor._run_chunked); results must equal the one-shot path and the C linker, including ragged last chunks
+    rng = np.random.default_rng(67)
+    T = pt.TensorType(dtype, shape=(None,) * len(shape))
+    x, y, z = T("x"), T("y"), T("z")
+    if dtype == "int64":
+        outs = [x * y - z, pt.maximum(x, y) + (z & 7)]
+        vals = [rng.integers(-1000, 1000, size=shape).astype(dtype) for _ in range(3)]
+    else:
+        outs = [pt.tanh(x * y) + pt.exp(-z * z), x - y * z]
+        vals = [rng.standard_normal(shape).astype(dtype) for _ in range(3)]
+    f = pytensor.function([x, y, z], outs, mode="CUDA")
+    f_ref = pytensor.function([x, y, z], outs, mode="CVM")
+    for _ in range(3):  # eager + arena measurement, per-chunk graph capture, per-chunk graph replay
+        got = f(*vals)
+    assert f.vm.executor.chunked_calls == 3
+    assert len(f.vm.executor._chunk_plan["bounds"]) >= 3
+    f.vm.executor.STREAM_MIN_BYTES = 1 << 60  # same function, one-shot path
+    whole = f(*vals)
+    assert f.vm.executor.chunked_calls == 3
+    for g, w, r in zip(got, whole, f_ref(*vals)):
+        assert g.shape == r.shape and g.dtype == r.dtype
+        np.testing.assert_array_equal(g, w)
+        if dtype == "int64":
+            np.testing.assert_array_equal(g, r)
+        else:
+            np.testing.assert_allclose(g, r, rtol=1e-5 if dtype == "float32" else 1e-12, atol=1e-6)
+
+
+def test_chunked_pipeline_not_taken_for_broadcast_or_small(gpu):
+    x, y = pt.fmatrix("x"), pt.fvector("y")
+    f = pytensor.function([x, y], x * y + 1, mode="CUDA")
+    xv = np.ones((4096, 4096), "float32")
+    r = f(xv, np.arange(4096, dtype="float32"))
+    assert f.vm.executor.chunked_calls == 0
+    np.testing.assert_array_equal(r[5], np.arange(4096, dtype="float32") + 1)
+    g = pytensor.function([x], pt.exp(x), mode="CUDA")
+    g(np.ones((64, 64), "float32"))
+    assert g.vm.executor.chunked_calls == 0
+
+
+def test_chunked_pipeline_with_row_reduction_cfg2(gpu):
+    # BASELINE.json configs[1] at reduced size: fused Elemwise -> row sum keeps axis 0, so host calls are pipelined too;
+    # chunking must not change a single bit (rows are reduced independently)
+    from pytensor_b200 import workloads as W
+
+    pytensor.config.floatX = "float32"
+    ins, outs, make_args, _ = W.cfg2_fused_elemwise(2048)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    args = make_args(71)
+    for _ in range(4):
+        got = f(*args)
+    assert f.vm.executor.chunked_calls == 4
+    assert f.vm.executor._chunk_plan["sub"].last_from_graph
+    f.vm.executor.STREAM_MIN_BYTES = 1 << 60
+    whole = f(*args)
+    ref = pytensor.function(ins, outs, mode="CVM")(*args)
+    for g, w, r in zip(got, whole, ref):
+        np.testing.assert_array_equal(g, w)
+        np.testing.assert_allclose(g, r, rtol=1e-5, atol=1e-6)
