@@ -221,8 +221,8 @@ class Executor:
 
     MAX_GRAPHS = 8
     STREAM_MIN_BYTES = 24 << 20   # host inputs smaller than this are not worth pipelining over PCIe
-    STREAM_CHUNKS = 16            # at most this many chunks ...
-    STREAM_CHUNK_BYTES = 8 << 20  # ... of about this many input bytes each
+    STREAM_CHUNKS = 8              # at most this many chunks ... (measured: 4-8 best; every extra chunk costs ~30 us
+    STREAM_CHUNK_BYTES = 16 << 20  # ... of about this many input bytes each     of copy-engine turnaround)
 
     def __getstate__(self):
         return {"program": self.program, "allow_gc": self.allow_gc, "use_graph": self.use_graph}
