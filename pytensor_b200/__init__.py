@@ -20,6 +20,13 @@ def register():
     return cuda
 
 
+def shared(value, **kwargs):
+    """Device-resident `pytensor.shared` (see pytensor_b200/sharedvar.py)."""
+    from pytensor_b200.sharedvar import shared as _shared
+
+    return _shared(value, **kwargs)
+
+
 try:  # registration is best-effort at import: the runtime/vm layers work without the host framework
     register()
 except ImportError:  # pragma: no cover - host not present

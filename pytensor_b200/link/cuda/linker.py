@@ -46,6 +46,11 @@ class CudaVM:
         self.position_of_error = -1
         self.time_thunks = False
         self.borrow_outputs = False
+        # device-resident shared variables (pytensor_b200.shared): fgraph input positions whose cell may hold a torch
+        # CUDA tensor, and update outputs (output index -> input index) that are written back on the device
+        self.dev_shared = []
+        self.dev_updates = {}
+        self._shared_dev = {}
         self.call_times = executor.call_times
         self.call_counts = executor.call_counts
 
@@ -53,11 +58,15 @@ class CudaVM:
         ex = self.executor
         ex.time_nodes = self.time_thunks
         ex.host_outputs = not self.device_outputs
+        if self.dev_shared:
+            self._promote_shared()
         try:
             out_vals = ex.run([cell[0] for cell in self.input_storage])
         except Exception:
             self.position_of_error = ex.position_of_error
             raise
+        if self.dev_updates:
+            return self._finish_with_device_updates(out_vals, output_subset)
         if ex.last_from_graph and self.device_outputs and self.borrow_outputs and output_subset is None:
             # replayed graph, borrowed device outputs: hand out the arena views directly (no copies, no sync)
             outs = [v.d if v.d is not None else v.h for v in out_vals]
@@ -70,6 +79,80 @@ class CudaVM:
         if output_subset is not None:
             return [o if i in output_subset else None for i, o in enumerate(outs)]
         return outs
+
+    # ---- device-resident shared variables -------------------------------------------------------
+    def _promote_shared(self):
+        """A CudaSharedVariable whose cell still holds a NumPy array (fresh, or after set_value(ndarray)) is uploaded
+        once and the device tensor is left in the cell.  The previous device buffer is reused when the layout allows, so
+        captured CUDA graphs (keyed on input addresses) keep replaying after a `set_value`."""
+        from pytensor_b200.runtime import device as dev
+
+        for k in self.dev_shared:
+            cell = self.input_storage[k]
+            v = cell[0]
+            if v is None or hasattr(v, "is_cuda"):
+                continue
+            a = np.asarray(v)
+            last = self._shared_dev.get(k)
+            if (last is not None and tuple(last.shape) == a.shape and dev.TORCH_TO_NP[last.dtype] == a.dtype.name
+                    and last.is_contiguous()):
+                dev.to_device_async(a, out=last)
+                dev.synchronize()  # the host array is dropped from the cell below: the copy must have completed
+                t = last
+            else:
+                t = dev.to_device(a)
+            cell[0] = t
+            self._shared_dev[k] = t
+
+    def _finish_with_device_updates(self, out_vals, output_subset):
+        """Outputs that are `updates=` of device-resident shared variables stay in HBM: the new value is copied
+        device-to-device INTO the variable's current buffer (stable address -> the CUDA graph keeps replaying) and that
+        same tensor object is handed back, which `Function.__call__` stores into the container
+        (pytensor/compile/executor.py:712-716).  Everything else takes the usual host/device output path."""
+        from pytensor_b200.runtime import device as dev
+
+        ex = self.executor
+        res = [None] * len(out_vals)
+        for j, k in self.dev_updates.items():
+            v = out_vals[j]
+            cur = self.input_storage[k][0]
+            cur_ok = hasattr(cur, "is_cuda")
+            if v.d is None:  # small value computed on the host (shape arithmetic, scalars)
+                h = np.ascontiguousarray(np.asarray(v.h))
+                if cur_ok and tuple(cur.shape) == h.shape and dev.TORCH_TO_NP[cur.dtype] == h.dtype.name \
+                        and cur.is_contiguous():
+                    dev.to_device_async(h, out=cur)
+                    dev.synchronize()
+                    res[j] = cur
+                else:
+                    res[j] = dev.to_device(h)
+                continue
+            src = v.d
+            same_layout = cur_ok and tuple(cur.shape) == tuple(src.shape) and cur.dtype == src.dtype
+            if same_layout and cur.data_ptr() == src.data_ptr() and cur.stride() == src.stride():
+                res[j] = cur  # computed in place on the variable's buffer (destroy_map on a mutable input)
+            elif same_layout and cur.untyped_storage().data_ptr() != src.untyped_storage().data_ptr():
+                dev.copy_strided(cur, src)
+                res[j] = cur
+            else:  # new shape, or a view overlapping the old value: give the variable a new buffer
+                res[j] = dev.clone(src)
+            self._shared_dev[k] = res[j]
+        rest = [j for j in range(len(out_vals)) if j not in self.dev_updates]
+        if rest:
+            outs = outputs_to_host([out_vals[j] for j in rest], self.device_outputs,
+                                   copy_device=ex.last_from_graph and not self.borrow_outputs)
+            for j, o in zip(rest, outs):
+                res[j] = o
+        else:
+            from pytensor_b200.vm import nodes_basic
+
+            if len(nodes_basic._pending_flags) > 256:  # nothing forces a sync here: flags are checked lazily
+                del nodes_basic._pending_flags[:-64]
+        for cell, o in zip(self.output_storage, res):
+            cell[0] = o
+        if output_subset is not None:
+            return [o if (i in output_subset or i in self.dev_updates) else None for i, o in enumerate(res)]
+        return res
 
     def clear_storage(self):
         for i in range(len(self.executor.vals)):
@@ -143,6 +226,11 @@ class CUDALinker(LocalLinker):
         vm = CudaVM(fgraph, order, executor, input_storage, output_storage, storage_map, bool(self.allow_gc),
                     self.device_outputs, thunks)
         vm.borrow_outputs = self.borrow_outputs
+        from pytensor_b200.sharedvar import CudaSharedVariable
+
+        vm.dev_shared = [k for k, v in enumerate(fgraph.inputs) if isinstance(v, CudaSharedVariable)]
+        mapping = getattr(fgraph, "update_mapping", None) or {}
+        vm.dev_updates = {int(o): int(i) for o, i in mapping.items() if i in vm.dev_shared}
         return (
             vm,
             [Container(i, s) for i, s in zip(fgraph.inputs, input_storage, strict=True)],

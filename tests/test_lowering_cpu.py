@@ -156,3 +156,23 @@ template <typename T> static inline T ptk_fmod_py(T x, T y) { T r = std::fmod(x,
     for k, o in enumerate(node_outs):
         j = f.maker.fgraph.outputs.index(o)
         np.testing.assert_allclose(outs_np[k], ref[j], rtol=2e-6, atol=2e-6)
+
+
+def test_device_resident_shared_variables_are_recognised_by_the_linker():
+    # pytensor_b200.shared: the VM must find the shared input and its update output (trace-only: no device needed)
+    import pytensor_b200
+    from pytensor_b200.sharedvar import CudaSharedVariable
+
+    pytensor.config.floatX = "float32"
+    Wd = pytensor_b200.shared(np.ones((8, 4), "float32"), name="W")
+    b = pytensor.shared(np.zeros(4, "float32"), name="b")
+    x = pt.fmatrix("x")
+    loss = (pt.tanh(pt.dot(x, Wd) + b) ** 2).sum()
+    f = pytensor.function([x], loss, updates={Wd: Wd - np.float32(0.1) * pytensor.grad(loss, Wd)}, mode="CUDA")
+    k = [i for i, v in enumerate(f.maker.fgraph.inputs) if isinstance(v, CudaSharedVariable)]
+    assert f.vm.dev_shared == k and len(k) == 1
+    assert f.vm.dev_updates == {1: k[0]}
+    assert isinstance(Wd.type, pt.TensorType) and type(Wd.type) is pt.TensorType  # rewrites see a dense tensor
+    assert "GemmNode" in _steps(f)  # ... so the BLAS rewrites still fire on it
+    assert not Wd.on_device
+    assert trace_function(f, [np.ones((5, 8), "float32")]) >= 2
