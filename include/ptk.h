@@ -104,6 +104,20 @@ size_t       ptk_put_rows_workspace_bytes(int64_t n_dst, int64_t n_idx);
 ptk_status   ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
                           int dtype, void* workspace, size_t workspace_bytes, int* err_flag, void* stream);
 
+/* ---- more glue of the Op library ------------------------------------------------------------
+ * ARange (tensor/basic.py:3139; perform = np.arange): out[i] = first + i*delta evaluated in the output type like NumPy's
+ * <type>_fill loops (first/delta = the first element and the difference of the first two, computed by the caller);
+ * the float variants take first_f/delta_f, the integer variants first_i/delta_i. */
+ptk_status   ptk_arange(int dtype, void* out, int64_t n, double first_f, double delta_f, int64_t first_i, int64_t delta_i,
+                        void* stream);
+/* Argmax (tensor/math.py:188-206): x viewed as contiguous (outer, n, inner) -> out (outer, inner) int64 = index of the
+ * FIRST maximal element along the middle axis; NaN counts as maximal (np.argmax). Bit-exact. */
+ptk_status   ptk_argmax(int dtype, const void* x, int64_t* out, int64_t outer, int64_t n, int64_t inner, void* stream);
+/* CumOp (tensor/extra_ops.py:295-321; np.cumsum / np.cumprod along one axis): x, out contiguous (outer, n, inner);
+ * op 0 = add, 1 = mul; float32/float64/int64/uint64 (the dtypes np.cumsum does not widen).  inner > 1: sequential per
+ * line (bit-exact); inner == 1: warp scan (integers exact, floats within rounding). */
+ptk_status   ptk_cumop(int dtype, int op, const void* x, void* out, int64_t outer, int64_t n, int64_t inner, void* stream);
+
 /* ---- BLAS family (A5/A6: Gemm tensor/blas/gemm.py:76, Dot22 :248, Dot22Scalar :298, Gemv tensor/blas/gemv.py:16,
  *      Ger tensor/blas/ger.py:8; the C linker calls sgemm_/dgemm_/sgemv_/dgemv_ at blas/c_code/codegen.py:463-805) */
 /* C[M,N] = alpha * A[M,K] @ B[K,N] + beta * C, arbitrary element strides, dtype PTK_F32 | PTK_F64.

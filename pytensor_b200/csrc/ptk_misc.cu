@@ -1,0 +1,251 @@
+// Glue kernels of the "more of the Op library" row: ARange, Argmax, CumOp.
+// All HBM-bound integer/byte style work: coalesced access along the contiguous axis, one pass over the input.
+#include <algorithm>
+#include <limits>
+#include <type_traits>
+
+#include "ptk_common.h"
+
+namespace {
+
+using ptk::fail;
+
+inline unsigned grid_for(int64_t work_items, int per_block) {
+  int64_t want = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)std::max(1, ptk::sm_count()) * 16;
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, cap));
+}
+
+// ---- ARange: out[i] = first + i * delta, evaluated in the output type like NumPy's <type>_fill ------------------------
+template <typename T>
+__global__ void arange_float_kernel(T* __restrict__ out, int64_t n, T first, T delta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if constexpr (sizeof(T) == 4) {
+      out[i] = __fadd_rn(first, __fmul_rn((float)i, delta));  // no FMA contraction: two roundings, as the C loop does
+    } else {
+      out[i] = __dadd_rn(first, __dmul_rn((double)i, delta));
+    }
+  }
+}
+template <typename T>
+__global__ void arange_int_kernel(T* __restrict__ out, int64_t n, int64_t first, int64_t delta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (T)((uint64_t)first + (uint64_t)i * (uint64_t)delta);  // wraps like the fixed-width C arithmetic
+}
+
+// ---- Argmax --------------------------------------------------------------------------------------------------------
+// np.argmax semantics: index of the FIRST maximal element; a NaN counts as maximal (the first NaN wins).
+template <typename T>
+__device__ __forceinline__ bool is_nan_v(T v) {
+  if constexpr (std::is_floating_point<T>::value) return v != v;
+  return false;
+}
+template <typename T>
+__device__ __forceinline__ bool better(T v, int64_t i, T bv, int64_t bi) {
+  const bool n1 = is_nan_v(v), n2 = is_nan_v(bv);
+  if (n1 || n2) return n1 && (!n2 || i < bi);
+  return v > bv || (v == bv && i < bi);
+}
+
+// inner == 1: one warp (small rows) or one CTA (long rows / few rows) per row; lanes stride over the row (coalesced)
+template <typename T, int THREADS>
+__global__ void argmax_rows_kernel(const T* __restrict__ x, int64_t* __restrict__ out, int64_t rows, int64_t n) {
+  constexpr int WARPS = THREADS / 32;
+  __shared__ T s_v[WARPS];
+  __shared__ int64_t s_i[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const T* row = x + r * n;
+    T bv = row[0];
+    int64_t bi = 0;
+    for (int64_t j = threadIdx.x; j < n; j += THREADS) {
+      const T v = row[j];
+      if (better(v, j, bv, bi)) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const T ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const int64_t oi = __shfl_down_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (WARPS > 1) {
+      if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+      __syncthreads();
+      if (warp == 0) {
+        bv = s_v[lane < WARPS ? lane : 0];
+        bi = s_i[lane < WARPS ? lane : 0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const T ov = __shfl_down_sync(0xffffffffu, bv, off);
+          const int64_t oi = __shfl_down_sync(0xffffffffu, bi, off);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+      }
+    }
+    if (threadIdx.x == 0) out[r] = bi;
+    if (WARPS > 1) __syncthreads();
+  }
+}
+
+// inner > 1: one thread per output (o, i); consecutive threads read consecutive addresses at every step j
+template <typename T>
+__global__ void argmax_cols_kernel(const T* __restrict__ x, int64_t* __restrict__ out, int64_t outer, int64_t n,
+                                   int64_t inner) {
+  const int64_t total = outer * inner;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = t / inner, i = t - o * inner;
+    const T* p = x + o * n * inner + i;
+    T bv = p[0];
+    int64_t bi = 0;
+    for (int64_t j = 1; j < n; ++j) {
+      const T v = p[j * inner];
+      if (better(v, j, bv, bi)) { bv = v; bi = j; }
+    }
+    out[t] = bi;
+  }
+}
+
+template <typename T>
+ptk_status argmax_t(const void* x, int64_t* out, int64_t outer, int64_t n, int64_t inner, cudaStream_t st) {
+  if (inner == 1) {
+    if (n >= 2048 || outer < 64) {
+      const unsigned g = (unsigned)std::min<int64_t>(outer, (int64_t)std::max(1, ptk::sm_count()) * 8);
+      argmax_rows_kernel<T, 256><<<g, 256, 0, st>>>((const T*)x, out, outer, n);
+    } else {
+      const unsigned g = (unsigned)std::min<int64_t>(outer, (int64_t)std::max(1, ptk::sm_count()) * 64);
+      argmax_rows_kernel<T, 32><<<g, 32, 0, st>>>((const T*)x, out, outer, n);
+    }
+  } else {
+    argmax_cols_kernel<T><<<grid_for(outer * inner, 256), 256, 0, st>>>((const T*)x, out, outer, n, inner);
+  }
+  PTK_LAUNCH_CHECK("argmax");
+  return PTK_OK;
+}
+
+// ---- CumOp ---------------------------------------------------------------------------------------------------------
+template <typename T, int OP>
+__device__ __forceinline__ T cum_combine(T a, T b) {
+  return OP == 0 ? (T)(a + b) : (T)(a * b);
+}
+
+// inner > 1: one thread per line, strictly sequential along the axis (same order as np.add.accumulate -> bit-exact)
+template <typename T, int OP>
+__global__ void cum_cols_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t outer, int64_t n, int64_t inner) {
+  const int64_t total = outer * inner;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = t / inner, i = t - o * inner;
+    const T* p = x + o * n * inner + i;
+    T* q = out + o * n * inner + i;
+    T acc = p[0];
+    q[0] = acc;
+    for (int64_t j = 1; j < n; ++j) {
+      acc = cum_combine<T, OP>(acc, p[j * inner]);
+      q[j * inner] = acc;
+    }
+  }
+}
+
+// inner == 1: one warp per row; 32-element chunks scanned with shuffles, the running total carried between chunks
+// (tree order inside a chunk: equal to the sequential result for integers, within rounding for floats)
+template <typename T, int OP>
+__global__ void cum_rows_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t rows, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const T ident = OP == 0 ? (T)0 : (T)1;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* row = x + r * n;
+    T* orow = out + r * n;
+    T carry = ident;
+    bool first = true;
+    for (int64_t base = 0; base < n; base += 32) {
+      const int64_t j = base + lane;
+      T v = j < n ? row[j] : ident;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const T u = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v = cum_combine<T, OP>(u, v);
+      }
+      if (!first) v = cum_combine<T, OP>(carry, v);
+      if (j < n) orow[j] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      first = false;
+    }
+  }
+}
+
+template <typename T>
+ptk_status cumop_t(int op, const void* x, void* out, int64_t outer, int64_t n, int64_t inner, cudaStream_t st) {
+  if (inner == 1) {
+    const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((outer + 7) / 8, (int64_t)std::max(1, ptk::sm_count()) * 16));
+    if (op == 0) cum_rows_kernel<T, 0><<<g, 256, 0, st>>>((const T*)x, (T*)out, outer, n);
+    else cum_rows_kernel<T, 1><<<g, 256, 0, st>>>((const T*)x, (T*)out, outer, n);
+  } else {
+    const unsigned g = grid_for(outer * inner, 256);
+    if (op == 0) cum_cols_kernel<T, 0><<<g, 256, 0, st>>>((const T*)x, (T*)out, outer, n, inner);
+    else cum_cols_kernel<T, 1><<<g, 256, 0, st>>>((const T*)x, (T*)out, outer, n, inner);
+  }
+  PTK_LAUNCH_CHECK("cumop");
+  return PTK_OK;
+}
+
+}  // namespace
+
+extern "C" ptk_status ptk_arange(int dtype, void* out, int64_t n, double first_f, double delta_f, int64_t first_i,
+                                 int64_t delta_i, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (n <= 0) return PTK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(n, 256 * 4);
+  switch (dtype) {
+    case PTK_F32: arange_float_kernel<float><<<g, 256, 0, st>>>((float*)out, n, (float)first_f, (float)delta_f); break;
+    case PTK_F64: arange_float_kernel<double><<<g, 256, 0, st>>>((double*)out, n, first_f, delta_f); break;
+    case PTK_I8: arange_int_kernel<int8_t><<<g, 256, 0, st>>>((int8_t*)out, n, first_i, delta_i); break;
+    case PTK_U8: arange_int_kernel<uint8_t><<<g, 256, 0, st>>>((uint8_t*)out, n, first_i, delta_i); break;
+    case PTK_I16: arange_int_kernel<int16_t><<<g, 256, 0, st>>>((int16_t*)out, n, first_i, delta_i); break;
+    case PTK_U16: arange_int_kernel<uint16_t><<<g, 256, 0, st>>>((uint16_t*)out, n, first_i, delta_i); break;
+    case PTK_I32: arange_int_kernel<int32_t><<<g, 256, 0, st>>>((int32_t*)out, n, first_i, delta_i); break;
+    case PTK_U32: arange_int_kernel<uint32_t><<<g, 256, 0, st>>>((uint32_t*)out, n, first_i, delta_i); break;
+    case PTK_I64: arange_int_kernel<int64_t><<<g, 256, 0, st>>>((int64_t*)out, n, first_i, delta_i); break;
+    case PTK_U64: arange_int_kernel<uint64_t><<<g, 256, 0, st>>>((uint64_t*)out, n, first_i, delta_i); break;
+    default: return fail(PTK_ERR_ARG, "ptk_arange: unsupported dtype");
+  }
+  PTK_LAUNCH_CHECK("arange");
+  return PTK_OK;
+}
+
+extern "C" ptk_status ptk_argmax(int dtype, const void* x, int64_t* out, int64_t outer, int64_t n, int64_t inner,
+                                 void* stream) {
+  PTK_REQUIRE_INIT();
+  if (outer * inner == 0) return PTK_OK;
+  if (n <= 0) return fail(PTK_ERR_ARG, "ptk_argmax: attempt to get argmax of an empty sequence");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case PTK_BOOL: case PTK_U8: return argmax_t<uint8_t>(x, out, outer, n, inner, st);
+    case PTK_I8: return argmax_t<int8_t>(x, out, outer, n, inner, st);
+    case PTK_I16: return argmax_t<int16_t>(x, out, outer, n, inner, st);
+    case PTK_U16: return argmax_t<uint16_t>(x, out, outer, n, inner, st);
+    case PTK_I32: return argmax_t<int32_t>(x, out, outer, n, inner, st);
+    case PTK_U32: return argmax_t<uint32_t>(x, out, outer, n, inner, st);
+    case PTK_I64: return argmax_t<int64_t>(x, out, outer, n, inner, st);
+    case PTK_U64: return argmax_t<uint64_t>(x, out, outer, n, inner, st);
+    case PTK_F32: return argmax_t<float>(x, out, outer, n, inner, st);
+    case PTK_F64: return argmax_t<double>(x, out, outer, n, inner, st);
+  }
+  return fail(PTK_ERR_ARG, "ptk_argmax: unsupported dtype");
+}
+
+extern "C" ptk_status ptk_cumop(int dtype, int op, const void* x, void* out, int64_t outer, int64_t n, int64_t inner,
+                                void* stream) {
+  PTK_REQUIRE_INIT();
+  if (outer * n * inner == 0) return PTK_OK;
+  if (op != 0 && op != 1) return fail(PTK_ERR_ARG, "ptk_cumop: op must be 0 (add) or 1 (mul)");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case PTK_F32: return cumop_t<float>(op, x, out, outer, n, inner, st);
+    case PTK_F64: return cumop_t<double>(op, x, out, outer, n, inner, st);
+    case PTK_I64: return cumop_t<int64_t>(op, x, out, outer, n, inner, st);
+    case PTK_U64: return cumop_t<uint64_t>(op, x, out, outer, n, inner, st);
+  }
+  return fail(PTK_ERR_ARG, "ptk_cumop: dtype must be float32/float64/int64/uint64 (np.cumsum keeps only those)");
+}

@@ -242,6 +242,29 @@ def lower_node(node, opts):
         return nlin.SolveTriangularNode(node.outputs[0].type.dtype, bool(core.lower), bool(core.unit_diagonal),
                                         int(core.b_ndim), name=str(op))
 
+    # more of the Op library
+    if cname in ("ARange", "Eye", "ExtractDiag", "Split", "Argmax", "CumOp") and not isinstance(op, Blockwise):
+        from pytensor_b200.vm import nodes_extra as nx
+
+        if cname == "ARange":
+            return nx.ARangeNode(op.dtype)
+        if cname == "Eye":
+            return nx.EyeNode(op.dtype)
+        if cname == "ExtractDiag":
+            return nx.ExtractDiagNode(op.offset, op.axis1, op.axis2, op.view, name=str(op))
+        if cname == "Split":
+            return nx.SplitNode(op.len_splits, op.axis, name=str(op))
+        x = node.inputs[0]
+        if cname == "Argmax":
+            if x.type.dtype not in ("bool", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64",
+                                    "float32", "float64"):
+                raise UnsupportedOp(f"Argmax of dtype {x.type.dtype}")
+            return nx.ArgmaxNode(op.axis, x.type.ndim, x.type.dtype, name=str(op))
+        if x.type.dtype not in nx.CumOpNode.SUPPORTED:
+            raise UnsupportedOp(f"{op}: np.cumsum/cumprod widen dtype {x.type.dtype}; only "
+                                f"{nx.CumOpNode.SUPPORTED} keep the declared output type")
+        return nx.CumOpNode(op.axis, op.mode, x.type.dtype, name=str(op))
+
     if cname == "BatchedDot":
         dt = node.outputs[0].type.dtype
         if dt not in ("float32", "float64"):

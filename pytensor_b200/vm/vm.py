@@ -75,6 +75,9 @@ class Program:
             name = type(st.impl).__name__
             if name in VIEW and st.ins and st.outs:
                 union(st.ins[0], st.outs[0])
+            if getattr(st.impl, "views_input0", False) and st.ins:  # every output is a view of input 0 (Split, ...)
+                for o in st.outs:
+                    union(st.ins[0], o)
             destroy = getattr(st.impl, "destroy", None) or {}
             for o, k in destroy.items():
                 if o < len(st.outs) and k < len(st.ins):

@@ -116,7 +116,7 @@ def test_chunked_host_pipeline_matches_cvm(gpu, shape, dtype):
     for _ in range(3):  # eager + arena measurement, per-chunk graph capture, per-chunk graph replay
         got = f(*vals)
     assert f.vm.executor.chunked_calls == 3
-    assert len(f.vm.executor._chunk_plan["bounds"]) >= 3
+    assert len(f.vm.executor._chunk_plan["bounds"]) >= 2
     f.vm.executor.STREAM_MIN_BYTES = 1 << 60  # same function, one-shot path
     whole = f(*vals)
     assert f.vm.executor.chunked_calls == 3
