@@ -96,7 +96,10 @@ def test_cumsum_cumprod(gpu, shape, axis, dtype):
     else:
         xs = rng.standard_normal(shape).astype(dtype)
         xp = (1.0 + 0.01 * rng.standard_normal(shape)).astype(dtype)  # products stay O(1)
-    tol = dict(rtol=2e-5, atol=2e-4) if dtype == "float32" else dict(rtol=1e-10, atol=1e-10)
+    # last-axis scans use a warp tree + carried total instead of NumPy's strictly sequential loop: same values up to fp
+    # reassociation, i.e. an absolute error relative to the magnitude of the running sums (1e-5 of it in fp32)
+    scale = max(1.0, float(np.abs(np.cumsum(xs.astype(np.float64), axis=axis)).max()))
+    tol = dict(rtol=1e-5, atol=1e-5 * scale) if dtype == "float32" else dict(rtol=1e-10, atol=1e-12 * scale)
     compare_cuda_and_cvm([x], [pt.cumsum(x, axis=axis)], [xs], exact=(dtype == "int64"), **tol)
     compare_cuda_and_cvm([x], [pt.cumprod(x, axis=axis)], [xp], exact=(dtype == "int64"), **tol)
 
