@@ -104,6 +104,13 @@ size_t       ptk_put_rows_workspace_bytes(int64_t n_dst, int64_t n_idx);
 ptk_status   ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t outer, int64_t n_dst, int64_t n_idx,
                           int dtype, void* workspace, size_t workspace_bytes, int* err_flag, void* stream);
 
+/* Advanced indexing with k integer index arrays on k CONSECUTIVE axes (AdvancedSubtensor / AdvancedIncSubtensor,
+ * tensor/subtensor.py:1932,2275; NumPy semantics :2164): out[t] = sum_j wrap(idx[j][t], dims[j]) * prod(dims[j+1:]) — the
+ * row-major position inside the indexed block, which ptk_take / ptk_put then use as a single axis.  All k arrays are int64,
+ * contiguous and already broadcast to n elements; an out-of-range entry sets *err_flag (checked at the call's sync). */
+ptk_status   ptk_linearize_index(int k, const void* const* idx, const int64_t* dims, int64_t n, int64_t* out,
+                                 int* err_flag, void* stream);
+
 /* ---- more glue of the Op library ------------------------------------------------------------
  * ARange (tensor/basic.py:3139; perform = np.arange): out[i] = first + i*delta evaluated in the output type like NumPy's
  * <type>_fill loops (first/delta = the first element and the difference of the first two, computed by the caller);

@@ -189,7 +189,48 @@ ptk_status cumop_t(int op, const void* x, void* out, int64_t outer, int64_t n, i
   return PTK_OK;
 }
 
+// ---- linear index of several integer index arrays (advanced indexing on consecutive axes) -----------------------------
+struct LinIdxArgs {
+  const int64_t* idx[8];
+  int64_t dim[8];
+  int64_t stride[8];
+  int k;
+};
+__global__ void linearize_index_kernel(LinIdxArgs a, int64_t n, int64_t* __restrict__ out, int* __restrict__ err) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lin = 0;
+    bool bad = false;
+    for (int j = 0; j < a.k; ++j) {
+      int64_t v = a.idx[j][t];
+      if (v < 0) v += a.dim[j];            // NumPy's negative-index wrap, per axis
+      if (v < 0 || v >= a.dim[j]) { bad = true; v = 0; }
+      lin += v * a.stride[j];
+    }
+    if (bad) *err = 1;
+    out[t] = lin;
+  }
+}
+
 }  // namespace
+
+extern "C" ptk_status ptk_linearize_index(int k, const void* const* idx, const int64_t* dims, int64_t n, int64_t* out,
+                                          int* err_flag, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (k < 1 || k > 8) return fail(PTK_ERR_ARG, "ptk_linearize_index: 1..8 index arrays");
+  if (n <= 0) return PTK_OK;
+  LinIdxArgs a;
+  a.k = k;
+  int64_t stride = 1;
+  for (int j = k - 1; j >= 0; --j) {
+    a.idx[j] = (const int64_t*)idx[j];
+    a.dim[j] = dims[j];
+    a.stride[j] = stride;
+    stride *= dims[j];
+  }
+  linearize_index_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, n, out, err_flag);
+  PTK_LAUNCH_CHECK("linearize_index");
+  return PTK_OK;
+}
 
 extern "C" ptk_status ptk_arange(int dtype, void* out, int64_t n, double first_f, double delta_f, int64_t first_i,
                                  int64_t delta_i, void* stream) {

@@ -127,13 +127,14 @@ def _idx_template(idx_list):
 
 
 def _take_axis(idx_list, ndim):
+    """(first axis, k) when the index arrays sit on k consecutive axes and every other axis is taken in full
+    (NumPy then leaves the broadcast index shape in place of the block); None for any other pattern."""
     int_axes = [i for i, e in enumerate(idx_list) if isinstance(e, int)]
-    if len(int_axes) != 1:
+    if not 1 <= len(int_axes) <= 8 or int_axes != list(range(int_axes[0], int_axes[0] + len(int_axes))):
         return None
-    ax = int_axes[0]
-    if any(e != slice(None) for i, e in enumerate(idx_list) if i != ax):
+    if any(e != slice(None) for i, e in enumerate(idx_list) if i not in int_axes):
         return None
-    return ax
+    return int_axes[0], len(int_axes)
 
 
 def lower_node(node, opts):
@@ -221,17 +222,22 @@ def lower_node(node, opts):
         return nb.IncSubtensorNode(_idx_template(op.idx_list), bool(op.inplace), bool(op.set_instead_of_inc),
                                    node.outputs[0].type.dtype, name=str(op))
     if isinstance(op, AdvancedSubtensor):
-        ax = _take_axis(op.idx_list, node.inputs[0].type.ndim)
-        if ax is None or node.inputs[1].type.dtype == "bool" or len(node.inputs) != 2:
-            raise UnsupportedOp(f"{op}: only one integer index array with all other axes taken in full is supported")
-        return nb.TakeNode(ax, name=str(op))
+        blk = _take_axis(op.idx_list, node.inputs[0].type.ndim)
+        if (blk is None or len(node.inputs) != 1 + blk[1]
+                or any(i.type.dtype == "bool" or i.type.dtype.startswith("float") for i in node.inputs[1:])):
+            raise UnsupportedOp(f"{op}: integer index arrays on consecutive axes with all other axes taken in full "
+                                "are supported (no boolean masks, no partial slices mixed in)")
+        return nb.TakeNode(blk[0], name=str(op), naxes=blk[1])
     if isinstance(op, AdvancedIncSubtensor):
-        ax = _take_axis(op.idx_list, node.inputs[0].type.ndim)
-        if ax is None or len(node.inputs) != 3 or node.inputs[2].type.dtype == "bool":
-            raise UnsupportedOp(f"{op}: only one integer index array with all other axes taken in full is supported")
+        blk = _take_axis(op.idx_list, node.inputs[0].type.ndim)
+        if (blk is None or len(node.inputs) != 2 + blk[1]
+                or any(i.type.dtype == "bool" or i.type.dtype.startswith("float") for i in node.inputs[2:])):
+            raise UnsupportedOp(f"{op}: integer index arrays on consecutive axes with all other axes taken in full "
+                                "are supported (no boolean masks, no partial slices mixed in)")
         if op.ignore_duplicates and not op.set_instead_of_inc:
             raise UnsupportedOp(f"{op}: ignore_duplicates increments")
-        return nb.PutNode(ax, bool(op.inplace), bool(op.set_instead_of_inc), node.outputs[0].type.dtype, name=str(op))
+        return nb.PutNode(blk[0], bool(op.inplace), bool(op.set_instead_of_inc), node.outputs[0].type.dtype,
+                          name=str(op), naxes=blk[1])
 
     # linear algebra (possibly wrapped in Blockwise for batches)
     core = op.core_op if isinstance(op, Blockwise) else op

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ptk_put_rows_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ptk_put_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p,
                              c_void_p]),
+    "ptk_linearize_index": (c_int, [c_int, POINTER(c_void_p), _i64p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ptk_arange": (c_int, [c_int, c_void_p, c_int64, c_double, c_double, c_int64, c_int64, c_void_p]),
     "ptk_argmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "ptk_cumop": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

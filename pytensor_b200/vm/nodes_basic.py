@@ -8,6 +8,8 @@ bit-exact by construction.
 
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -298,32 +300,61 @@ class IncSubtensorNode(Node):
         return [Val(d=x)]
 
 
-# ---- advanced indexing: one integer index array on one axis, all other axes taken in full ------------------------------
-class TakeNode(Node):
-    """AdvancedSubtensor with the take-along-axis pattern (pytensor/tensor/subtensor.py:1932, `_take_axis` :1940)."""
+# ---- advanced indexing: integer index arrays on one axis or on k consecutive axes, all other axes taken in full ---------
+def _as_int64(t):
+    if dev.TORCH_TO_NP[t.dtype] != "int64":
+        from .nodes_cast import cast_to  # local import to avoid a cycle
 
-    def __init__(self, axis, name="AdvancedSubtensor"):
+        t = cast_to(t, "int64")
+    return t
+
+
+def _index_block(index_vals, dims, name):
+    """k index arrays (NumPy broadcasting among them) -> ONE int64 device array of positions inside the row-major block
+    of the k indexed axes (`ptk_linearize_index`: per-axis negative wrap + bounds check), shaped like the broadcast."""
+    its = [_as_int64(v.dev()) for v in index_vals]
+    if len(its) == 1:
+        return dev.contiguous(its[0])  # ptk_take / ptk_put wrap and bounds-check a single axis themselves
+    shape = tuple(torch.broadcast_shapes(*[tuple(t.shape) for t in its]))
+    its = [dev.contiguous(_broadcast_view(t, shape)) for t in its]
+    n = 1
+    for s in shape:
+        n *= s
+    lin = dev.empty(shape, "int64")
+    if n:
+        ptrs = (ctypes.c_void_p * len(its))(*[dev.ptr(t) for t in its])
+        flag = _err_flag()
+        _lib.check(_lib.lib().ptk_linearize_index(len(its), ptrs, dev.i64_array(dims), n, dev.ptr(lin), dev.ptr(flag),
+                                                  dev.stream_ptr()), "ptk_linearize_index")
+        _pending_flags.append((flag, f"{name}: index out of bounds"))
+    return lin
+
+
+class TakeNode(Node):
+    """AdvancedSubtensor (pytensor/tensor/subtensor.py:1932; NumPy semantics, perform :2164): `naxes` integer index arrays
+    on the consecutive axes [axis, axis + naxes), every other axis taken in full.  The indexed block is treated as one
+    axis of length prod(dims) addressed by a linearised index, so a single gather kernel serves every case."""
+
+    def __init__(self, axis, name="AdvancedSubtensor", naxes=1):
         self.axis = axis
+        self.naxes = naxes
         self.name = name
         self._flag = None
 
     def run(self, vals):
         x = dev.contiguous(vals[0].dev())
-        idx = vals[1]
-        it = idx.dev()
-        if dev.TORCH_TO_NP[it.dtype] != "int64":
-            from .nodes_cast import cast_to  # local import to avoid a cycle
-            it = cast_to(it, "int64")
-        it = dev.contiguous(it)
-        ax = self.axis
+        ax, k = self.axis, self.naxes
+        it = _index_block(vals[1:1 + k], x.shape[ax:ax + k], self.name)
         outer = 1
         for s in x.shape[:ax]:
             outer *= s
         inner = 1
-        for s in x.shape[ax + 1:]:
+        for s in x.shape[ax + k:]:
             inner *= s
-        n_src = x.shape[ax]
-        oshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
+        n_src = 1
+        for s in x.shape[ax:ax + k]:
+            n_src *= s
+        oshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + k:])
         out = dev.empty_t(oshape, x.dtype)
         if out.numel():
             if n_src == 0:
@@ -339,8 +370,9 @@ class PutNode(Node):
     """AdvancedIncSubtensor with the same single-axis pattern (pytensor/tensor/subtensor.py:2275): x[.., idx, ..] += y
     (duplicates accumulate, np.add.at semantics :2513-2531) or = y."""
 
-    def __init__(self, axis, inplace, set_instead_of_inc, dtype, name="AdvancedIncSubtensor"):
+    def __init__(self, axis, inplace, set_instead_of_inc, dtype, name="AdvancedIncSubtensor", naxes=1):
         self.axis = axis
+        self.naxes = naxes
         self.inplace = inplace
         self.set_instead_of_inc = set_instead_of_inc
         self.dtype = dtype
@@ -354,19 +386,18 @@ class PutNode(Node):
         elif not x.is_contiguous():
             raise NotImplementedError(f"{self.name}: in-place scatter into a non-contiguous buffer")
         x = x if x.is_contiguous() else dev.contiguous(x)
-        it = vals[2].dev()
-        if dev.TORCH_TO_NP[it.dtype] != "int64":
-            from .nodes_cast import cast_to
-            it = cast_to(it, "int64")
-        it = dev.contiguous(it)
-        ax = self.axis
+        ax, k = self.axis, self.naxes
+        it = _index_block(vals[2:2 + k], x.shape[ax:ax + k], self.name)
         outer = 1
         for s in x.shape[:ax]:
             outer *= s
         inner = 1
-        for s in x.shape[ax + 1:]:
+        for s in x.shape[ax + k:]:
             inner *= s
-        yshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + 1:])
+        n_dst = 1
+        for s in x.shape[ax:ax + k]:
+            n_dst *= s
+        yshape = list(x.shape[:ax]) + list(it.shape) + list(x.shape[ax + k:])
         y = vals[1].dev()
         if dev.TORCH_TO_NP[y.dtype] != self.dtype:
             from .nodes_cast import cast_to
@@ -379,20 +410,20 @@ class PutNode(Node):
             n *= s
         isz = x.element_size()
         if (n and inner == 1 and it.dim() == 1 and not self.set_instead_of_inc and self.dtype in ("float32", "float64")
-                and outer >= 64 and x.shape[ax] + 1 <= 12000 and it.numel() * isz <= 48 * 1024):
+                and outer >= 64 and n_dst + 1 <= 12000 and it.numel() * isz <= 48 * 1024):
             # many rows share one index vector: deterministic segmented reduction instead of atomics
             L = _lib.lib()
-            wsb = int(L.ptk_put_rows_workspace_bytes(x.shape[ax], it.numel()))
+            wsb = int(L.ptk_put_rows_workspace_bytes(n_dst, it.numel()))
             ws = dev.empty_t((wsb,), torch.uint8)
             flag = _err_flag()
-            _lib.check(L.ptk_put_rows(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, x.shape[ax], it.numel(),
+            _lib.check(L.ptk_put_rows(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, n_dst, it.numel(),
                                       _lib.DTYPE_CODE[self.dtype], dev.ptr(ws), wsb, dev.ptr(flag), dev.stream_ptr()),
                        "ptk_put_rows")
             _pending_flags.append((flag, f"{self.name}: index out of bounds"))
             return [Val(d=x)]
         if n:
             flag = _err_flag()
-            _lib.check(_lib.lib().ptk_put(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, x.shape[ax], it.numel(), inner,
+            _lib.check(_lib.lib().ptk_put(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, n_dst, it.numel(), inner,
                                           _lib.DTYPE_CODE[self.dtype], 0 if self.set_instead_of_inc else 1,
                                           dev.ptr(flag), dev.stream_ptr()), "ptk_put")
             _pending_flags.append((flag, f"{self.name}: index out of bounds"))

@@ -109,3 +109,30 @@ def test_cumsum_gradient_graph(gpu):
     x = pt.dmatrix("x")
     g = pytensor.grad((pt.cumsum(x, axis=1) ** 2).sum(), x)
     compare_cuda_and_cvm([x], [g], [np.random.default_rng(97).standard_normal((9, 17))])
+
+
+def test_advanced_indexing_with_several_index_arrays(gpu):
+    # NumPy advanced indexing with k index arrays on consecutive axes (tests/tensor/test_subtensor.py TestAdvancedSubtensor):
+    # broadcasting between the index arrays, negative indices, leading / trailing full axes, gather + set + inc
+    rng = np.random.default_rng(98)
+    x = pt.dtensor3("x")
+    i, j = pt.lvector("i"), pt.lmatrix("j")
+    xv = rng.standard_normal((5, 6, 7))
+    iv = np.array([0, -1, 3, 3], dtype="int64")
+    jv = rng.integers(-6, 6, size=(3, 4)).astype("int64")
+    y = pt.dmatrix("y")
+    yv = rng.standard_normal((3, 4))
+    outs = [x[i, i], x[i, j], x[:, i, j], x[:, :, i][:, j[0]], x[i, j, i]]
+    compare_cuda_and_cvm([x, i, j], outs, [xv, iv, jv], exact=True)
+    outs = [pt.set_subtensor(x[i, j], 1.5), pt.inc_subtensor(x[:, i, j], y), pt.inc_subtensor(x[i, j, i], 2.0)]
+    compare_cuda_and_cvm([x, i, j, y], outs, [xv, iv, jv, yv])
+    # duplicates accumulate (np.add.at): every pair is (0, 0)
+    z = pt.dmatrix("z")
+    compare_cuda_and_cvm([z], [pt.inc_subtensor(z[[0, 0, 0], [0, 0, 0]], 1.0)], [np.zeros((2, 2))])
+    # pt.diag(vector) = AllocDiag: zeros + arange + two-array set (tensor/basic.py:3903-3913)
+    v = pt.dvector("v")
+    compare_cuda_and_cvm([v], [pt.diag(v), pt.diag(v, k=2), pt.diag(v, k=-1) @ pt.diag(v, k=1)], [rng.standard_normal(6)])
+    f = pytensor.function([x, i, j], x[i, j], mode="CUDA")
+    if gpu:
+        with pytest.raises(IndexError):
+            f(xv, np.array([0, 5, 0, 0], dtype="int64"), jv)  # 5 is out of range for axis 0 (length 5)
