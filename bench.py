@@ -196,6 +196,18 @@ def extra_workloads(pytensor, W, cuda_mode, dev, torch, peaks):
         out["cfg4_scan_general_loop"] = {"evals_per_s": 1e3 / mse, "ms": mse}
     except Exception as e:  # noqa: BLE001
         out["cfg4_scan_persistent"] = {"error": repr(e)[:300]}
+    try:  # configs[3], full-trace variant: every step's state is an output -> 1000 x 16 MiB of HBM writes
+        ins, outs, make_args, meta = W.cfg4_scan(8192, 512, 1000, full_trace=True)
+        f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True), trust_input=True)
+        a = [dev.to_device(x) for x in make_args()]
+        ms = _time_dev(f, a, torch, 4, 3)
+        out["cfg4_scan_full_trace"] = {"evals_per_s": 1e3 / ms, "ms": ms, "trace_bytes": meta["bytes"],
+                                       "hbm_write_GBs": meta["bytes"] / (ms * 1e-3) / 1e9,
+                                       "frac_of_hbm_peak": meta["bytes"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        del f, a
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["cfg4_scan_full_trace"] = {"error": repr(e)[:300]}
     try:  # the metric graph of BASELINE.json: 265 compiled nodes (84 x Dot22+tanh(+bias), 16-step Scan, Sum)
         for n, kw, steps in ((64, {}, 50), (1024, {"gemm_precision": "bf16"}, 10)):
             ins, outs, make_args, meta = W.metric_graph(n=n)
