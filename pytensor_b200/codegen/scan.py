@@ -71,6 +71,15 @@ def gen_fused_scan_kernel(prog: ScalarProgram, name: str, n_seq: int, state_taps
             A(f"    {CTYPE[dt]} w{k}_{j} = pst{k}[off{o_st + k} + {j}LL * d.tstride[{o_st + k}]];")
     for k, dt in enumerate(seq_dt):
         A(f"    {CTYPE[dt]} sq{k} = (T > 0) ? pseq{k}[off{o_seq + k}] : ({CTYPE[dt]})0;")
+    # trace-slot bookkeeping without a 64-bit modulo per step: slot = (L + i) % store advances incrementally, and the
+    # byte offset of the slot is carried along with it (a full-trace Scan stores at EVERY step, so this is its hot path)
+    for k in range(n_state):
+        A(f"    const long long fs{k} = T - d.store[{k}];")
+        A(f"    long long sl{k} = {L[k]}LL % d.store[{k}];")
+        A(f"    long long wo{k} = sl{k} * d.tstride[{o_st + k}];")
+    for k in range(n_nit):
+        A(f"    const long long fn{k} = T - d.store[{n_state + k}];")
+        A(f"    long long sn{k} = 0, no{k} = 0;")
     A("    for (long long i = 0; i < T; ++i) {")
     for k, dt in enumerate(seq_dt):
         A(f"      const {CTYPE[dt]} cur_sq{k} = sq{k};")
@@ -90,9 +99,13 @@ def gen_fused_scan_kernel(prog: ScalarProgram, name: str, n_seq: int, state_taps
         for j in range(L[k] - 1):
             A(f"      w{k}_{j} = w{k}_{j + 1};")
         A(f"      w{k}_{L[k] - 1} = nv{k};")
-        A(f"      if (i >= T - d.store[{k}]) pst{k}[off{o_st + k} + (({L[k]}LL + i) % d.store[{k}]) * d.tstride[{o_st + k}]] = nv{k};")
+        A(f"      if (i >= fs{k}) pst{k}[off{o_st + k} + wo{k}] = nv{k};")
+        A(f"      wo{k} += d.tstride[{o_st + k}];")
+        A(f"      if (++sl{k} == d.store[{k}]) {{ sl{k} = 0; wo{k} = 0; }}")
     for k in range(n_nit):
-        A(f"      if (i >= T - d.store[{n_state + k}]) pnit{k}[off{o_nit + k} + (i % d.store[{n_state + k}]) * d.tstride[{o_nit + k}]] = nn{k};")
+        A(f"      if (i >= fn{k}) pnit{k}[off{o_nit + k} + no{k}] = nn{k};")
+        A(f"      no{k} += d.tstride[{o_nit + k}];")
+        A(f"      if (++sn{k} == d.store[{n_state + k}]) {{ sn{k} = 0; no{k} = 0; }}")
     A("    }")
     A("  }")
     A("}")
