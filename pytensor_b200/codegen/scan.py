@@ -71,41 +71,63 @@ def gen_fused_scan_kernel(prog: ScalarProgram, name: str, n_seq: int, state_taps
             A(f"    {CTYPE[dt]} w{k}_{j} = pst{k}[off{o_st + k} + {j}LL * d.tstride[{o_st + k}]];")
     for k, dt in enumerate(seq_dt):
         A(f"    {CTYPE[dt]} sq{k} = (T > 0) ? pseq{k}[off{o_seq + k}] : ({CTYPE[dt]})0;")
-    # trace-slot bookkeeping without a 64-bit modulo per step: slot = (L + i) % store advances incrementally, and the
-    # byte offset of the slot is carried along with it (a full-trace Scan stores at EVERY step, so this is its hot path)
+    # The time loop runs in two phases.  Phase 1 covers the steps whose results do not survive in any (truncated) trace
+    # buffer: body only, no stores, no slot bookkeeping — for `hs[-1]` graphs (store = 2) that is all but the last steps.
+    # Phase 2 stores: slot = (L + i) % store is computed ONCE at its start and then advanced incrementally together with
+    # the slot's offset (no 64-bit modulo / multiply per step; a full-trace Scan spends all its steps here).
+    n_out = n_state + n_nit
+    A("    const int Ti = (int)T;")
+    A("    int i0 = Ti;")
     for k in range(n_state):
-        A(f"    const long long fs{k} = T - d.store[{k}];")
-        A(f"    long long sl{k} = {L[k]}LL % d.store[{k}];")
+        A(f"    const int fs{k} = (int)max(0LL, T - d.store[{k}]); i0 = min(i0, fs{k});")
+    for k in range(n_nit):
+        A(f"    const int fn{k} = (int)max(0LL, T - d.store[{n_state + k}]); i0 = min(i0, fn{k});")
+
+    def step(stores: bool):
+        for k, dt in enumerate(seq_dt):
+            A(f"      const {CTYPE[dt]} cur_sq{k} = sq{k};")
+            A(f"      if (i + 1 < Ti) sq{k} = pseq{k}[off{o_seq + k} + (long long)(i + 1) * d.tstride[{o_seq + k}]];")
+        args = [f"cur_sq{k}" for k in range(n_seq)]
+        for k, taps in enumerate(state_taps):
+            for t in taps:
+                args.append(f"w{k}_{L[k] + t}")
+        args += [f"ns{k}" for k in range(n_nonseq)]
+        for k, dt in enumerate(state_dt):
+            A(f"      {CTYPE[dt]} nv{k};")
+        for k, dt in enumerate(nit_dt):
+            A(f"      {CTYPE[dt]} nn{k};")
+        outs = [f"nv{k}" for k in range(n_state)] + [f"nn{k}" for k in range(n_nit)]
+        A(f"      ptk_body({', '.join(args + outs)});")
+        for k in range(n_state):
+            for j in range(L[k] - 1):
+                A(f"      w{k}_{j} = w{k}_{j + 1};")
+            A(f"      w{k}_{L[k] - 1} = nv{k};")
+        if not stores:
+            return
+        for k in range(n_state):
+            cond = f"if (i >= fs{k}) " if n_out > 1 else ""
+            A(f"      {cond}pst{k}[off{o_st + k} + wo{k}] = nv{k};")
+            A(f"      wo{k} += d.tstride[{o_st + k}];")
+            A(f"      if (++sl{k} == st{k}) {{ sl{k} = 0; wo{k} = 0; }}")
+        for k in range(n_nit):
+            cond = f"if (i >= fn{k}) " if n_out > 1 else ""
+            A(f"      {cond}pnit{k}[off{o_nit + k} + no{k}] = nn{k};")
+            A(f"      no{k} += d.tstride[{o_nit + k}];")
+            A(f"      if (++sn{k} == stn{k}) {{ sn{k} = 0; no{k} = 0; }}")
+
+    A("    for (int i = 0; i < i0; ++i) {")
+    step(False)
+    A("    }")
+    for k in range(n_state):
+        A(f"    const int st{k} = (int)d.store[{k}];")
+        A(f"    int sl{k} = (int)(({L[k]}LL + i0) % d.store[{k}]);")
         A(f"    long long wo{k} = sl{k} * d.tstride[{o_st + k}];")
     for k in range(n_nit):
-        A(f"    const long long fn{k} = T - d.store[{n_state + k}];")
-        A(f"    long long sn{k} = 0, no{k} = 0;")
-    A("    for (long long i = 0; i < T; ++i) {")
-    for k, dt in enumerate(seq_dt):
-        A(f"      const {CTYPE[dt]} cur_sq{k} = sq{k};")
-        A(f"      if (i + 1 < T) sq{k} = pseq{k}[off{o_seq + k} + (i + 1) * d.tstride[{o_seq + k}]];")
-    args = [f"cur_sq{k}" for k in range(n_seq)]
-    for k, taps in enumerate(state_taps):
-        for t in taps:
-            args.append(f"w{k}_{L[k] + t}")
-    args += [f"ns{k}" for k in range(n_nonseq)]
-    for k, dt in enumerate(state_dt):
-        A(f"      {CTYPE[dt]} nv{k};")
-    for k, dt in enumerate(nit_dt):
-        A(f"      {CTYPE[dt]} nn{k};")
-    outs = [f"nv{k}" for k in range(n_state)] + [f"nn{k}" for k in range(n_nit)]
-    A(f"      ptk_body({', '.join(args + outs)});")
-    for k in range(n_state):
-        for j in range(L[k] - 1):
-            A(f"      w{k}_{j} = w{k}_{j + 1};")
-        A(f"      w{k}_{L[k] - 1} = nv{k};")
-        A(f"      if (i >= fs{k}) pst{k}[off{o_st + k} + wo{k}] = nv{k};")
-        A(f"      wo{k} += d.tstride[{o_st + k}];")
-        A(f"      if (++sl{k} == d.store[{k}]) {{ sl{k} = 0; wo{k} = 0; }}")
-    for k in range(n_nit):
-        A(f"      if (i >= fn{k}) pnit{k}[off{o_nit + k} + no{k}] = nn{k};")
-        A(f"      no{k} += d.tstride[{o_nit + k}];")
-        A(f"      if (++sn{k} == d.store[{n_state + k}]) {{ sn{k} = 0; no{k} = 0; }}")
+        A(f"    const int stn{k} = (int)d.store[{n_state + k}];")
+        A(f"    int sn{k} = stn{k} > 0 ? (int)(i0 % d.store[{n_state + k}]) : 0;")
+        A(f"    long long no{k} = sn{k} * d.tstride[{o_nit + k}];")
+    A("    for (int i = i0; i < Ti; ++i) {")
+    step(True)
     A("    }")
     A("  }")
     A("}")

@@ -97,7 +97,7 @@ class ScanFusedElemwiseNode(Node):
             outs[n_state + k] = dev.empty((nit_lens[k], *S), g.out_dtypes[n_state + k])
         if total == 0:
             return [Val(d=o) for o in outs]
-        if D > MAX_DIMS:
+        if D > MAX_DIMS or n_steps >= 2 ** 31 or max(store) >= 2 ** 31:  # the kernel counts steps / slots in int32
             return g.run(vals)
         ops = seqs + outs[:n_state] + outs[n_state:n_state + self.n_nit] + leaves
         nops = len(ops)
