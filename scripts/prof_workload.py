@@ -23,6 +23,8 @@ if which == "cfg3":
     kw = dict(gemm_precision="bf16")
 elif which == "cfg4":
     ins, outs, mk, meta = W.cfg4_scan(8192, 512, 1000)
+elif which == "cfg4full":
+    ins, outs, mk, meta = W.cfg4_scan(8192, 512, 1000, full_trace=True)
 elif which == "cfg5":
     ins, outs, mk, meta = W.cfg5_logp_grad(B=1 << 17, n=1024, J=64, K=8)
 elif which == "metric":
