@@ -1,0 +1,71 @@
+
+// ---- ptk scalar helpers ----
+__device__ __forceinline__ float ptk_max_nan_f32(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float ptk_min_nan_f32(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+// Python floor-division / modulo semantics of IntDiv / Mod
+template <typename T> __device__ __forceinline__ T ptk_floordiv(T x, T y) {
+  if (y == 0) return 0;
+  T q = x / y;
+  if ((x % y != 0) && ((x < 0) != (y < 0))) --q;
+  return q;
+}
+template <typename T> __device__ __forceinline__ T ptk_imod_py(T x, T y) {
+  if (y == 0) return 0;
+  T r = x % y;
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+template <typename T> __device__ __forceinline__ T ptk_fmod_py(T x, T y) {
+  if (y == 0) return x - x + (T)__int_as_float(0x7fc00000);
+  T r = fmod(x, y);
+  if (r != 0 && ((r < 0) != (y < 0))) r += y;
+  return r;
+}
+
+__device__ __forceinline__ void ptk_body(const double i0, const double i1, double& o0) {
+  const double t0 = (double)(((i0) * (i1)));
+  o0 = (double)(t0);
+}
+struct ScDims { int ndim; long long shape[8]; long long st[2][8]; long long tstride[2]; long long store[1]; };
+extern "C" __global__ void __launch_bounds__(256) ptk_scan_fused_1fbf292471449a1c(double* pst0, const double* __restrict__ pns0, const ScDims d, long long total, long long T) {
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
+    long long rem = e;
+    long long off0 = 0;
+    long long off1 = 0;
+#pragma unroll
+    for (int k = 8 - 1; k >= 0; --k) {
+      if (k < d.ndim) {
+        const long long q = rem / d.shape[k]; const long long c = rem - q * d.shape[k]; rem = q;
+        off0 += c * d.st[0][k];
+        off1 += c * d.st[1][k];
+      }
+    }
+    const double ns0 = pns0[off1];
+    double w0_0 = pst0[off0 + 0LL * d.tstride[0]];
+    const int Ti = (int)T;
+    int i0 = Ti;
+    const int fs0 = (int)max(0LL, T - d.store[0]); i0 = min(i0, fs0);
+    for (int i = 0; i < i0; ++i) {
+      double nv0;
+      ptk_body(w0_0, ns0, nv0);
+      w0_0 = nv0;
+    }
+    const int st0 = (int)d.store[0];
+    int sl0 = (int)((1LL + i0) % d.store[0]);
+    double* wp = pst0 + off0 + sl0 * d.tstride[0];
+    for (int i = i0; i < Ti;) {
+      const int run = min(Ti - i, st0 - sl0);
+      const int i_end = i + run;
+      for (; i < i_end; ++i) {
+      double nv0;
+      ptk_body(w0_0, ns0, nv0);
+      w0_0 = nv0;
+        *wp = nv0;
+        wp += d.tstride[0];
+      }
+      sl0 += run;
+      if (sl0 == st0) { sl0 = 0; wp = pst0 + off0; }
+    }
+  }
+}

@@ -118,17 +118,35 @@ def gen_fused_scan_kernel(prog: ScalarProgram, name: str, n_seq: int, state_taps
     A("    for (int i = 0; i < i0; ++i) {")
     step(False)
     A("    }")
-    for k in range(n_state):
-        A(f"    const int st{k} = (int)d.store[{k}];")
-        A(f"    int sl{k} = (int)(({L[k]}LL + i0) % d.store[{k}]);")
-        A(f"    long long wo{k} = sl{k} * d.tstride[{o_st + k}];")
-    for k in range(n_nit):
-        A(f"    const int stn{k} = (int)d.store[{n_state + k}];")
-        A(f"    int sn{k} = stn{k} > 0 ? (int)(i0 % d.store[{n_state + k}]) : 0;")
-        A(f"    long long no{k} = sn{k} * d.tstride[{o_nit + k}];")
-    A("    for (int i = i0; i < Ti; ++i) {")
-    step(True)
-    A("    }")
+    if n_out == 1 and n_state == 1:
+        # single recurrent output (the common case, incl. BASELINE configs[3]): walk the trace buffer in RUNS that end
+        # where the circular slot index wraps — inside a run a step costs body + one store + one pointer bump
+        A("    const int st0 = (int)d.store[0];")
+        A(f"    int sl0 = (int)(({L[0]}LL + i0) % d.store[0]);")
+        A(f"    {CTYPE[state_dt[0]]}* wp = pst0 + off{o_st} + sl0 * d.tstride[{o_st}];")
+        A("    for (int i = i0; i < Ti;) {")
+        A("      const int run = min(Ti - i, st0 - sl0);")
+        A("      const int i_end = i + run;")
+        A("      for (; i < i_end; ++i) {")
+        step(False)
+        A("        *wp = nv0;")
+        A(f"        wp += d.tstride[{o_st}];")
+        A("      }")
+        A("      sl0 += run;")
+        A(f"      if (sl0 == st0) {{ sl0 = 0; wp = pst0 + off{o_st}; }}")
+        A("    }")
+    else:
+        for k in range(n_state):
+            A(f"    const int st{k} = (int)d.store[{k}];")
+            A(f"    int sl{k} = (int)(({L[k]}LL + i0) % d.store[{k}]);")
+            A(f"    long long wo{k} = sl{k} * d.tstride[{o_st + k}];")
+        for k in range(n_nit):
+            A(f"    const int stn{k} = (int)d.store[{n_state + k}];")
+            A(f"    int sn{k} = stn{k} > 0 ? (int)(i0 % d.store[{n_state + k}]) : 0;")
+            A(f"    long long no{k} = sn{k} * d.tstride[{o_nit + k}];")
+        A("    for (int i = i0; i < Ti; ++i) {")
+        step(True)
+        A("    }")
     A("  }")
     A("}")
     return "\n".join(lines)
