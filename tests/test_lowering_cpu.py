@@ -176,3 +176,31 @@ def test_device_resident_shared_variables_are_recognised_by_the_linker():
     assert "GemmNode" in _steps(f)  # ... so the BLAS rewrites still fire on it
     assert not Wd.on_device
     assert trace_function(f, [np.ones((5, 8), "float32")]) >= 2
+
+
+def test_glue_ops_lower_and_trace():
+    # §8(f).3 ops lower to their own nodes (no CPU fallback) and their launch logic runs in trace-only mode
+    x = pt.dmatrix("x")
+    i, j = pt.lvector("i"), pt.lvector("j")
+    a, b = pt.split(x, [2, 3], n_splits=2, axis=1)
+    outs = [pt.argmax(x, axis=0), pt.cumsum(x, axis=1), pt.eye(x.shape[0], x.shape[1], 1), pt.arange(x.shape[0] * 5000),
+            a.sum() + b.sum(), pt.diagonal(x, offset=1), x[i, j], pt.inc_subtensor(x[i, j], 1.0)]
+    f = pytensor.function([x, i, j], outs, mode="CUDA")
+    names = _steps(f)
+    for want in ("ArgmaxNode", "CumOpNode", "EyeNode", "ARangeNode", "SplitNode", "ExtractDiagNode", "TakeNode", "PutNode"):
+        assert want in names, (want, names)
+    take = next(st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "TakeNode")
+    assert take.naxes == 2 and take.axis == 0
+    assert trace_function(f, [np.ones((5, 5)), np.array([0, 1]), np.array([1, -1])]) >= 1  # (counts JIT kernels only)
+
+
+def test_streamable_programs_are_row_independent_only():
+    # the chunked host pipeline (Executor._run_chunked) may only split programs whose steps keep axis 0
+    pytensor.config.floatX = "float32"
+    ins, outs, _, _ = W.cfg2_fused_elemwise(64)
+    assert pytensor.function(ins, outs, mode="CUDA").vm.executor.program.streamable()
+    x, y = pt.fmatrix("x"), pt.fvector("y")
+    assert pytensor.function([x], [pt.exp(x) + 1, x.sum(axis=1)], mode="CUDA").vm.executor.program.streamable()
+    assert not pytensor.function([x], x.sum(axis=0), mode="CUDA").vm.executor.program.streamable()   # reduces axis 0
+    assert not pytensor.function([x, y], x * y, mode="CUDA").vm.executor.program.streamable()       # broadcast operand
+    assert not pytensor.function([x], pt.dot(x, x.T), mode="CUDA").vm.executor.program.streamable()  # not elementwise
