@@ -74,6 +74,7 @@ class ClockSampler:
         self.index = index
         self.samples = []
         self._stop = threading.Event()
+        self.first_done = threading.Event()  # set when the first nvidia-smi call has returned (or failed)
         self._t = None
 
     def _loop(self):
@@ -86,6 +87,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
+            self.first_done.set()
             self._stop.wait(0.2)
 
     def __enter__(self):
@@ -326,6 +328,16 @@ def main():
     n_kernels = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        # Spawning nvidia-smi forks this (large) process while holding the GIL for milliseconds: if that lands inside the
+        # ~1 ms timed region the launch loop stalls and the device idles.  So keep running the same (untimed) work until
+        # the sampler's first call has returned — that sample sees this workload's clocks — and time the K steps in the
+        # 200 ms gap before its next call.
+        t_wait = time.perf_counter() + 3.0
+        while not clocks.first_done.is_set() and time.perf_counter() < t_wait:
+            for i in range(16):
+                f_dev(*dev_args[i % 2])
+            torch.cuda.synchronize()
+        barrier()
         e0.record()
         for i in range(args.steps):
             f_dev(*dev_args[i % 2])
