@@ -482,6 +482,10 @@ class JoinNode(Node):
         nd = parts[0].dim()
         axis %= nd
         oshape = list(parts[0].shape)
+        for p in parts[1:]:
+            if p.dim() != nd or any(p.shape[d] != oshape[d] for d in range(nd) if d != axis):
+                raise ValueError("all the input array dimensions except for the concatenation axis must match exactly, "
+                                 f"but got shapes {[tuple(q.shape) for q in parts]} for axis {axis}")
         oshape[axis] = sum(p.shape[axis] for p in parts)
         out = dev.empty(oshape, self.dtype)
         pos = 0

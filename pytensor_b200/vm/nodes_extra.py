@@ -33,6 +33,7 @@ class ARangeNode(Node):
     def run(self, vals):
         start, stop, step = (np.asarray(v.host())[()] for v in vals)
         if step == 0:
+            np.arange(start, stop, step, dtype=self.dtype)  # raises exactly what the reference's np.arange raises
             raise ValueError("ARange: step must not be zero")
         if all(np.asarray(s).dtype.kind in "iub" for s in (start, stop, step)):
             n = len(range(int(start), int(stop), int(step)))

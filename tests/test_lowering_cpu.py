@@ -204,3 +204,33 @@ def test_streamable_programs_are_row_independent_only():
     assert not pytensor.function([x], x.sum(axis=0), mode="CUDA").vm.executor.program.streamable()   # reduces axis 0
     assert not pytensor.function([x, y], x * y, mode="CUDA").vm.executor.program.streamable()       # broadcast operand
     assert not pytensor.function([x], pt.dot(x, x.T), mode="CUDA").vm.executor.program.streamable()  # not elementwise
+
+
+def test_shape_errors_raise_the_reference_exception_types():
+    # the boundary mirrors the reference's error behaviour: shape problems found by the host-side launch logic raise the
+    # same exception TYPE as the C linker (trace-only mode runs exactly that logic, no device needed)
+    pytensor.config.floatX = "float64"
+    x, y = pt.dmatrix("x"), pt.dmatrix("y")
+    v = pt.dvector("v")
+    n = pt.lscalar("n")
+    iv = pt.lvector("iv")
+    cases = [
+        ([x, y], x + y, [np.ones((3, 4)), np.ones((3, 5))]),                      # Elemwise dimension mismatch
+        ([x, y], x * y, [np.ones((3, 4)), np.ones((1, 4))]),                      # runtime broadcasting is an error
+        ([x, y], pt.dot(x, y), [np.ones((3, 4)), np.ones((5, 2))]),
+        ([x, v], pt.dot(x, v), [np.ones((3, 4)), np.ones(5)]),
+        ([x, n], x.reshape((n, 5)), [np.ones((3, 4)), np.asarray(2)]),
+        ([x, y], pt.concatenate([x, y], axis=0), [np.ones((3, 4)), np.ones((2, 5))]),
+        ([v, n], v[n], [np.ones(3), np.asarray(7)]),
+        ([x, iv], pt.split(x, iv, n_splits=2, axis=1)[0], [np.ones((3, 4)), np.array([1, 1])]),
+        ([x, v], pt.set_subtensor(x[0], v), [np.ones((3, 4)), np.ones(5)]),
+        ([x], pt.linalg.cholesky(x), [np.ones((3, 4))]),
+        ([x], pt.argmax(x, axis=1), [np.ones((3, 0))]),
+    ]
+    for ins, out, vals in cases:
+        with pytest.raises(Exception) as ref:
+            pytensor.function(ins, out, mode="CVM")(*vals)
+        f = pytensor.function(ins, out, mode="CUDA")
+        with pytest.raises(Exception) as got:
+            trace_function(f, vals)
+        assert got.type is ref.type, (str(out), got.type, ref.type, str(got.value).split("\\n")[0])
