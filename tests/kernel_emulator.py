@@ -1,0 +1,84 @@
+"""Test infrastructure: run a GENERATED CUDA kernel on the host, one simulated thread after another.
+
+The elementwise and fused-Scan kernels that `pytensor_b200/codegen` emits contain no barriers, shuffles or shared memory:
+every thread is an independent loop nest over `blockIdx/threadIdx/gridDim`.  Compiled as C++ with those built-ins turned
+into plain variables, the very same source runs on the CPU, which lets the CPU suite check the kernels' index arithmetic
+(grid-stride loops, row/column decomposition, vector tails, circular trace buffers) against NumPy without a GPU.
+Vector loads/stores keep their alignment requirement: the shim asserts it, because a misaligned 16-byte access that the
+CPU would tolerate is a fault on the device.  (Kernels with warp shuffles / shared memory — the reductions — and the
+hand-written libptk kernels are covered by the -m gpu suite only.)"""
+
+import ctypes
+import re
+import subprocess
+
+from pytensor_b200.codegen.scalar import PRELUDE
+
+HOST_PRELUDE = r"""
+#include <cmath>
+#include <cstring>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+using std::min; using std::max; using std::isnan; using std::isinf;
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+struct emu_dim3 { unsigned x, y, z; };
+static emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline double __longlong_as_double(long long v) { double f; std::memcpy(&f, &v, 8); return f; }
+static inline float ptk_max_nan_f32(float a, float b) { return (b > a) ? b : ((a >= b) ? a : NAN); }
+static inline float ptk_min_nan_f32(float a, float b) { return (b < a) ? b : ((a <= b) ? a : NAN); }
+template <typename T> static inline T ptk_floordiv(T x, T y) { if (y == 0) return 0; T q = x / y; if ((x % y != 0) && ((x < 0) != (y < 0))) --q; return q; }
+template <typename T> static inline T ptk_imod_py(T x, T y) { if (y == 0) return 0; T r = x % y; if (r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
+template <typename T> static inline T ptk_fmod_py(T x, T y) { T r = std::fmod(x, y); if (r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
+"""
+
+# the vector helpers of codegen/elemwise.py, with the device's alignment rule made explicit
+ALIGN_CHECKED_VEC = r"""
+template <typename T, int N> struct alignas(sizeof(T) * N) PVec { T v[N]; };
+static inline void emu_check_align(const void* p, size_t a) {
+  if (reinterpret_cast<uintptr_t>(p) % a) { std::fprintf(stderr, "misaligned %zu-byte vector access\n", a); std::abort(); }
+}
+template <typename T, int N> static inline PVec<T, N> ptk_ldv(const T* p) {
+  emu_check_align(p, sizeof(T) * N); PVec<T, N> r; std::memcpy(&r, p, sizeof(r)); return r;
+}
+template <typename T, int N> static inline void ptk_stv(T* p, const PVec<T, N>& v) {
+  emu_check_align(p, sizeof(T) * N); std::memcpy(p, &v, sizeof(v));
+}
+"""
+
+
+class EmulatedKernel:
+    def __init__(self, source: str, name: str, tmp_path):
+        from pytensor_b200.codegen.elemwise import _VEC_HELPERS
+
+        body = source.replace(PRELUDE, "").replace(_VEC_HELPERS, ALIGN_CHECKED_VEC)
+        m = re.search(r'extern "C" __global__ void (?:__launch_bounds__\(\d+\) )?' + re.escape(name) + r"\((.*?)\) \{", body, re.S)
+        assert m, "kernel signature not found"
+        self.param_types = []
+        for p in m.group(1).split(","):
+            p = p.strip()
+            self.param_types.append(p[: re.search(r"[A-Za-z_0-9]+$", p).start()].strip())
+        unpack = ", ".join(f"*reinterpret_cast<{t.replace('const ', '', 1) if not t.endswith('*') else t}*>(a[{k}])"
+                           for k, t in enumerate(self.param_types))
+        wrapper = (f'\nextern "C" void emu_launch(unsigned grid, unsigned block, void** a) {{\n'
+                   f"  gridDim = {{grid, 1, 1}}; blockDim = {{block, 1, 1}};\n"
+                   f"  for (unsigned b = 0; b < grid; ++b) for (unsigned t = 0; t < block; ++t) {{\n"
+                   f"    blockIdx = {{b, 0, 0}}; threadIdx = {{t, 0, 0}};\n    {name}({unpack});\n  }}\n}}\n")
+        cpp, so = tmp_path / f"{name}.cpp", tmp_path / f"{name}.so"
+        cpp.write_text(HOST_PRELUDE + body + wrapper)
+        subprocess.run(["g++", "-O1", "-march=native", "-fno-math-errno", "-shared", "-fPIC", "-std=c++17", "-w", str(cpp), "-o", str(so)],
+                       check=True)
+        self.lib = ctypes.CDLL(str(so))
+
+    def launch(self, grid: int, block: int, args):
+        """`args`: ctypes objects in kernel-parameter order (pointers as c_void_p to HOST memory)."""
+        assert len(args) == len(self.param_types), (len(args), self.param_types)
+        arr = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
+        self.lib.emu_launch(ctypes.c_uint(grid), ctypes.c_uint(block), arr)

@@ -1,0 +1,183 @@
+"""CPU suite: the generated sync-free CUDA kernels (fused Elemwise vec / flat / generic, fused Scan) executed thread by
+thread on the host (tests/kernel_emulator.py) against NumPy — index arithmetic, vector tails, broadcasting strides and the
+circular trace-buffer protocol, without a GPU."""
+
+import ctypes
+from ctypes import c_int, c_longlong, c_uint, c_void_p
+
+import numpy as np
+import pytest
+
+from kernel_emulator import EmulatedKernel
+from pytensor_b200.codegen import elemwise as cg_ew
+from pytensor_b200.codegen import scan as cg_scan
+from pytensor_b200.codegen.scalar import ScalarInst, ScalarProgram
+
+
+def _prog_fma_tanh(dtype="float32"):
+    # o0 = tanh(i0 * i1 + i2), o1 = i0 - i2
+    p = ScalarProgram(in_dtypes=[dtype] * 3, out_dtypes=[dtype, dtype])
+    p.insts = [ScalarInst("Mul", [("i", 0), ("i", 1)], [dtype, dtype], dtype),
+               ScalarInst("Add", [("t", 0), ("i", 2)], [dtype, dtype], dtype),
+               ScalarInst("Tanh", [("t", 1)], [dtype], dtype),
+               ScalarInst("Sub", [("i", 0), ("i", 2)], [dtype, dtype], dtype)]
+    p.outputs = [("t", 2), ("t", 3)]
+    return p
+
+
+def _ptr(a):
+    return c_void_p(a.ctypes.data)
+
+
+def _aligned(shape, dtype, rng=None, align=64):
+    n = int(np.prod(shape))
+    raw = np.empty(n * np.dtype(dtype).itemsize + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    a = raw[off:off + n * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+    a[...] = rng.standard_normal(shape).astype(dtype) if rng is not None else 0
+    return a
+
+
+@pytest.mark.parametrize("n,grid", [(1003, 3), (7, 1), (4096, 2), (3, 1), (260 * 4 * 4 + 5, 1)])
+def test_flat_vector_kernel_with_scalar_broadcast_and_tail(tmp_path, n, grid):
+    rng = np.random.default_rng(1)
+    prog = _prog_fma_tanh()
+    src = cg_ew.gen_vec_kernel(prog, "k_flat", (1, 0, 1, 1, 1), {}, 4, flat=True)   # input 1 is a broadcast scalar
+    k = EmulatedKernel(src, "k_flat", tmp_path)
+    a, c = _aligned((n,), "float32", rng), _aligned((n,), "float32", rng)
+    b = np.array([0.7], dtype="float32")
+    o0, o1 = _aligned((n,), "float32"), _aligned((n,), "float32")
+    nchunks = n // 4
+    args = [_ptr(a), _ptr(b), _ptr(c), _ptr(o0), _ptr(o1)] + [c_longlong(0)] * 5 + \
+           [c_longlong(nchunks), c_uint(0), c_longlong(nchunks * 4), c_longlong(n)]
+    k.launch(grid, 256, args)
+    np.testing.assert_allclose(o0, np.tanh(a * b + c), rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(o1, a - c)
+
+
+@pytest.mark.parametrize("rows,cols,grid", [(5, 16, 1), (37, 64, 2), (1000, 8, 3)])
+def test_row_vector_kernel_with_row_broadcast_operand_and_pitched_rows(tmp_path, rows, cols, grid):
+    rng = np.random.default_rng(2)
+    prog = _prog_fma_tanh()
+    src = cg_ew.gen_vec_kernel(prog, "k_rows", (1, 0, 1, 1, 1), {}, 4, flat=False)  # input 1: one value per row
+    k = EmulatedKernel(src, "k_rows", tmp_path)
+    pitch = cols + 8                                                                   # input 0 lives in a wider buffer
+    abuf = _aligned((rows, pitch), "float32", rng)
+    a = abuf[:, :cols]
+    b = _aligned((rows,), "float32", rng)
+    c = _aligned((rows, cols), "float32", rng)
+    o0, o1 = _aligned((rows, cols), "float32"), _aligned((rows, cols), "float32")
+    cpr = cols // 4
+    args = [_ptr(abuf), _ptr(b), _ptr(c), _ptr(o0), _ptr(o1),
+            c_longlong(pitch), c_longlong(1), c_longlong(cols), c_longlong(cols), c_longlong(cols),
+            c_longlong(rows * cpr), c_uint(cpr), c_longlong(cols), c_longlong(cols)]
+    k.launch(grid, 256, args)
+    np.testing.assert_allclose(o0, np.tanh(a * b[:, None] + c), rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(o1, a - c)
+
+
+def test_generic_kernel_with_transposed_broadcast_and_negative_strides(tmp_path):
+    rng = np.random.default_rng(3)
+    prog = _prog_fma_tanh("float64")
+    src = cg_ew.gen_generic_kernel(prog, "k_gen", {})
+    k = EmulatedKernel(src, "k_gen", tmp_path)
+    shape = (4, 5, 6)
+    a = rng.standard_normal((6, 5, 4)).transpose(2, 1, 0)             # transposed view
+    b = rng.standard_normal((1, 5, 1))                                 # broadcast along dims 0 and 2
+    cfull = rng.standard_normal(shape)
+    c = cfull[:, ::-1, :]                                              # negative stride along dim 1
+    o0, o1 = np.empty(shape), np.empty(shape[::-1]).transpose(2, 1, 0)  # second output written through a transposed view
+    ops = [a, b, c, o0, o1]
+
+    class EwDims(ctypes.Structure):
+        _fields_ = [("ndim", c_int), ("shape", c_longlong * cg_ew.MAX_DIMS), ("st", (c_longlong * cg_ew.MAX_DIMS) * len(ops))]
+
+    d = EwDims()
+    d.ndim = 3
+    for i, s in enumerate(shape):
+        d.shape[i] = s
+    for j, t in enumerate(ops):
+        for i in range(3):
+            d.st[j][i] = 0 if t.shape[i] == 1 else t.strides[i] // t.itemsize
+    total = int(np.prod(shape))
+    k.launch(2, 256, [_ptr(t) for t in ops] + [d, c_longlong(total)])
+    np.testing.assert_allclose(o0, np.tanh(a * b + c), rtol=1e-14)
+    np.testing.assert_array_equal(o1, a - c)
+
+
+def _scan_reference(T, store, taps, h_init, seq, a, b):
+    """NumPy statement of the buffer protocol (codegen/scan.py docstring): `store` slots, the first L hold the initial
+    taps, step i writes slot (L + i) % store, a value survives iff i >= T - store."""
+    L = -min(taps)
+    buf = np.zeros((store,) + h_init.shape[1:], dtype=h_init.dtype)
+    buf[:L] = h_init
+    window = [h_init[j].copy() for j in range(L)]
+    for i in range(T):
+        args = [window[L + t] for t in taps]
+        new = np.tanh(args[-1] * a + b) + (0.5 * args[0] if len(taps) > 1 else 0) + (seq[i] if seq is not None else 0)
+        window = window[1:] + [new.astype(h_init.dtype)]
+        if i >= T - store:
+            buf[(L + i) % store] = window[-1]
+    return buf
+
+
+@pytest.mark.parametrize("T,store,taps,with_seq", [(10, 11, (-1,), False), (10, 2, (-1,), False), (7, 3, (-1,), True),
+                                                    (1, 2, (-1,), False), (0, 2, (-1,), False), (9, 4, (-2, -1), True),
+                                                    (6, 8, (-2, -1), False), (25, 5, (-1,), True)])
+def test_fused_scan_kernel_trace_buffers_taps_and_sequences(tmp_path, T, store, taps, with_seq):
+    rng = np.random.default_rng(4)
+    dt = "float32"
+    L = -min(taps)
+    S = (3, 5)
+    # scalar program: inputs [seq?] + taps (in tap order) + nonseq a, b ; output: new state
+    n_seq = 1 if with_seq else 0
+    n_in = n_seq + len(taps) + 2
+    p = ScalarProgram(in_dtypes=[dt] * n_in, out_dtypes=[dt])
+    last_tap = n_seq + len(taps) - 1
+    a_i, b_i = n_seq + len(taps), n_seq + len(taps) + 1
+    insts = [ScalarInst("Mul", [("i", last_tap), ("i", a_i)], [dt, dt], dt), ScalarInst("Add", [("t", 0), ("i", b_i)], [dt, dt], dt),
+             ScalarInst("Tanh", [("t", 1)], [dt], dt)]
+    cur = 2
+    if len(taps) > 1:
+        insts += [ScalarInst("Mul", [("i", n_seq), ("c", 0)], [dt, dt], dt), ScalarInst("Add", [("t", cur), ("t", cur + 1)], [dt, dt], dt)]
+        p.consts = [(dt, 0.5)]
+        cur += 2
+    if with_seq:
+        insts += [ScalarInst("Add", [("t", cur), ("i", 0)], [dt, dt], dt)]
+        cur += 1
+    p.insts, p.outputs = insts, [("t", cur)]
+    src = cg_scan.gen_fused_scan_kernel(p, "k_scan", n_seq, [taps], 0, 2)
+    k = EmulatedKernel(src, "k_scan", tmp_path)
+
+    h_init = rng.standard_normal((L,) + S).astype(dt)
+    seq = rng.standard_normal((max(T, 1),) + S).astype(dt) * 0.1 if with_seq else None
+    a = rng.uniform(0.5, 1.0, S[1]).astype(dt)          # broadcast over rows
+    b = (rng.standard_normal(S) * 0.1).astype(dt)
+    buf = np.zeros((store,) + S, dtype=dt)
+    buf[:L] = h_init
+    ops = ([seq] if with_seq else []) + [buf, a, b]
+    nops = len(ops)
+
+    class ScDims(ctypes.Structure):
+        _fields_ = [("ndim", c_int), ("shape", c_longlong * cg_scan.MAX_DIMS), ("st", (c_longlong * cg_scan.MAX_DIMS) * nops),
+                    ("tstride", c_longlong * nops), ("store", c_longlong * 1)]
+
+    d = ScDims()
+    d.ndim = 2
+    d.shape[0], d.shape[1] = S
+    for j, t in enumerate(ops):
+        per_elem = j >= n_seq + 1
+        if per_elem:
+            full = np.broadcast_to(t, S)
+            for kk in range(2):
+                d.st[j][kk] = full.strides[kk] // t.itemsize
+            d.tstride[j] = 0
+        else:
+            for kk in range(2):
+                d.st[j][kk] = t.strides[kk + 1] // t.itemsize
+            d.tstride[j] = t.strides[0] // t.itemsize
+    d.store[0] = store
+    total = int(np.prod(S))
+    k.launch(2, 256, [_ptr(t) for t in ops] + [d, c_longlong(total), c_longlong(T)])
+    expect = _scan_reference(T, store, taps, h_init, seq, a[None, :], b)
+    np.testing.assert_allclose(buf, expect, rtol=3e-6, atol=1e-6)
