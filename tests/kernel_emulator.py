@@ -54,8 +54,36 @@ template <typename T, int N> static inline void ptk_stv(T* p, const PVec<T, N>& 
 """
 
 
+# Threaded variant for kernels with warp shuffles, __syncthreads and __shared__ memory (the row reductions): every
+# simulated thread of a block is a real OS thread, a shuffle is "publish my value, warp barrier, read the partner's value,
+# warp barrier", __syncthreads is a block barrier, `__shared__` becomes a function-local static (blocks run one at a time).
+HOST_PRELUDE_MT = HOST_PRELUDE.replace("static emu_dim3 threadIdx, blockIdx, blockDim, gridDim;",
+                                       "static thread_local emu_dim3 threadIdx;\nstatic emu_dim3 blockIdx, blockDim, gridDim;") + r"""
+#include <pthread.h>
+#include <thread>
+#include <vector>
+#define __shared__ static
+static pthread_barrier_t emu_block_bar;
+static pthread_barrier_t emu_warp_bar[32];
+static unsigned long long emu_slot[1024];
+static inline void __syncthreads() { pthread_barrier_wait(&emu_block_bar); }
+template <typename T> static inline T emu_exchange(T v, int src_lane_in_block) {
+  const int tid = threadIdx.x, w = tid >> 5;
+  std::memcpy(&emu_slot[tid], &v, sizeof(T));
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  T r; std::memcpy(&r, &emu_slot[src_lane_in_block], sizeof(T));
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  return r;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (int)(threadIdx.x ^ m)); }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
+  const int lane = threadIdx.x & 31; return emu_exchange(v, lane + d < 32 ? (int)threadIdx.x + d : (int)threadIdx.x);
+}
+"""
+
+
 class EmulatedKernel:
-    def __init__(self, source: str, name: str, tmp_path):
+    def __init__(self, source: str, name: str, tmp_path, threaded: bool = False):
         from pytensor_b200.codegen.elemwise import _VEC_HELPERS
 
         body = source.replace(PRELUDE, "").replace(_VEC_HELPERS, ALIGN_CHECKED_VEC)
@@ -67,18 +95,31 @@ class EmulatedKernel:
             self.param_types.append(p[: re.search(r"[A-Za-z_0-9]+$", p).start()].strip())
         unpack = ", ".join(f"*reinterpret_cast<{t.replace('const ', '', 1) if not t.endswith('*') else t}*>(a[{k}])"
                            for k, t in enumerate(self.param_types))
-        wrapper = (f'\nextern "C" void emu_launch(unsigned grid, unsigned block, void** a) {{\n'
-                   f"  gridDim = {{grid, 1, 1}}; blockDim = {{block, 1, 1}};\n"
-                   f"  for (unsigned b = 0; b < grid; ++b) for (unsigned t = 0; t < block; ++t) {{\n"
-                   f"    blockIdx = {{b, 0, 0}}; threadIdx = {{t, 0, 0}};\n    {name}({unpack});\n  }}\n}}\n")
+        if not threaded:
+            wrapper = (f'\nextern "C" void emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned block, void** a) {{\n'
+                       f"  gridDim = {{gx, gy, gz}}; blockDim = {{block, 1, 1}};\n"
+                       f"  for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned b = 0; b < gx; ++b)\n"
+                       f"    for (unsigned t = 0; t < block; ++t) {{\n"
+                       f"      blockIdx = {{b, by, bz}}; threadIdx = {{t, 0, 0}};\n      {name}({unpack});\n    }}\n}}\n")
+        else:
+            wrapper = (f'\nextern "C" void emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned block, void** a) {{\n'
+                       f"  gridDim = {{gx, gy, gz}}; blockDim = {{block, 1, 1}};\n"
+                       f"  pthread_barrier_init(&emu_block_bar, nullptr, block);\n"
+                       f"  for (unsigned w = 0; w < block / 32; ++w) pthread_barrier_init(&emu_warp_bar[w], nullptr, 32);\n"
+                       f"  for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned b = 0; b < gx; ++b) {{\n"
+                       f"    blockIdx = {{b, by, bz}};\n    std::vector<std::thread> ts;\n"
+                       f"    for (unsigned t = 0; t < block; ++t) ts.emplace_back([=]() {{ threadIdx = {{t, 0, 0}}; {name}({unpack}); }});\n"
+                       f"    for (auto& th : ts) th.join();\n  }}\n}}\n")
         cpp, so = tmp_path / f"{name}.cpp", tmp_path / f"{name}.so"
-        cpp.write_text(HOST_PRELUDE + body + wrapper)
-        subprocess.run(["g++", "-O1", "-march=native", "-fno-math-errno", "-shared", "-fPIC", "-std=c++17", "-w", str(cpp), "-o", str(so)],
-                       check=True)
+        cpp.write_text((HOST_PRELUDE_MT if threaded else HOST_PRELUDE) + body + wrapper)
+        subprocess.run(["g++", "-O1", "-march=native", "-fno-math-errno", "-shared", "-fPIC", "-std=c++17", "-w", "-pthread",
+                        str(cpp), "-o", str(so)], check=True)
         self.lib = ctypes.CDLL(str(so))
 
-    def launch(self, grid: int, block: int, args):
-        """`args`: ctypes objects in kernel-parameter order (pointers as c_void_p to HOST memory)."""
+    def launch(self, grid, block: int, args):
+        """`grid`: int or (x, y, z); `args`: ctypes objects in kernel-parameter order (pointers = c_void_p to HOST memory)."""
         assert len(args) == len(self.param_types), (len(args), self.param_types)
+        g = (grid, 1, 1) if isinstance(grid, int) else tuple(grid) + (1,) * (3 - len(grid))
+        assert block % 32 == 0 or not hasattr(self.lib, "dummy")
         arr = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
-        self.lib.emu_launch(ctypes.c_uint(grid), ctypes.c_uint(block), arr)
+        self.lib.emu_launch(ctypes.c_uint(g[0]), ctypes.c_uint(g[1]), ctypes.c_uint(g[2]), ctypes.c_uint(block), arr)

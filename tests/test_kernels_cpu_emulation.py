@@ -181,3 +181,75 @@ def test_fused_scan_kernel_trace_buffers_taps_and_sequences(tmp_path, T, store, 
     k.launch(2, 256, [_ptr(t) for t in ops] + [d, c_longlong(total), c_longlong(T)])
     expect = _scan_reference(T, store, taps, h_init, seq, a[None, :], b)
     np.testing.assert_allclose(buf, expect, rtol=3e-6, atol=1e-6)
+
+
+# ---- kernels with warp shuffles / __syncthreads / __shared__ (threaded emulator: one OS thread per simulated thread) ------
+from pytensor_b200.codegen import careduce as cg_red  # noqa: E402
+
+
+@pytest.mark.parametrize("rows,cols,tpr,vw,store", [(9, 64, 32, 4, True), (3, 1024, 256, 4, True), (10, 70, 32, 1, True),
+                                                     (5, 260, 32, 4, False), (2, 2052, 256, 4, True)])
+def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store):
+    """The bench's dominant kernel shape (gen_row_kernel): map over (rows, cols), store the map result (or not), reduce each
+    row with fp64 accumulation — warp-shuffle tree, cross-warp combine through shared memory for TPR = 256, scalar tail for
+    cols % VW, rows that do not fill the last block."""
+    rng = np.random.default_rng(6)
+    dt = "float32"
+    prog = ScalarProgram(in_dtypes=[dt, dt, dt], out_dtypes=[dt])
+    prog.insts = [ScalarInst("Mul", [("i", 0), ("i", 1)], [dt, dt], dt), ScalarInst("Add", [("t", 0), ("i", 2)], [dt, dt], dt),
+                  ScalarInst("Tanh", [("t", 1)], [dt], dt)]
+    prog.outputs = [("t", 2)]
+    in_modes = (1, 0, 1)                                      # input 1: one value per row
+    src = cg_red.gen_row_kernel(prog, "k_row", in_modes, (store,), "add", "float64", "float32", 0, vw, tpr)
+    k = EmulatedKernel(src, "k_row", tmp_path, threaded=True)
+    a, c = _aligned((rows, cols), dt, rng), _aligned((rows, cols), dt, rng)
+    b = _aligned((rows,), dt, rng)
+    e = _aligned((rows, cols), dt)
+    r = _aligned((rows,), dt)
+    args = [_ptr(a), _ptr(b), _ptr(c)] + ([_ptr(e)] if store else []) + [_ptr(r), c_longlong(cols), c_longlong(1), c_longlong(cols)] \
+        + ([c_longlong(cols)] if store else []) + [c_longlong(rows), c_longlong(cols), c_int(1)]
+    rows_per_block = 256 // tpr
+    k.launch(((rows + rows_per_block - 1) // rows_per_block, 1), 256, args)
+    expect = np.tanh(a * b[:, None] + c)
+    if store:
+        np.testing.assert_allclose(e, expect, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(r, expect.astype(np.float64).sum(axis=1).astype(np.float32), rtol=3e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("red_op,np_fn,identity", [("add", np.sum, 0), ("maximum", np.max, float("-inf")), ("mul", np.prod, 1)])
+def test_column_and_generic_reduce_kernels(tmp_path, red_op, np_fn, identity):
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0.5, 1.5, size=(3, 37, 70))            # (outer, red, inner)
+    # column kernel: reduce the middle axis, threads along the contiguous inner axis, optional split of the reduced axis
+    src = cg_red.gen_col_kernel("k_col", "float64", red_op, "float64", "float64", identity)
+    k = EmulatedKernel(src, "k_col", tmp_path, threaded=True)
+    out = np.empty((3, 70))
+    k.launch((1, 3, 1), 256, [_ptr(x), _ptr(out), c_longlong(3), c_longlong(37), c_longlong(70), c_int(1)])
+    np.testing.assert_allclose(out, np_fn(x, axis=1), rtol=1e-13)
+    if red_op == "add":  # split into 4 partial sums [split][outer][inner], finished by the warp-per-output kernel
+        part = np.empty((4, 3, 70))
+        k.launch((1, 2, 4), 256, [_ptr(x), _ptr(part), c_longlong(3), c_longlong(37), c_longlong(70), c_int(4)])
+        np.testing.assert_allclose(part.sum(axis=0), x.sum(axis=1), rtol=1e-13)
+        fsrc = cg_red.gen_finish_kernel("k_fin", "add", "float64", "float64", 0)
+        fk = EmulatedKernel(fsrc, "k_fin", tmp_path, threaded=True)
+        out2 = np.empty(3 * 70)
+        fk.launch(2, 256, [_ptr(part), _ptr(out2), c_longlong(210), c_int(4), c_longlong(1), c_longlong(210)])
+        np.testing.assert_allclose(out2.reshape(3, 70), x.sum(axis=1), rtol=1e-13)
+    # generic kernel: keep dims (0, 2) of a TRANSPOSED view, reduce dim 1 and a broadcast-free extra dim
+    xt = x.transpose(2, 1, 0)                                # shape (70, 37, 3), non-contiguous
+    src = cg_red.gen_generic_kernel("k_rgen", "float64", red_op, "float64", "float64", identity)
+    gk = EmulatedKernel(src, "k_rgen", tmp_path, threaded=True)
+
+    class RdDims(ctypes.Structure):
+        _fields_ = [("nk", c_int), ("nr", c_int), ("kshape", c_longlong * cg_red.MAX_DIMS), ("kst", c_longlong * cg_red.MAX_DIMS),
+                    ("rshape", c_longlong * cg_red.MAX_DIMS), ("rst", c_longlong * cg_red.MAX_DIMS)]
+
+    d = RdDims()
+    d.nk, d.nr = 2, 1
+    es = [s // 8 for s in xt.strides]
+    d.kshape[0], d.kshape[1], d.kst[0], d.kst[1] = 70, 3, es[0], es[2]
+    d.rshape[0], d.rst[0] = 37, es[1]
+    outg = np.empty((70, 3))
+    base = x  # the kernel indexes from the base pointer of the view (offset 0 here)
+    gk.launch(1, 256, [_ptr(base), _ptr(outg), d, c_longlong(210), c_longlong(37)])
+    np.testing.assert_allclose(outg, np_fn(xt, axis=1), rtol=1e-13)
