@@ -253,3 +253,61 @@ def test_column_and_generic_reduce_kernels(tmp_path, red_op, np_fn, identity):
     base = x  # the kernel indexes from the base pointer of the view (offset 0 here)
     gk.launch(1, 256, [_ptr(base), _ptr(outg), d, c_longlong(210), c_longlong(37)])
     np.testing.assert_allclose(outg, np_fn(xt, axis=1), rtol=1e-13)
+
+
+@pytest.mark.parametrize("in_dt,red_op,acc_dt,out_dt,identity,np_fn", [
+    ("int8", "add", "int64", "int64", 0, lambda a: a.astype(np.int64).sum(axis=1)),
+    ("uint8", "maximum", "uint8", "uint8", 0, lambda a: a.max(axis=1)),
+    ("int16", "minimum", "int16", "int16", 32767, lambda a: a.min(axis=1)),
+    ("bool", "and", "bool", "bool", 1, lambda a: a.all(axis=1)),
+    ("bool", "or", "bool", "bool", 0, lambda a: a.any(axis=1)),
+    ("int32", "xor", "int32", "int32", 0, lambda a: np.bitwise_xor.reduce(a, axis=1)),
+    ("int64", "mul", "int64", "int64", 1, lambda a: a.prod(axis=1)),
+    ("float32", "maximum", "float32", "float32", float("-inf"), lambda a: a.max(axis=1)),
+    ("float64", "add", "float64", "float64", 0, lambda a: a.sum(axis=1)),
+])
+@pytest.mark.parametrize("cols,tpr,nsplit", [(100, 32, 1), (4100, 256, 1), (4096, 32, 4)])
+def test_careduce_row_kernel_dtypes_accumulators_and_splits(tmp_path, in_dt, red_op, acc_dt, out_dt, identity, np_fn, cols, tpr, nsplit):
+    """Pure CAReduce row kernel (identity map): the reference's accumulator / output dtypes (`_acc_dtype`,
+    pytensor/tensor/elemwise.py:1383-1417: small ints accumulate in int64), the shuffle specialisations for 1- and 2-byte
+    accumulators, NaN-free max/min, and the split-row variant finished by the warp-per-output kernel."""
+    rng = np.random.default_rng(8)
+    rows = 5
+    if in_dt == "bool":
+        a = _aligned((rows, cols), "uint8")
+        a[...] = rng.integers(0, 2, size=(rows, cols)) if red_op == "or" else 1
+        a[1, cols // 2] = 0 if red_op == "and" else a[1, cols // 2]
+        a[2] = 0 if red_op == "or" else a[2]
+    elif in_dt.startswith("float"):
+        a = _aligned((rows, cols), in_dt, rng)
+    else:
+        a = _aligned((rows, cols), in_dt)
+        lo, hi = (-3, 4) if red_op != "mul" else (1, 2)
+        a[...] = rng.integers(max(lo, np.iinfo(in_dt).min), hi, size=(rows, cols)).astype(in_dt)
+        if red_op == "mul":
+            a[:, ::97] = -1
+    isz = a.itemsize
+    vw = 4 if isz >= 4 else (8 if isz == 2 else 16)
+    if cols % vw:
+        vw = 1
+    prog = cg_red.identity_program(in_dt)
+    src = cg_red.gen_row_kernel(prog, "k_red", (1,), (False,), red_op, acc_dt, out_dt, identity, vw, tpr)
+    k = EmulatedKernel(src, "k_red", tmp_path, threaded=True)
+    np_out = np.dtype("uint8" if out_dt == "bool" else out_dt)
+    np_acc = np.dtype("uint8" if acc_dt == "bool" else acc_dt)
+    rows_per_block = 256 // tpr
+    gx = (rows + rows_per_block - 1) // rows_per_block
+    if nsplit == 1:
+        out = np.zeros(rows, dtype=np_out)
+        k.launch((gx, 1), 256, [_ptr(a), _ptr(out), c_longlong(cols), c_longlong(rows), c_longlong(cols), c_int(1)])
+    else:
+        part = np.zeros((rows, nsplit), dtype=np_acc)
+        k.launch((gx, nsplit), 256, [_ptr(a), _ptr(part), c_longlong(cols), c_longlong(rows), c_longlong(cols), c_int(nsplit)])
+        fk = EmulatedKernel(cg_red.gen_finish_kernel("k_fin2", red_op, acc_dt, out_dt, identity), "k_fin2", tmp_path, threaded=True)
+        out = np.zeros(rows, dtype=np_out)
+        fk.launch(1, 256, [_ptr(part), _ptr(out), c_longlong(rows), c_int(nsplit), c_longlong(nsplit), c_longlong(1)])
+    ref = np_fn(a.view(np.bool_) if in_dt == "bool" else a)
+    if np_out.kind == "f":
+        np.testing.assert_allclose(out, ref, rtol=1e-5 if in_dt == "float32" else 1e-12)
+    else:
+        np.testing.assert_array_equal(out.astype(ref.dtype) if in_dt != "bool" else out.astype(bool), ref)
