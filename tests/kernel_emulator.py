@@ -82,17 +82,66 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
 """
 
 
+def extract_static_kernel(cu_path: str, name: str) -> str:
+    """Source text of one `__global__` (template) kernel of a hand-written .cu file: from its `template <...>` line (if any)
+    to the closing brace in column 0."""
+    text = open(cu_path).read()
+    m = re.search(r"^(?:template <[^\n]*>\n)?__global__ void[^\n]*\b" + re.escape(name) + r"\(", text, re.M)
+    assert m, f"{name} not found in {cu_path}"
+    end = text.index("\n}\n", m.start()) + 3
+    return text[m.start():end]
+
+
+def _strip_launch_bounds(text: str) -> str:
+    out, pos = [], 0
+    while True:
+        i = text.find("__launch_bounds__(", pos)
+        if i < 0:
+            out.append(text[pos:])
+            return "".join(out)
+        out.append(text[pos:i])
+        depth, j = 0, i + len("__launch_bounds__")
+        while True:
+            depth += text[j] == "("
+            depth -= text[j] == ")"
+            j += 1
+            if depth == 0:
+                break
+        pos = j
+
+
+STATIC_SHIM = r"""
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline void __syncwarp() {}
+"""
+
+
 class EmulatedKernel:
-    def __init__(self, source: str, name: str, tmp_path, threaded: bool = False):
+    def __init__(self, source: str, name: str, tmp_path, threaded: bool = False, template_args: str = "",
+                 type_subst: dict | None = None, dynamic_smem: str | None = None):
+        """`template_args` / `type_subst`: instantiate a template kernel (e.g. "float, 8", {"T": "float"});
+        `dynamic_smem`: name of the kernel's `extern __shared__` array (gets a fixed 100 KiB static buffer)."""
         from pytensor_b200.codegen.elemwise import _VEC_HELPERS
 
         body = source.replace(PRELUDE, "").replace(_VEC_HELPERS, ALIGN_CHECKED_VEC)
-        m = re.search(r'extern "C" __global__ void (?:__launch_bounds__\(\d+\) )?' + re.escape(name) + r"\((.*?)\) \{", body, re.S)
+        if dynamic_smem:
+            body = re.sub(r"extern __shared__[^\n;]*\b" + re.escape(dynamic_smem) + r"\[\];",
+                          f"alignas(16) static unsigned char {dynamic_smem}[100 * 1024];", body)
+            body = STATIC_SHIM + body
+        body = _strip_launch_bounds(body)
+        m = re.search(r"__global__ void\s+" + re.escape(name) + r"\((.*?)\) \{", body, re.S)
         assert m, "kernel signature not found"
         self.param_types = []
         for p in m.group(1).split(","):
-            p = p.strip()
-            self.param_types.append(p[: re.search(r"[A-Za-z_0-9]+$", p).start()].strip())
+            p = " ".join(p.split())
+            t = p[: re.search(r"[A-Za-z_0-9]+$", p).start()].strip()
+            for a, b in (type_subst or {}).items():
+                t = re.sub(r"\b" + a + r"\b", b, t)
+            self.param_types.append(t)
+        if template_args:
+            name_call = f"{name}<{template_args}>"
+        else:
+            name_call = name
         unpack = ", ".join(f"*reinterpret_cast<{t.replace('const ', '', 1) if not t.endswith('*') else t}*>(a[{k}])"
                            for k, t in enumerate(self.param_types))
         if not threaded:
@@ -100,7 +149,7 @@ class EmulatedKernel:
                        f"  gridDim = {{gx, gy, gz}}; blockDim = {{block, 1, 1}};\n"
                        f"  for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned b = 0; b < gx; ++b)\n"
                        f"    for (unsigned t = 0; t < block; ++t) {{\n"
-                       f"      blockIdx = {{b, by, bz}}; threadIdx = {{t, 0, 0}};\n      {name}({unpack});\n    }}\n}}\n")
+                       f"      blockIdx = {{b, by, bz}}; threadIdx = {{t, 0, 0}};\n      {name_call}({unpack});\n    }}\n}}\n")
         else:
             wrapper = (f'\nextern "C" void emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned block, void** a) {{\n'
                        f"  gridDim = {{gx, gy, gz}}; blockDim = {{block, 1, 1}};\n"
@@ -108,9 +157,10 @@ class EmulatedKernel:
                        f"  for (unsigned w = 0; w < block / 32; ++w) pthread_barrier_init(&emu_warp_bar[w], nullptr, 32);\n"
                        f"  for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned b = 0; b < gx; ++b) {{\n"
                        f"    blockIdx = {{b, by, bz}};\n    std::vector<std::thread> ts;\n"
-                       f"    for (unsigned t = 0; t < block; ++t) ts.emplace_back([=]() {{ threadIdx = {{t, 0, 0}}; {name}({unpack}); }});\n"
+                       f"    for (unsigned t = 0; t < block; ++t) ts.emplace_back([=]() {{ threadIdx = {{t, 0, 0}}; {name_call}({unpack}); }});\n"
                        f"    for (auto& th : ts) th.join();\n  }}\n}}\n")
-        cpp, so = tmp_path / f"{name}.cpp", tmp_path / f"{name}.so"
+        tag = re.sub(r"[^A-Za-z0-9]+", "_", name_call)
+        cpp, so = tmp_path / f"{tag}.cpp", tmp_path / f"{tag}.so"
         cpp.write_text((HOST_PRELUDE_MT if threaded else HOST_PRELUDE) + body + wrapper)
         subprocess.run(["g++", "-O1", "-march=native", "-fno-math-errno", "-shared", "-fPIC", "-std=c++17", "-w", "-pthread",
                         str(cpp), "-o", str(so)], check=True)

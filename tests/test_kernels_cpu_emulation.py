@@ -311,3 +311,58 @@ def test_careduce_row_kernel_dtypes_accumulators_and_splits(tmp_path, in_dt, red
         np.testing.assert_allclose(out, ref, rtol=1e-5 if in_dt == "float32" else 1e-12)
     else:
         np.testing.assert_array_equal(out.astype(ref.dtype) if in_dt != "bool" else out.astype(bool), ref)
+
+
+# ---- hand-written libptk kernels, extracted from the .cu source and instantiated for the host ----------------------------
+import os  # noqa: E402
+
+from kernel_emulator import extract_static_kernel  # noqa: E402
+from ctypes import c_double, c_float  # noqa: E402
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pytensor_b200", "csrc")
+
+
+def _smallk_case(tmp_path, kernel, M, N, K, KM, beta, dtype="float32"):
+    rng = np.random.default_rng(9)
+    cT, ct = ("float", c_float) if dtype == "float32" else ("double", c_double)
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), kernel)
+    k = EmulatedKernel(src, kernel, tmp_path, threaded=True, template_args=f"{cT}, {KM}", type_subst={"T": cT})
+    A = _aligned((M, K), dtype, rng)
+    B = _aligned((K, N), dtype, rng)
+    C = _aligned((M, N), dtype, rng)
+    expect = 1.5 * (A.astype(np.float64) @ B.astype(np.float64)) + beta * C.astype(np.float64)
+    args = [c_longlong(M), c_longlong(N), c_int(K), ct(1.5), _ptr(A), c_longlong(K), c_longlong(1), _ptr(B), c_longlong(N),
+            c_longlong(1), ct(beta), _ptr(C), c_longlong(N)]
+    k.launch(((N + 255) // 256, 2), 256, args)
+    np.testing.assert_allclose(C, expect, rtol=1e-5 if dtype == "float32" else 1e-12, atol=1e-5 if dtype == "float32" else 1e-12)
+
+
+@pytest.mark.parametrize("M,N,K,KM,beta", [(130, 256, 8, 8, 0.0), (300, 70, 8, 8, 0.75), (65, 1024, 3, 4, 1.0), (200, 260, 13, 16, 0.5)])
+def test_skinny_gemm_small_k_kernel(tmp_path, M, N, K, KM, beta):
+    """gemm_smallk_kernel (csrc/ptk_blas.cu): C = alpha*A[M,K<=16] @ B[K,N] + beta*C with A tiles staged in shared memory,
+    ragged last row tile, columns that do not fill the last block, vector and scalar epilogues."""
+    _smallk_case(tmp_path, "gemm_smallk_kernel", M, N, K, KM, beta)
+
+
+def _smalln_case(tmp_path, kernel, M, N_act, NT, K, beta, grid=3):
+    rng = np.random.default_rng(10)
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), kernel)
+    k = EmulatedKernel(src, kernel, tmp_path, threaded=True, template_args=f"float, {NT}", type_subst={"T": "float"},
+                       dynamic_smem="sn_smem")
+    A = _aligned((M, K), "float32", rng)
+    B = _aligned((K, N_act), "float32", rng)
+    C = _aligned((M, N_act), "float32", rng)
+    expect = 0.5 * (A.astype(np.float64) @ B.astype(np.float64)) + beta * C.astype(np.float64)
+    unit = 32 * 4 * 4
+    kchunk = (K + unit - 1) // unit * unit
+    args = [c_longlong(M), c_int(N_act), c_longlong(K), c_int(kchunk), c_float(0.5), _ptr(A), c_longlong(K), _ptr(B),
+            c_longlong(N_act), c_longlong(1), c_float(beta), _ptr(C), c_longlong(N_act), c_longlong(1)]
+    k.launch(grid, 256, args)
+    np.testing.assert_allclose(C, expect, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("M,N_act,NT,K,beta", [(50, 8, 8, 1024, 0.0), (27, 5, 8, 700, 1.0), (64, 1, 1, 512, 0.5), (40, 16, 16, 96, 0.0)])
+def test_skinny_gemm_small_n_kernel(tmp_path, M, N_act, NT, K, beta):
+    """gemm_smalln_kernel: C[M, N<=16] = alpha*A[M,K] @ B[K,N] + beta*C, one warp per row, B transposed in shared memory,
+    vector path with a K that is not a multiple of the sweep, padded template width (n_act < N)."""
+    _smalln_case(tmp_path, "gemm_smalln_kernel", M, N_act, NT, K, beta)
