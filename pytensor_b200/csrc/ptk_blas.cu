@@ -2,6 +2,7 @@
 // These are the "<= 1e-5 vs the C linker" paths behind Gemm / Dot22 / Dot22Scalar / Gemv / Ger
 // (pytensor/tensor/blas/gemm.py:76,248,298, gemv.py:16, ger.py:8); the bf16 tensor-core path is ptk_gemm_tc.cu.
 #include <algorithm>
+#include <cstdlib>
 #include "ptk_common.h"
 
 namespace ptk {
@@ -160,6 +161,85 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2)) gemm_smallk_ker
   }
 }
 
+// v2 of the small-K kernel (selected with PTK_BLAS_V2=1 until measured on the device): identical arithmetic, but the
+// read-modify-write of C is software-pipelined.  In v1 every row's `old = C[m, n0..n0+3]` load sits behind the previous row's
+// store to the same array, which the compiler must keep in order, so each thread has ONE 16-byte load in flight and the
+// kernel is latency-bound (ncu: 31 % of DRAM peak at 36 % warps active).  Here the loads of G = 4 rows are issued together,
+// before any of the group's stores.
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) gemm_smallk_v2_kernel(
+    int64_t M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t sa0, int64_t sa1, const T* __restrict__ B,
+    int64_t sb0, int64_t sb1, T beta, T* __restrict__ C, int64_t sc0) {
+  constexpr int TR = 64, G = 4;
+  struct __align__(4 * sizeof(T)) V4 { T v[4]; };
+  __shared__ T As[TR][KMAX + 1];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 column-threads x 4 row-threads
+  const int64_t n0 = ((int64_t)blockIdx.x * 64 + tx) * 4;
+  T b[KMAX][4];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n0 + j < N) ? B[k * sb0 + (n0 + j) * sb1] : T(0);
+  const bool col_ok = n0 < N;
+  const bool full4 = n0 + 3 < N;
+  for (int64_t m0 = (int64_t)blockIdx.y * TR; m0 < M; m0 += (int64_t)gridDim.y * TR) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TR * KMAX; e += blockDim.x) {
+      const int r = e / KMAX, k = e - r * KMAX;
+      As[r][k] = (m0 + r < M && k < K) ? A[(m0 + r) * sa0 + k * sa1] : T(0);
+    }
+    __syncthreads();
+    if (!col_ok) continue;
+    for (int rr0 = 0; rr0 < TR / 4; rr0 += G) {
+      V4 old[G];
+      bool vec[G];
+      // phase 1: all of the group's reads of C (independent loads, nothing of this group has been stored yet)
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int64_t m = m0 + (rr0 + u) * 4 + ty;
+        T* c = C + m * sc0 + n0;
+        vec[u] = m < M && full4 && ((((uintptr_t)c) & (4 * sizeof(T) - 1)) == 0);
+        if (vec[u] && beta != T(0)) old[u] = *reinterpret_cast<const V4*>(c);
+      }
+      // phase 2: products, epilogue, stores
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int r = (rr0 + u) * 4 + ty;
+        const int64_t m = m0 + r;
+        if (m >= M) continue;
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const T a = As[r][k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] += a * b[k][j];
+        }
+        T* c = C + m * sc0 + n0;
+        if (vec[u]) {
+          V4 out;
+          if (beta != T(0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j] + beta * old[u].v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out.v[j] = alpha * acc[j];
+          }
+          *reinterpret_cast<V4*>(c) = out;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + j < N) {
+              T v = alpha * acc[j];
+              if (beta != T(0)) v += beta * c[j];
+              c[j] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 constexpr int SN_MAXN = 16;
 // N <= 16, A unit-stride along K: one warp per row of A; each lane streams 16-byte vectors of the row (4 in flight) and
 // multiplies them with B, which is staged TRANSPOSED in shared memory ONCE per CTA and K-chunk (Bs[n][k], k contiguous ->
@@ -242,6 +322,112 @@ __global__ void __launch_bounds__(256) gemm_smalln_kernel(int64_t M, int n_act, 
   }
 }
 
+// PTK_BLAS_V2=1 selects the restructured skinny-GEMM kernels below (validated on the host emulator, tests/; to be timed on
+// the device before they become the default).
+static bool blas_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PTK_BLAS_V2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// v2 of the small-N kernel (PTK_BLAS_V2=1): one warp owns R rows at a time.  v1 re-reads the N vectors of B from shared
+// memory for every row (8 x 16 B of LDS per 16 B of A: ~16 TB/s of shared-memory traffic at 2 TB/s of HBM — the
+// shared-memory pipe, not DRAM, is what saturates); with R rows per warp each LDS.128 of B feeds R rows' FMAs, and the
+// R x U row vectors are independent global loads in flight.
+template <typename T, int N, int R>
+__global__ void __launch_bounds__(256) gemm_smalln_v2_kernel(int64_t M, int n_act, int64_t K, int kchunk, T alpha,
+                                                             const T* __restrict__ A, int64_t sa0, const T* __restrict__ B,
+                                                             int64_t sb0, int64_t sb1, T beta, T* __restrict__ C,
+                                                             int64_t sc0, int64_t sc1) {
+  constexpr int V = 16 / sizeof(T);  // elements per 16-byte vector
+  constexpr int U = 2;               // vectors per lane and row in flight
+  extern __shared__ __align__(16) unsigned char sn_smem[];
+  T* Bs = reinterpret_cast<T*>(sn_smem);  // [N][kchunk + V]
+  const int ldb = kchunk + V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + warp;
+  const bool vec_ok = (sa0 % V == 0) && ((((uintptr_t)A) & 15) == 0) && (kchunk % (32 * V * U) == 0);
+  for (int64_t k0 = 0; k0 < K; k0 += kchunk) {
+    const int kc = (int)min((int64_t)kchunk, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * kchunk; e += blockDim.x) {
+      const int n = e / kchunk, k = e - n * kchunk;
+      Bs[n * ldb + k] = (k < kc && n < n_act) ? B[(k0 + k) * sb0 + n * sb1] : T(0);
+    }
+    __syncthreads();
+    const bool first = k0 == 0;
+    for (int64_t mb = gw * R; mb < M; mb += warps_total * R) {
+      T acc[R][N];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[r][n] = T(0);
+      const T* arow[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) arow[r] = A + min(mb + r, M - 1) * sa0 + k0;  // rows past M alias the last row (not stored)
+      if (vec_ok && ((k0 % V) == 0)) {
+        for (int kb = 0; kb < kchunk; kb += 32 * V * U) {
+          T a[R][U][V];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int kk = kb + (u * 32 + lane) * V;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (kk + V <= kc) *reinterpret_cast<uint4*>(a[r][u]) = *reinterpret_cast<const uint4*>(arow[r] + kk);
+              else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) a[r][u][e] = (kk + e < kc) ? arow[r][kk + e] : T(0);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int kk = kb + (u * 32 + lane) * V;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              T bv[V];
+              *reinterpret_cast<uint4*>(bv) = *reinterpret_cast<const uint4*>(&Bs[n * ldb + kk]);
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[r][n] += a[r][u][e] * bv[e];
+            }
+          }
+        }
+      } else {
+        for (int k = lane; k < kc; k += 32) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const T av = arow[r][k];
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[r][n] += av * Bs[n * ldb + k];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          T v = acc[r][n];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && n < n_act && mb + r < M) {
+            T* c = C + (mb + r) * sc0 + n * sc1;
+            T out = alpha * v;
+            if (first) { if (beta != T(0)) out += beta * (*c); }
+            else out += *c;
+            *c = out;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <typename T, int N>
 ptk_status launch_smalln(int64_t M, int n_act, int64_t K, T alpha, const T* A, int64_t sa0, const T* B, int64_t sb0,
                          int64_t sb1, T beta, T* C, int64_t sc0, int64_t sc1, unsigned grid, cudaStream_t st) {
@@ -255,6 +441,14 @@ ptk_status launch_smalln(int64_t M, int n_act, int64_t K, T alpha, const T* A, i
   (void)attr_done;
   cudaError_t e = cudaFuncSetAttribute(gemm_smalln_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (e != cudaSuccess) return ptk::check_cuda(e, "cudaFuncSetAttribute(gemm_smalln)");
+  if (blas_v2()) {
+    constexpr int R = (N <= 8) ? 4 : 2;  // R x N accumulators per lane
+    e = cudaFuncSetAttribute(gemm_smalln_v2_kernel<T, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return ptk::check_cuda(e, "cudaFuncSetAttribute(gemm_smalln_v2)");
+    const unsigned g2 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((M + 8 * R - 1) / (8 * R), grid));
+    gemm_smalln_v2_kernel<T, N, R><<<g2, 256, smem, st>>>(M, n_act, K, (int)kchunk, alpha, A, sa0, B, sb0, sb1, beta, C, sc0, sc1);
+    return PTK_OK;
+  }
   gemm_smalln_kernel<T, N><<<grid, 256, smem, st>>>(M, n_act, K, (int)kchunk, alpha, A, sa0, B, sb0, sb1, beta, C, sc0, sc1);
   return PTK_OK;
 }
@@ -270,9 +464,16 @@ ptk_status launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const void
     unsigned gy = (unsigned)std::min<int64_t>((M + 63) / 64, std::max<int64_t>(1, (int64_t)sms * 12 / gx));
 #define PTK_SK(KM) gemm_smallk_kernel<T, KM><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, \
                                                                       (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0)
-    if (K <= 4) PTK_SK(4);
+#define PTK_SK2(KM) gemm_smallk_v2_kernel<T, KM><<<dim3(gx, gy), 256, 0, st>>>(M, N, (int)K, (T)alpha, (const T*)A, sa0, sa1, \
+                                                                          (const T*)B, sb0, sb1, (T)beta, (T*)C, sc0)
+    if (blas_v2()) {
+      if (K <= 4) PTK_SK2(4);
+      else if (K <= 8) PTK_SK2(8);
+      else PTK_SK2(16);
+    } else if (K <= 4) PTK_SK(4);
     else if (K <= 8) PTK_SK(8);
     else PTK_SK(16);
+#undef PTK_SK2
 #undef PTK_SK
     PTK_LAUNCH_CHECK("gemm_smallk");
     return PTK_OK;

@@ -344,16 +344,17 @@ def test_skinny_gemm_small_k_kernel(tmp_path, M, N, K, KM, beta):
     _smallk_case(tmp_path, "gemm_smallk_kernel", M, N, K, KM, beta)
 
 
-def _smalln_case(tmp_path, kernel, M, N_act, NT, K, beta, grid=3):
+def _smalln_case(tmp_path, kernel, M, N_act, NT, K, beta, grid=3, R=None):
     rng = np.random.default_rng(10)
     src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), kernel)
-    k = EmulatedKernel(src, kernel, tmp_path, threaded=True, template_args=f"float, {NT}", type_subst={"T": "float"},
+    targs = f"float, {NT}" + (f", {R}" if R else "")
+    k = EmulatedKernel(src, kernel, tmp_path, threaded=True, template_args=targs, type_subst={"T": "float"},
                        dynamic_smem="sn_smem")
     A = _aligned((M, K), "float32", rng)
     B = _aligned((K, N_act), "float32", rng)
     C = _aligned((M, N_act), "float32", rng)
     expect = 0.5 * (A.astype(np.float64) @ B.astype(np.float64)) + beta * C.astype(np.float64)
-    unit = 32 * 4 * 4
+    unit = 32 * 4 * 4   # launch_smalln's sweep unit (a multiple of the v2 kernel's 32 * V * U as well)
     kchunk = (K + unit - 1) // unit * unit
     args = [c_longlong(M), c_int(N_act), c_longlong(K), c_int(kchunk), c_float(0.5), _ptr(A), c_longlong(K), _ptr(B),
             c_longlong(N_act), c_longlong(1), c_float(beta), _ptr(C), c_longlong(N_act), c_longlong(1)]
@@ -366,3 +367,19 @@ def test_skinny_gemm_small_n_kernel(tmp_path, M, N_act, NT, K, beta):
     """gemm_smalln_kernel: C[M, N<=16] = alpha*A[M,K] @ B[K,N] + beta*C, one warp per row, B transposed in shared memory,
     vector path with a K that is not a multiple of the sweep, padded template width (n_act < N)."""
     _smalln_case(tmp_path, "gemm_smalln_kernel", M, N_act, NT, K, beta)
+
+
+@pytest.mark.parametrize("M,N,K,KM,beta", [(130, 256, 8, 8, 0.0), (300, 70, 8, 8, 0.75), (65, 1024, 3, 4, 1.0), (200, 260, 13, 16, 0.5),
+                                           (61, 64, 8, 8, 1.0), (259, 513, 8, 8, 0.25)])
+def test_skinny_gemm_small_k_kernel_v2(tmp_path, M, N, K, KM, beta):
+    """The software-pipelined variant (PTK_BLAS_V2=1): the group's reads of C are issued before its stores — same results,
+    incl. ragged row groups (M not a multiple of 16 / 64), misaligned rows (N = 513: only every 4th row is 16-byte aligned)
+    and the scalar edge columns."""
+    _smallk_case(tmp_path, "gemm_smallk_v2_kernel", M, N, K, KM, beta)
+
+
+@pytest.mark.parametrize("M,N_act,NT,K,beta,R", [(50, 8, 8, 1024, 0.0, 4), (27, 5, 8, 700, 1.0, 4), (64, 1, 1, 512, 0.5, 4), (41, 16, 16, 96, 0.0, 2),
+                                                 (3, 8, 8, 1024, 1.0, 4), (130, 4, 4, 2100, 0.5, 4)])
+def test_skinny_gemm_small_n_kernel_v2(tmp_path, M, N_act, NT, K, beta, R):
+    """The R-rows-per-warp variant: row groups that run past M, fewer rows than one group, K spanning several sweeps."""
+    _smalln_case(tmp_path, "gemm_smalln_v2_kernel", M, N_act, NT, K, beta, R=R)
