@@ -44,9 +44,18 @@ def register():
 
     @rewrite_ofg_inner_graph.register(CUDALinker)
     def _cuda_rewrite_ofg_inner_graph(linker, op, node, inner, *, mode):
+        # Same contract as the reference's destructive variant (compile/rewriting.py:141-152): an OpFromGraph declares
+        # no destroy_map / view_map, so its inner graph must neither write into its inputs (the outer VM hands the
+        # caller's device buffers straight to the inner Executor) nor return views of them; in-place between purely
+        # internal buffers stays allowed.
+        from pytensor.compile.aliasing import add_supervisor_to_fgraph, insert_deepcopy
+        from pytensor.compile.io import In, Out
         from pytensor.compile.rewriting import _ofg_inner_optimizer
 
+        specs = [In(x, borrow=True, mutable=False) for x in inner.inputs]
+        add_supervisor_to_fgraph(fgraph=inner, input_specs=specs, accept_inplace=True)
         _ofg_inner_optimizer(mode, op).rewrite(inner)
+        insert_deepcopy(inner, wrapped_inputs=specs, wrapped_outputs=[Out(o, borrow=False) for o in inner.outputs])
 
     query = RewriteDatabaseQuery(include=["fast_run"], exclude=["cxx_only"])
     if "cuda" not in pmode.predefined_linkers:

@@ -73,7 +73,8 @@ class CudaVM:
             for cell, o in zip(self.output_storage, outs):
                 cell[0] = o
             return outs
-        outs = outputs_to_host(out_vals, self.device_outputs, copy_device=ex.last_from_graph and not self.borrow_outputs)
+        outs = outputs_to_host(out_vals, self.device_outputs, copy_device=ex.last_from_graph and not self.borrow_outputs,
+                               sink=ex.sink)
         for cell, o in zip(self.output_storage, outs):
             cell[0] = o
         if output_subset is not None:
@@ -140,19 +141,20 @@ class CudaVM:
         rest = [j for j in range(len(out_vals)) if j not in self.dev_updates]
         if rest:
             outs = outputs_to_host([out_vals[j] for j in rest], self.device_outputs,
-                                   copy_device=ex.last_from_graph and not self.borrow_outputs)
+                                   copy_device=ex.last_from_graph and not self.borrow_outputs, sink=ex.sink)
             for j, o in zip(rest, outs):
                 res[j] = o
-        else:
-            from pytensor_b200.vm import nodes_basic
-
-            if len(nodes_basic._pending_flags) > 256:  # nothing forces a sync here: flags are checked lazily
-                del nodes_basic._pending_flags[:-64]
+        # (an updates-only call never synchronises: its error words are inspected when the function is called again)
         for cell, o in zip(self.output_storage, res):
             cell[0] = o
         if output_subset is not None:
             return [o if (i in output_subset or i in self.dev_updates) else None for i, o in enumerate(res)]
         return res
+
+    def check_errors(self):
+        """Synchronise and raise the IndexError an earlier device-output / updates-only call may have flagged (those
+        calls never synchronise themselves; the next call of this function would raise it too)."""
+        self.executor.sink.check(sync=True)
 
     def clear_storage(self):
         for i in range(len(self.executor.vals)):

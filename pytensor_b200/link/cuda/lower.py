@@ -212,7 +212,8 @@ def lower_node(node, opts):
     if isinstance(op, DeepCopyOp):
         return nb.DeepCopyNode()
     if isinstance(op, CheckAndRaise):
-        return nb.AssertNode(op.msg, getattr(op.exc_type, "__name__", "AssertionError"))
+        et = op.exc_type
+        return nb.AssertNode(op.msg, getattr(et, "__qualname__", "AssertionError"), getattr(et, "__module__", "builtins"))
     if isinstance(op, Join):
         return nb.JoinNode(node.outputs[0].type.dtype, op.axis)
 

@@ -323,10 +323,9 @@ def _index_block(index_vals, dims, name):
     lin = dev.empty(shape, "int64")
     if n:
         ptrs = (ctypes.c_void_p * len(its))(*[dev.ptr(t) for t in its])
-        flag = _err_flag()
-        _lib.check(_lib.lib().ptk_linearize_index(len(its), ptrs, dev.i64_array(dims), n, dev.ptr(lin), dev.ptr(flag),
+        flag = _err_flag(f"{name}: index out of bounds")
+        _lib.check(_lib.lib().ptk_linearize_index(len(its), ptrs, dev.i64_array(dims), n, dev.ptr(lin), flag,
                                                   dev.stream_ptr()), "ptk_linearize_index")
-        _pending_flags.append((flag, f"{name}: index out of bounds"))
     return lin
 
 
@@ -359,10 +358,9 @@ class TakeNode(Node):
         if out.numel():
             if n_src == 0:
                 raise IndexError("index out of bounds (taking from an empty axis)")
-            flag = _err_flag()
+            flag = _err_flag(f"{self.name}: index out of bounds")
             _lib.check(_lib.lib().ptk_take(dev.ptr(out), dev.ptr(x), dev.ptr(it), outer, n_src, it.numel(), inner,
-                                           x.element_size(), dev.ptr(flag), dev.stream_ptr()), "ptk_take")
-            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
+                                           x.element_size(), flag, dev.stream_ptr()), "ptk_take")
         return [Val(d=out)]
 
 
@@ -415,55 +413,140 @@ class PutNode(Node):
             L = _lib.lib()
             wsb = int(L.ptk_put_rows_workspace_bytes(n_dst, it.numel()))
             ws = dev.empty_t((wsb,), torch.uint8)
-            flag = _err_flag()
+            flag = _err_flag(f"{self.name}: index out of bounds")
             _lib.check(L.ptk_put_rows(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, n_dst, it.numel(),
-                                      _lib.DTYPE_CODE[self.dtype], dev.ptr(ws), wsb, dev.ptr(flag), dev.stream_ptr()),
+                                      _lib.DTYPE_CODE[self.dtype], dev.ptr(ws), wsb, flag, dev.stream_ptr()),
                        "ptk_put_rows")
-            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
             return [Val(d=x)]
         if n:
-            flag = _err_flag()
+            flag = _err_flag(f"{self.name}: index out of bounds")
             _lib.check(_lib.lib().ptk_put(dev.ptr(x), dev.ptr(yc), dev.ptr(it), outer, n_dst, it.numel(), inner,
                                           _lib.DTYPE_CODE[self.dtype], 0 if self.set_instead_of_inc else 1,
-                                          dev.ptr(flag), dev.stream_ptr()), "ptk_put")
-            _pending_flags.append((flag, f"{self.name}: index out of bounds"))
+                                          flag, dev.stream_ptr()), "ptk_put")
         return [Val(d=x)]
 
 
-# ---- deferred device-side error flags (checked by the VM at the end of a call, at its one sync point) -------------------
-_pending_flags: list = []
+# ---- deferred device-side error flags ------------------------------------------------------------------------------------
+class FlagSink:
+    """Per-Executor error words: every gather/scatter launch of one compiled function reports out-of-bounds
+    indices into its own slot of ONE persistent int32 array (kernels `atomicExch(slot, 1)`: sticky, never cleared on the
+    device while a call is in flight).  The array is mirrored into page-locked host memory by an asynchronous copy that
+    is queued behind the call's kernels (inside the captured CUDA graph when the call replays one), so
+      * a call that returns host arrays reads the mirror right after its single synchronisation (no extra D2H sync),
+      * a call that returns device tensors never synchronises: the mirror is inspected (non-blocking) at the start of the
+        function's next call and by `check(sync=True)` (`CudaVM.check_errors()`), so an out-of-bounds index is never
+        dropped and never attributed to a different compiled function."""
+
+    SLOTS = 64
+
+    def __init__(self):
+        self.words = None     # device int32[SLOTS]
+        self.mirror = None    # pinned host int32[SLOTS]
+        self.msgs = [None] * self.SLOTS
+        self.cursor = 0
+        self.used = False     # some launch of the current call took a slot
+        self.in_flight = False
+
+    def _ensure(self):
+        if self.words is None:
+            st = dev.alloc_state
+            arena, st.arena = st.arena, None   # persistent: never inside a capture arena
+            measuring, st.measuring = st.measuring, False
+            try:
+                self.words = dev.empty_t((self.SLOTS,), torch.int32)
+            finally:
+                st.arena, st.measuring = arena, measuring
+            side = dev._side_stream() if dev.alloc_state.capturing else None
+            sp = side.cuda_stream if side is not None else dev.stream_ptr()
+            _lib.check(_lib.lib().ptk_memset_async(dev.ptr(self.words), 0, 4 * self.SLOTS, sp), "memset")
+            _lib.check(_lib.lib().ptk_sync_stream(sp), "sync")
+            self.mirror = dev.pinned_empty((self.SLOTS,), "int32") if not _lib.TRACE_ONLY else np.zeros(self.SLOTS, "int32")
+            self.mirror[:] = 0
+
+    def begin_call(self):
+        self.cursor = 0
+        self.used = False
+
+    def slot(self, msg) -> int:
+        """Device address of the next error word of this call (program order -> the same slot on every call)."""
+        self._ensure()
+        k = min(self.cursor, self.SLOTS - 1)
+        self.cursor += 1
+        self.msgs[k] = msg if self.cursor <= self.SLOTS else "index out of bounds"
+        self.used = True
+        return dev.ptr(self.words) + 4 * k
+
+    def queue_mirror(self):
+        """Queue words -> pinned mirror behind the work of the current stream (capturable: becomes a memcpy node)."""
+        if self.words is None or _lib.TRACE_ONLY:
+            return
+        _lib.check(_lib.lib().ptk_memcpy_d2h_async(self.mirror.ctypes.data, dev.ptr(self.words), 4 * self.SLOTS,
+                                                   dev.stream_ptr()), "d2h flags")
+        self.in_flight = True
+
+    def check(self, sync=False):
+        """Raise IndexError (like the reference's C code) if a completed call flagged an out-of-bounds index."""
+        if self.words is None or not self.in_flight:
+            return
+        if sync:
+            if dev.alloc_state.capturing:
+                return
+            dev.synchronize()
+        bad = np.flatnonzero(self.mirror)
+        if bad.size:
+            msg = self.msgs[int(bad[0])] or "index out of bounds"
+            self.mirror[:] = 0
+            _lib.check(_lib.lib().ptk_memset_async(dev.ptr(self.words), 0, 4 * self.SLOTS, dev.stream_ptr()), "memset")
+            raise IndexError(msg)
+        if sync:
+            self.in_flight = False
 
 
-def _err_flag() -> torch.Tensor:
-    t = dev.empty_t((1,), torch.int32)
-    _lib.check(_lib.lib().ptk_memset_async(dev.ptr(t), 0, 4, dev.stream_ptr()), "memset")
-    return t
+_default_sink = FlagSink()   # nodes run outside an Executor (unit tests drive node.run directly)
+_sink_stack: list = []
+
+
+def current_sink() -> FlagSink:
+    return _sink_stack[-1] if _sink_stack else _default_sink
+
+
+def _err_flag(msg="index out of bounds") -> int:
+    """Device ADDRESS (int) of an error word owned by the running Executor."""
+    return current_sink().slot(msg)
 
 
 def check_pending_flags():
-    """Called by the VM after its end-of-call synchronisation; raises IndexError like the reference's C code."""
-    if not _pending_flags:
-        return
-    flags = list(_pending_flags)
-    _pending_flags.clear()
-    for flag, msg in flags:
-        if int(dev.to_host(flag)[0]) != 0:
-            raise IndexError(msg)
+    """Synchronising check of the default sink (direct node use)."""
+    _default_sink.queue_mirror()
+    _default_sink.check(sync=True)
 
 
 class AssertNode(Node):
     """Reference: Assert / CheckAndRaise, pytensor/raise_op.py:148 (view of input 0 when all conditions hold)."""
 
-    def __init__(self, msg, exc_name="AssertionError"):
+    def __init__(self, msg, exc_name="AssertionError", exc_module="builtins"):
         self.msg = msg
-        self.exc_name = exc_name
+        self.exc_name = exc_name       # qualified name + module: resolved at raise time (keeps the node picklable)
+        self.exc_module = exc_module
         self.name = "Assert"
+
+    def _exc_class(self):
+        import importlib
+
+        try:
+            obj = importlib.import_module(self.exc_module)
+            for part in self.exc_name.split("."):
+                obj = getattr(obj, part)
+            if isinstance(obj, type) and issubclass(obj, BaseException):
+                return obj
+        except Exception:  # noqa: BLE001 - the class may live in a module this box does not have
+            pass
+        return AssertionError
 
     def run(self, vals):
         for c in vals[1:]:
             if not bool(np.all(np.asarray(c.host()))):
-                exc = {"AssertionError": AssertionError, "ValueError": ValueError}.get(self.exc_name, AssertionError)
-                raise exc(self.msg)
+                raise self._exc_class()(self.msg)
         v = vals[0]
         return [Val(h=v.h, d=v.d)]
 

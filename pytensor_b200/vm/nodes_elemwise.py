@@ -109,10 +109,11 @@ def host_eval_program(prog: ScalarProgram, inputs):
             r = -a[0]
         elif op == "Abs":
             r = np.abs(a[0])
-        elif op == "IntDiv":
-            r = np.floor_divide(a[0], np.where(a[1] == 0, 1, a[1]))
-        elif op == "Mod":
-            r = np.mod(a[0], np.where(a[1] == 0, 1, a[1]))
+        elif op in ("IntDiv", "Mod"):
+            if not is_float(od) and np.any(a[1] == 0):
+                # the reference's C code fails the thunk (scalar/basic.py:2058-2066 for IntDiv, the Mod twin below it)
+                raise ZeroDivisionError("integer division by zero" if op == "IntDiv" else "integer modulo by zero")
+            r = np.floor_divide(a[0], a[1]) if op == "IntDiv" else np.mod(a[0], a[1])
         elif op == "Maximum":
             r = np.maximum(a[0], a[1])
         elif op == "Minimum":
@@ -534,9 +535,19 @@ class ElemwiseReduceNode(Node):
         if rows == 0 or cols == 0:
             return self._unfused(vals)
         ins = [v.dev() for v in vals]
+        # the reduced map output is never materialised unless something else reads it: no buffer for it
+        skip = None if self.store_reduced_input else self.which
+        cstr = []  # C-contiguous strides of `oshape` (layout of every freshly allocated output)
+        acc = 1
+        for s_ in reversed(oshape):
+            cstr.insert(0, acc)
+            acc *= s_
         outs = []
         for k, dt in enumerate(ew.prog.out_dtypes):
-            outs.append(ins[ew.inplace[k]] if k in ew.inplace else dev.empty(oshape, dt))
+            if k == skip and k not in ew.inplace:
+                outs.append(None)
+            else:
+                outs.append(ins[ew.inplace[k]] if k in ew.inplace else dev.empty(oshape, dt))
         # collapse kept dims -> rows and reduced dims -> cols for every operand
         ops = ins + outs
         strides = []
@@ -544,7 +555,7 @@ class ElemwiseReduceNode(Node):
             strides.append([0 if (ew.in_bcast[k][d] or (t.shape[d] == 1 and oshape[d] != 1)) else t.stride(d)
                             for d in range(nd)])
         for t in outs:
-            strides.append([t.stride(d) for d in range(nd)])
+            strides.append(list(cstr) if t is None else [t.stride(d) for d in range(nd)])
         kshape, ksts = _collapse(oshape[: nd - n_red], [st[: nd - n_red] for st in strides])
         cshape, csts = _collapse(oshape[nd - n_red:], [st[nd - n_red:] for st in strides])
         if len(kshape) != 1 or len(cshape) != 1:
@@ -556,7 +567,7 @@ class ElemwiseReduceNode(Node):
             inner = cst[0]
             if inner not in (0, 1):
                 return self._unfused_given(vals, ins, outs)
-            if inner == 1 and (dev.ptr(t) % (ITEMSIZE[dt] * vw) != 0 or kst[0] % vw != 0):
+            if t is not None and inner == 1 and (dev.ptr(t) % (ITEMSIZE[dt] * vw) != 0 or kst[0] % vw != 0):
                 vw = 1
             col_modes.append(inner)
         if any(m != 1 for m in col_modes[len(ins):]):
@@ -587,7 +598,7 @@ class ElemwiseReduceNode(Node):
         args += [c_longlong(rows), c_longlong(cols), c_int(1)]
         gx = min(row_blocks, sms * 16)
         jit.launch(fn, (gx, 1), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())
-        res = [Val(d=o) for o in outs]
+        res = [Val(d=o) if o is not None else None for o in outs]
         if not self.store_reduced_input:
             res[self.which] = None  # never materialised: the fusion pass guarantees nothing reads it
         return res + [Val(d=rout)]

@@ -198,7 +198,7 @@ class _GraphEntry:
     def __init__(self, nbytes):
         self.stage, self.nbytes = 1, nbytes
         self.arena = self.gexec = self.out_vals = None
-        self.static_in, self.flags, self.keep = [], [], []
+        self.static_in, self.flags, self.keep = [], None, []   # flags: the sink's slot messages of this signature
 
     def __del__(self):
         g, self.gexec = self.gexec, None
@@ -256,6 +256,7 @@ class Executor:
         self.call_times = [0.0] * n
         self.call_counts = [0] * n
         self.event_log = None  # when a list: (step index, start event, stop event) per executed step (no syncs)
+        self.sink = nodes_basic.FlagSink()  # this function's device-side error words (out-of-bounds indices)
 
     # ---- CUDA-graph path ------------------------------------------------------------------------------------------
     @staticmethod
@@ -277,6 +278,24 @@ class Executor:
         return tuple(sig)
 
     def run(self, inputs):
+        """Outermost executors own the error-word sink of the call; nested ones (OpFromGraph, Scan bodies, pipeline
+        chunks) report into their caller's."""
+        stack = nodes_basic._sink_stack
+        if stack:
+            return self._run(inputs)
+        sink = self.sink
+        sink.check()          # non-blocking: an out-of-bounds index flagged by an earlier device-output call
+        sink.begin_call()
+        stack.append(sink)
+        try:
+            outs = self._run(inputs)
+            if sink.used and not self.last_from_graph:
+                sink.queue_mirror()   # (a replayed graph carries the mirror copy as its last node)
+            return outs
+        finally:
+            stack.pop()
+
+    def _run(self, inputs):
         from ..runtime import lib as _lib
 
         self.last_from_graph = False
@@ -330,7 +349,9 @@ class Executor:
                 if a.size:
                     _lib.check(L.ptk_memcpy_h2d_async(dev.ptr(t), a.ctypes.data, a.nbytes, sp), "h2d")
             _lib.check(L.ptk_graph_launch(e.gexec, sp), "graph launch")
-            nodes_basic._pending_flags.extend(e.flags)
+            if e.flags is not None:
+                sink = nodes_basic.current_sink()
+                sink.msgs, sink.used, sink.in_flight = e.flags, True, True
             e.keep.clear() if len(e.keep) > 64 else None
             self.last_from_graph = True
             return e.out_vals
@@ -460,12 +481,16 @@ class Executor:
                     e.static_in.append((k, t))
                     vals_in.append(Val(h=a if a.size <= 8 else None, d=t))
             _lib.check(L.ptk_sync_stream(sp), "sync")
-            n_flags = len(nodes_basic._pending_flags)
+            sink = nodes_basic.current_sink()
+            sink._ensure()
+            sink.begin_call()
             _lib.check(L.ptk_graph_begin_capture(sp), "begin capture")
             st.capturing = True
             ok = True
             try:
                 outs = self._run_streams(vals_in) if self.multi_stream else self._run_eager(vals_in)
+                if sink.used:
+                    sink.queue_mirror()   # memcpy node at the end of the graph: every replay refreshes the mirror
             except dev.GraphUnsupported:
                 ok = False
             finally:
@@ -473,20 +498,22 @@ class Executor:
                 g = ctypes_void_p()
                 rc = L.ptk_graph_end_capture(sp, ctypes_byref(g))
             if not ok or rc != 0:
-                del nodes_basic._pending_flags[n_flags:]
+                sink.begin_call()
                 if rc == 0 and g.value:
                     L.ptk_graph_destroy(g)
                 e.stage, e.arena, e.static_in = -1, None, []
                 st.arena = None
                 return self._run_eager(inputs)
             e.gexec = g.value
-            e.flags = list(nodes_basic._pending_flags[n_flags:])
+            e.flags = list(sink.msgs) if sink.used else None
             e.out_vals = outs
             e.stage = 2
         finally:
             st.arena = None
             st.capturing = False
         _lib.check(L.ptk_graph_launch(e.gexec, sp), "graph launch")
+        if e.flags is not None:
+            sink.in_flight = True
         self.last_from_graph = True
         return e.out_vals
 
@@ -586,14 +613,17 @@ class Executor:
         return outs
 
 
-def outputs_to_host(out_vals, device_outputs=False, copy_device=False):
+def outputs_to_host(out_vals, device_outputs=False, copy_device=False, sink=None):
     """Val -> what Function.__call__ hands to the user: NumPy arrays (one sync) or device tensors.
-    `copy_device`: device outputs may live in a graph arena that the next call overwrites -> hand out copies."""
+    `copy_device`: device outputs may live in a graph arena that the next call overwrites -> hand out copies.
+    `sink`: the executor's error words; their mirror copy was queued behind the call's kernels, so after the one
+    synchronisation of a host-output call it is inspected for free.  Device outputs never synchronise: their flags are
+    looked at when the function is called again (or by `CudaVM.check_errors()`)."""
     res = []
     pending = []
     for v in out_vals:
         if v.h is not None and v.d is None:
-            res.append(np.asarray(v.h))
+            res.append(np.array(v.h, copy=True))  # host-only values (shape vectors ...): a fresh object per call
         elif device_outputs:
             res.append(dev.clone(v.d) if copy_device else v.d)
         else:
@@ -603,11 +633,8 @@ def outputs_to_host(out_vals, device_outputs=False, copy_device=False):
         res[k] = dev.to_host(v.d, sync=False)
     if pending:
         dev.synchronize()
-        nodes_basic.check_pending_flags()
-    elif nodes_basic._pending_flags and not device_outputs:
-        dev.synchronize()
-        nodes_basic.check_pending_flags()
-    elif len(nodes_basic._pending_flags) > 256:
-        # device outputs never force a synchronisation; index-error flags are checked lazily (next host-visible call)
-        del nodes_basic._pending_flags[:-64]
+        if sink is not None:
+            sink.check()
+    elif sink is not None and sink.used and not device_outputs:
+        sink.check(sync=True)
     return res

@@ -160,3 +160,34 @@ def test_chunked_pipeline_with_row_reduction_cfg2(gpu):
     for g, w, r in zip(got, whole, ref):
         np.testing.assert_array_equal(g, w)
         np.testing.assert_allclose(g, r, rtol=1e-5, atol=1e-6)
+
+
+def test_opfromgraph_does_not_clobber_its_inputs(gpu):
+    """An OpFromGraph declares no destroy_map: its inner graph must not write into the outer value it was handed
+    (reference: destructive_rewrite_ofg_inner_graph protects the inner inputs, compile/rewriting.py:141-152)."""
+    from pytensor.compile.builders import OpFromGraph
+
+    xi = pt.fmatrix("xi")
+    ofg = OpFromGraph([xi], [pt.exp(-xi)])
+    x = pt.fmatrix("x")
+    y = x * np.float32(2)
+    w = y + ofg(y)  # y is read again AFTER the OpFromGraph node
+    xv = np.random.default_rng(71).standard_normal((33, 65)).astype("float32")
+    compare_cuda_and_cvm([x], [w], [xv])
+    # an inner output that is a view of an inner input must come back as a fresh buffer
+    ofg_t = OpFromGraph([xi], [xi.T])
+    compare_cuda_and_cvm([x], [ofg_t(y) + np.float32(1), y], [xv])
+
+
+def test_opfromgraph_leaves_device_shared_variables_intact(gpu):
+    from pytensor.compile.builders import OpFromGraph
+    import pytensor_b200
+
+    xi = pt.fvector("xi")
+    ofg = OpFromGraph([xi], [pt.tanh(xi) * np.float32(3)])
+    v0 = np.linspace(-1, 1, 257).astype("float32")
+    s = pytensor_b200.shared(v0.copy(), name="s")
+    f = pytensor.function([], ofg(s) + s, mode="CUDA")
+    for _ in range(4):  # eager, capture, replay, replay
+        np.testing.assert_allclose(f(), np.tanh(v0) * 3 + v0, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(s.get_value(), v0)

@@ -234,3 +234,20 @@ def test_shape_errors_raise_the_reference_exception_types():
         with pytest.raises(Exception) as got:
             trace_function(f, vals)
         assert got.type is ref.type, (str(out), got.type, ref.type, str(got.value).split("\\n")[0])
+
+
+def test_opfromgraph_inner_graph_never_destroys_its_inputs():
+    """the CUDA OpFromGraph rewrite must protect inner inputs and deep-copy aliased outputs like the
+    reference's destructive variant (pytensor/compile/rewriting.py:141-152)."""
+    from pytensor.compile.builders import OpFromGraph
+    from pytensor.compile.ops import DeepCopyOp
+
+    xi = pt.fmatrix("xi")
+    x = pt.fmatrix("x")
+    y = x * np.float32(2)
+    f = pytensor.function([x], y + OpFromGraph([xi], [pt.exp(-xi)])(y), mode="CUDA")
+    inner_nodes = [m for n in f.maker.fgraph.toposort() if isinstance(n.op, OpFromGraph) for m in n.op.fgraph.toposort()]
+    assert inner_nodes and all(not getattr(m.op, "destroy_map", None) for m in inner_nodes)
+    f2 = pytensor.function([x], OpFromGraph([xi], [xi.T])(y), mode="CUDA")
+    inner2 = [m.op for n in f2.maker.fgraph.toposort() if isinstance(n.op, OpFromGraph) for m in n.op.fgraph.toposort()]
+    assert any(isinstance(o, DeepCopyOp) for o in inner2)
