@@ -97,11 +97,15 @@ class ShardedSum:
     all-reduce.  Works for NumPy outputs (CPU/gloo) and device tensors (NCCL)."""
 
     def __init__(self, f_local, batch_arg_idx, group=None, collective="nccl"):
-        """collective: "nccl" (torch.distributed all_reduce) or "oneshot" (PeerAllReduce; packed device outputs only)."""
+        """collective: "nccl" (torch.distributed all_reduce after the call), "oneshot" (PeerAllReduce kernel launched
+        after the call; packed device outputs only), "oneshot_ingraph" (the same kernel registered as the executor's
+        epilogue: it is part of the function's launch list, hence of its captured CUDA graph — one cudaGraphLaunch per
+        evaluation covers compute AND the all-reduce; packed device output only), "none" (single process)."""
         import torch.distributed as dist
 
         self.collective = collective
         self._peer = None
+        self._ingraph = False
         self.f = f_local
         self.batch_arg_idx = list(batch_arg_idx)
         self.group = group
@@ -112,6 +116,43 @@ class ShardedSum:
 
     def local_args(self, args):
         return shard_args(args, self.batch_arg_idx, self.world, self.rank)
+
+    def describe(self):
+        if self.world == 1:
+            return None
+        return {"nccl": "ncclAllReduce (torch.distributed) after the graph replay",
+                "oneshot": "hand-written one-shot NVLink all-reduce kernel after the graph replay",
+                "oneshot_ingraph": "hand-written one-shot NVLink all-reduce kernel INSIDE the captured CUDA graph"
+                }.get(self.collective, self.collective) + ("" if self.collective != "oneshot_ingraph" or self._ingraph
+                                                           else " (NOT installed: fell back to launching it after the call)")
+
+    def _install_ingraph(self):
+        """Register the one-shot all-reduce as the executor's epilogue (runs right after the last node, on the VM
+        stream, also while capturing): needs a packed single device output."""
+        import torch
+
+        vm = getattr(self.f, "vm", None)
+        ex = getattr(vm, "executor", None)
+        if ex is None or not getattr(vm, "device_outputs", False):
+            return False
+        peer_box = {}
+
+        def epilogue(out_vals):
+            v = out_vals[0]
+            if len(out_vals) != 1 or v.d is None or not v.d.is_contiguous() or v.d.numel() > 1024 \
+                    or v.d.dtype not in (torch.float32, torch.float64):
+                raise RuntimeError("oneshot_ingraph needs ONE packed contiguous float device output of <= 1024 elements")
+            if "p" not in peer_box:
+                from pytensor_b200.runtime import device as dev
+
+                if dev.alloc_state.capturing:
+                    raise dev.GraphUnsupported("peer rendezvous inside a capture")
+                peer_box["p"] = PeerAllReduce(self.group, 1024, "float32" if v.d.dtype == torch.float32 else "float64")
+            peer_box["p"](v.d)
+
+        ex.epilogue = epilogue
+        self._peer_box = peer_box
+        return True
 
     def reduce(self, outs):
         """Pack -> all_reduce(sum) -> unpack. One collective per evaluation regardless of the number of outputs."""
@@ -156,7 +197,13 @@ class ShardedSum:
 
     def __call__(self, *args, presharded=False):
         local = list(args) if presharded else self.local_args(args)
+        if self.collective == "oneshot_ingraph" and self.world > 1 and not self._ingraph:
+            self._ingraph = self._install_ingraph()
+            if not self._ingraph:
+                self.collective = "oneshot"
         outs = self.f(*local)
         if not isinstance(outs, list | tuple):
             outs = [outs]
+        if self._ingraph or self.collective == "none":
+            return list(outs)
         return self.reduce(list(outs))

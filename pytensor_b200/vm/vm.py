@@ -257,6 +257,8 @@ class Executor:
         self.call_counts = [0] * n
         self.event_log = None  # when a list: (step index, start event, stop event) per executed step (no syncs)
         self.sink = nodes_basic.FlagSink()  # this function's device-side error words (out-of-bounds indices)
+        self.epilogue = None  # callable(out_vals) run on the VM stream right after the last node (e.g. the in-graph
+        #                       all-reduce of a batch-sharded evaluation, pytensor_b200/sharded.py); captured with the graph
 
     # ---- CUDA-graph path ------------------------------------------------------------------------------------------
     @staticmethod
@@ -563,6 +565,8 @@ class Executor:
                 ev.record(sd)
                 main.wait_event(ev)
         outs = [vals[s] for s in p.outputs]
+        if self.epilogue is not None:
+            self.epilogue(outs)
         for s in range(len(vals)):
             if s not in p.constants:
                 vals[s] = None
@@ -604,6 +608,8 @@ class Executor:
                 for j in st.free:
                     vals[j] = None
         outs = [vals[s] for s in p.outputs]
+        if self.epilogue is not None:
+            self.epilogue(outs)
         if self.allow_gc:
             for s in p.inputs:
                 vals[s] = None
