@@ -285,7 +285,12 @@ def build_program(fgraph, order, opts, storage_map=None):
             else:
                 slot(v)
     if opts.get("fuse", True):
-        steps = fuse_steps(steps, [slots[v] for v in fgraph.outputs], opts)
+        # static types of every slot (dtype, ndim, broadcast pattern) + the constants: what the region finder needs
+        fopts = dict(opts)
+        fopts["slot_types"] = {k: (v.type.dtype, v.type.ndim, tuple(v.type.broadcastable))
+                               for v, k in slots.items() if hasattr(v.type, "broadcastable")}
+        fopts["constants"] = constants
+        steps = fuse_steps(steps, [slots[v] for v in fgraph.outputs], fopts)
     program = Program(len(slots), [slots[v] for v in fgraph.inputs], [slots[v] for v in fgraph.outputs], constants,
                       steps)
     return program, thunks

@@ -115,10 +115,35 @@ struct alignas(16) uint4 { unsigned x, y, z, w; };
 static inline void __syncwarp() {}
 """
 
+# Warp-cooperative generated kernels (codegen/rowfuse.py): lanes hand values over through shared memory, so __syncwarp is
+# a REAL warp barrier here; shared/global atomics are host atomics; __ldg is a plain load; 128-bit vector types.
+WARP_SHIM = r"""
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline void __syncwarp() { pthread_barrier_wait(&emu_warp_bar[threadIdx.x >> 5]); }
+static inline float atomicAdd(float* p, float v) {
+  unsigned int* u = reinterpret_cast<unsigned int*>(p); unsigned int old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+  float f;
+  do { std::memcpy(&f, &old, 4); f += v; std::memcpy(&neu, &f, 4); }
+  while (!__atomic_compare_exchange_n(u, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return f - v;
+}
+static inline double atomicAdd(double* p, double v) {
+  unsigned long long* u = reinterpret_cast<unsigned long long*>(p); unsigned long long old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+  double f;
+  do { std::memcpy(&f, &old, 8); f += v; std::memcpy(&neu, &f, 8); }
+  while (!__atomic_compare_exchange_n(u, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return f - v;
+}
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+using std::fma;
+"""
+
 
 class EmulatedKernel:
     def __init__(self, source: str, name: str, tmp_path, threaded: bool = False, template_args: str = "",
-                 type_subst: dict | None = None, dynamic_smem: str | None = None):
+                 type_subst: dict | None = None, dynamic_smem: str | None = None, warp_shim: bool = False):
         """`template_args` / `type_subst`: instantiate a template kernel (e.g. "float, 8", {"T": "float"});
         `dynamic_smem`: name of the kernel's `extern __shared__` array (gets a fixed 100 KiB static buffer)."""
         from pytensor_b200.codegen.elemwise import _VEC_HELPERS
@@ -127,7 +152,9 @@ class EmulatedKernel:
         if dynamic_smem:
             body = re.sub(r"extern __shared__[^\n;]*\b" + re.escape(dynamic_smem) + r"\[\];",
                           f"alignas(16) static unsigned char {dynamic_smem}[100 * 1024];", body)
-            body = STATIC_SHIM + body
+            body = (WARP_SHIM if warp_shim else STATIC_SHIM) + body
+        elif warp_shim:
+            body = WARP_SHIM + body
         body = _strip_launch_bounds(body)
         m = re.search(r"__global__ void\s+" + re.escape(name) + r"\((.*?)\) \{", body, re.S)
         assert m, "kernel signature not found"

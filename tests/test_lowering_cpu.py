@@ -64,8 +64,13 @@ def test_cfg5_and_metric_graph_lower():
     ins, outs, mk, _ = W.cfg5_logp_grad(B=256, n=64, J=8, K=4)
     f = pytensor.function(ins, outs, mode="CUDA")
     names = _steps(f)
-    assert "TakeNode" in names and "PutNode" in names and "GemmNode" in names
-    trace_function(f, mk())
+    # gather, both skinny Gemms, the Composites, the scatter-add and every Sum run as ONE row-fused region kernel ...
+    assert names.count("RowRegionNode") == 1 and "TakeNode" not in names and "GemmNode" not in names
+    region = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "RowRegionNode"][0]
+    inner = [type(st.impl).__name__ for st in region.sub_steps]   # ... which keeps its constituent steps as the fallback
+    assert "TakeNode" in inner and "PutNode" in inner and "GemmNode" in inner
+    assert trace_function(f, mk()) <= 8   # region kernel + finishing kernel + the five tiny Join copies
+    assert region.fused_calls == 1 and region.unfused_calls == 0
     ins, outs, mk, _ = W.metric_graph(n=16, layers=84, scan_steps=16)
     f = pytensor.function(ins, outs, mode="CUDA")
     assert len(f.maker.fgraph.toposort()) >= 256
