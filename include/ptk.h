@@ -152,6 +152,18 @@ ptk_status   ptk_gemm_tc_ex(int64_t M, int64_t N, int64_t K, double alpha, const
                       const void* A_bf16, int64_t lda_bf16, const void* B_f32, int64_t sb0, int64_t sb1, double beta,
                       void* C, int64_t sc0, int64_t sc1, const void* bias, int act, void* C_bf16, int64_t ldc_bf16,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* fp32-ACCURATE product on the tensor cores — what mode="CUDA" runs for large fp32 Dot22 / Gemm (the reference calls sgemm_
+ * here: pytensor/tensor/blas/c_code/codegen.py:463-540; parity bar <= 1e-5 vs that result):
+ *   C = act(alpha * A @ B + beta * C + bias[N]),  A, B, C fp32 with arbitrary element strides.
+ * Each operand is staged as THREE bf16 pieces x = x1 + x2 + x3 (24 mantissa bits in total); per 64-wide k-block the
+ * cta_group::2 tcgen05 kernel accumulates `terms` piece products in the fp32 TMEM accumulator, smallest first:
+ *   terms = 6: A3B1+A2B2+A1B3+A2B1+A1B2+A1B1 (only O(2^-24) products dropped: below sgemm's own rounding noise),
+ *   terms = 3: A2B1+A1B2+A1B1 (about 4e-6 of the output scale at K = 4096; twice as fast).
+ * workspace >= ptk_gemm_split_workspace_bytes(M, N, K), caller-owned. */
+size_t       ptk_gemm_split_workspace_bytes(int64_t M, int64_t N, int64_t K);
+ptk_status   ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0, int64_t sa1,
+                      const void* B_f32, int64_t sb0, int64_t sb1, double beta, void* C, int64_t sc0, int64_t sc1,
+                      const void* bias, int act, int terms, void* workspace, size_t workspace_bytes, void* stream);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

@@ -161,7 +161,18 @@ struct EpiParams {
   __nv_bfloat16* Cbf;  // optional bf16 copy of the result, row-major [M, ldcbf] (the next layer's K-major A operand)
   long long ldcbf;
   int split_tail;      // pair kernel: split the units of the last partial round into 256 x 128 halves (PTK_GEMM_SPLIT=0: off)
+  // fp32-accurate mode (pair kernel): every fp32 operand is staged as THREE bf16 pieces x = x1 + x2 + x3 (8 mantissa bits
+  // each) stacked along the rows of the staging matrix (piece i of A at rows [i * a_rows, ...)); per k-block the kernel
+  // accumulates `terms` piece products into the same fp32 TMEM accumulator, smallest first:
+  //   terms = 6: A3B1 + A2B2 + A1B3 + A2B1 + A1B2 + A1B1   (drops only O(2^-24) terms: below sgemm's own rounding noise)
+  //   terms = 3:                      A2B1 + A1B2 + A1B1   (~4e-6 of the output scale at K = 4096)
+  //   terms = 1: plain bf16 operands (the CUDA_BF16 mode)
+  int terms;
+  int a_rows, b_rows;  // row pitch between the stacked pieces
 };
+// piece indices of the term sequence; a run of `terms` entries ending at index 5 is used
+__device__ __constant__ int kPieceA[6] = {2, 1, 0, 1, 0, 0};
+__device__ __constant__ int kPieceB[6] = {0, 1, 2, 0, 1, 0};
 
 // kCluster == 2: CTA pairs (cluster 2x1x1) share the B tile of a 256-row super-tile — each CTA loads HALF of it and
 // TMA-multicasts that half into both CTAs' shared memory, cutting the L2->SM traffic per CTA from 48 to 32 KiB per
@@ -465,17 +476,20 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int sq = unit0; sq < seq_len; sq += unit_stride) {
         PTK_DECODE_UNIT(sq, tm, ncol0, half)
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], half ? 2 * (P_A_BYTES + P_B_BYTES / 2) : 2 * P_STAGE_BYTES);
-          tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * P_A_BYTES, kb * BLOCK_K,
-                          tm * 2 * BLOCK_M + (int)crank * BLOCK_M);
-          if (half)  // this CTA's 64 of the 128 B rows of a half unit
-            tma_load_2d_2sm(&tmap_bh, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
-                            ncol0 + (int)crank * (BLOCK_N / 4));
-          else
-            tma_load_2d_2sm(&tmap_b, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
-                            ncol0 + (int)crank * (BLOCK_N / 2));
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          for (int t = 6 - p.terms; t < 6; ++t) {   // one ring stage per piece product (a single pass when terms == 1)
+            const int arow = kPieceA[t] * p.a_rows, brow = kPieceB[t] * p.b_rows;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[stage], half ? 2 * (P_A_BYTES + P_B_BYTES / 2) : 2 * P_STAGE_BYTES);
+            tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * P_A_BYTES, kb * BLOCK_K,
+                            arow + tm * 2 * BLOCK_M + (int)crank * BLOCK_M);
+            if (half)  // this CTA's 64 of the 128 B rows of a half unit
+              tma_load_2d_2sm(&tmap_bh, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
+                              brow + ncol0 + (int)crank * (BLOCK_N / 4));
+            else
+              tma_load_2d_2sm(&tmap_b, &full_bar[stage], smem_b + stage * P_B_BYTES, kb * BLOCK_K,
+                              brow + ncol0 + (int)crank * (BLOCK_N / 2));
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -493,7 +507,8 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int n_stages = k_blocks * p.terms;  // piece products of one k-block accumulate into the same tile
+        for (int it = 0; it < n_stages; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
@@ -501,7 +516,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             umma_f16_2sm(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+                         (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free again in BOTH CTAs
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
@@ -631,6 +646,60 @@ __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restri
   }
 }
 
+// ---- fp32 -> 3 x bf16 operand split: piece i of src[r*sr + c*sc] goes to dst[(i * piece_rows + r) * ld + c] ----------------
+// x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2): the residuals are exact in fp32, so x1 + x2 + x3 carries 24
+// mantissa bits of x.  Same 64 x 64 shared-memory tile as convert_bf16_kernel (coalesced reads along either source stride).
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, long long sr, long long sc,
+                                                           __nv_bfloat16* __restrict__ dst, long long ld, long long R,
+                                                           long long Cc, long long piece_rows) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool col_fast = (sc == 1) || (sr != 1);
+  if (col_fast) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + ty + 8 * i, c = c0 + tx + 32 * h;
+        tile[ty + 8 * i][tx + 32 * h] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + tx + 32 * h, c = c0 + ty + 8 * i;
+        tile[tx + 32 * h][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    if (r < R && c < Cc) {
+      float lo = tile[ty + 8 * i][2 * tx], hi = (c + 1 < Cc) ? tile[ty + 8 * i][2 * tx + 1] : 0.0f;
+#pragma unroll
+      for (int pc = 0; pc < 3; ++pc) {
+        const __nv_bfloat16 bl = __float2bfloat16_rn(lo), bh = __float2bfloat16_rn(hi);
+        __nv_bfloat16* d = dst + (pc * piece_rows + r) * ld + c;
+        if (c + 1 < ld) {
+          __nv_bfloat162 pk;
+          pk.x = bl;
+          pk.y = bh;
+          *reinterpret_cast<__nv_bfloat162*>(d) = pk;
+        } else {
+          *d = bl;
+        }
+        lo -= __bfloat162float(bl);
+        hi -= __bfloat162float(bh);
+      }
+    }
+  }
+}
+
 ptk_status make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {pitch_elems * 2};
@@ -651,6 +720,11 @@ namespace ptk {
 size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K) {
   long long Kp = round_up(K, 8);
   return (size_t)(round_up(M * Kp * 2, 256) + round_up(N * Kp * 2, 256) + 256);
+}
+
+size_t gemm_tc_split_workspace(int64_t M, int64_t N, int64_t K) {
+  long long Kp = round_up(K, 8), Mp = round_up(M, 256), Np = round_up(N, 256);
+  return (size_t)(round_up(3 * Mp * Kp * 2, 256) + round_up(3 * Np * Kp * 2, 256) + 256);
 }
 
 static int g_cluster = -1;  // -1: read PTK_GEMM_CLUSTER once (default 2)
@@ -704,6 +778,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     g_split = (e && e[0] == '0') ? 0 : 1;
   }
   p.split_tail = g_split;
+  p.terms = 1; p.a_rows = 0; p.b_rows = 0;
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -738,6 +813,67 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
   return PTK_OK;
 }
 
+// fp32-accurate product on the tensor cores: both operands split into three bf16 pieces, `terms` (3 or 6) piece products
+// per k-block accumulated in fp32 TMEM by the cta_group::2 kernel (see EpiParams::terms).
+ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1, const float* B,
+                         int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1, const float* bias, int act,
+                         int terms, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (M == 0 || N == 0) return PTK_OK;
+  if (terms != 3 && terms != 6) return fail(PTK_ERR_ARG, "gemm_tc_split: terms must be 3 or 6");
+  if (M > 500000000LL || N > 500000000LL || K > 2147483647LL) return fail(PTK_ERR_ARG, "gemm_tc_split: dims exceed int32");
+  if (workspace == nullptr || workspace_bytes < gemm_tc_split_workspace(M, N, K))
+    return fail(PTK_ERR_ARG, "gemm_tc_split: workspace too small (see ptk_gemm_split_workspace_bytes)");
+  const long long Kp = round_up(K, 8), Mp = round_up(M, 256), Np = round_up(N, 256);
+  uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  __nv_bfloat16* Abf = reinterpret_cast<__nv_bfloat16*>(w);
+  __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(w + round_up(3 * Mp * Kp * 2, 256));
+  {
+    dim3 ga((unsigned)((K + 63) / 64), (unsigned)((M + 63) / 64));
+    split_bf16x3_kernel<<<ga, 256, 0, st>>>(A, sa0, sa1, Abf, Kp, M, K, Mp);
+    dim3 gb((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64));
+    split_bf16x3_kernel<<<gb, 256, 0, st>>>(B, sb1, sb0, Bbf, Kp, N, K, Np);  // B[K,N] -> Bt[N,K] pieces
+    PTK_LAUNCH_CHECK("split_bf16x3");
+  }
+  CUtensorMap ta, tb, tbh;
+  ptk_status s;
+  // rows past M (N) inside a piece hold whatever the workspace held: they only reach output rows (columns) the epilogue
+  // masks, never a stored element; columns past K are zero-filled by TMA (the map's extent is K)
+  if ((s = make_tmap(&ta, Abf, (uint64_t)(3 * Mp), (uint64_t)K, (uint64_t)Kp, BLOCK_M)) != PTK_OK) return s;
+  if ((s = make_tmap(&tbh, Bbf, (uint64_t)(3 * Np), (uint64_t)K, (uint64_t)Kp, BLOCK_N / 4)) != PTK_OK) return s;
+  if ((s = make_tmap(&tb, Bbf, (uint64_t)(3 * Np), (uint64_t)K, (uint64_t)Kp, BLOCK_N / 2)) != PTK_OK) return s;
+  EpiParams p;
+  p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.Cbf = nullptr;
+  p.ldcbf = 0;
+  p.split_tail = 1;
+  p.terms = terms; p.a_rows = (int)Mp; p.b_rows = (int)Np;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  const int sms = std::max(2, ptk::sm_count());
+  const int units = ((m_tiles + 1) / 2) * n_tiles;
+  const int grid = 2 * std::max(1, std::min(units, sms / 2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = P_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
+  PTK_LAUNCH_CHECK("gemm_bf16x3_tc");
+  return PTK_OK;
+}
+
 ptk_status gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sa0, int64_t sa1,
                    const float* B, int64_t sb0, int64_t sb1, float beta, float* C, int64_t sc0, int64_t sc1,
                    const float* bias, int act, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -756,4 +892,17 @@ extern "C" ptk_status ptk_gemm_tc_ex(int64_t M, int64_t N, int64_t K, double alp
   return ptk::gemm_tc_ex(M, N, K, (float)alpha, (const float*)A_f32, sa0, sa1, A_bf16, lda_bf16, (const float*)B_f32, sb0, sb1,
                          (float)beta, (float*)C, sc0, sc1, (const float*)bias, act, C_bf16, ldc_bf16, workspace,
                          workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t ptk_gemm_split_workspace_bytes(int64_t M, int64_t N, int64_t K) { return ptk::gemm_tc_split_workspace(M, N, K); }
+
+extern "C" ptk_status ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0,
+                                        int64_t sa1, const void* B_f32, int64_t sb0, int64_t sb1, double beta, void* C,
+                                        int64_t sc0, int64_t sc1, const void* bias, int act, int terms, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (A_f32 == nullptr || B_f32 == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_gemm_tc_split: null operand");
+  return ptk::gemm_tc_split(M, N, K, (float)alpha, (const float*)A_f32, sa0, sa1, (const float*)B_f32, sb0, sb1, (float)beta,
+                            (float*)C, sc0, sc1, (const float*)bias, act, terms, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }

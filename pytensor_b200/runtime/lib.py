@@ -83,6 +83,9 @@ SIGNATURES = {
     "ptk_gemm_tc_ex": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                c_void_p, c_size_t, c_void_p]),
+    "ptk_gemm_split_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "ptk_gemm_tc_split": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                  c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -111,6 +114,8 @@ class _TraceLib:
             return lambda: 148
         if name == "ptk_gemm_workspace_bytes":
             return lambda M, N, K, p: 2 * (M * K + N * K) + 1024
+        if name == "ptk_gemm_split_workspace_bytes":
+            return lambda M, N, K: 6 * ((M + 255) // 256 * 256 + (N + 255) // 256 * 256) * ((K + 7) // 8 * 8) + 1024
         if name == "ptk_put_rows_workspace_bytes":
             return lambda n_dst, n_idx: 4 * (n_dst + 1 + n_idx) + 64
         if name == "ptk_last_error":

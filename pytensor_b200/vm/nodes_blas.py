@@ -13,8 +13,14 @@ from .nodes_basic import _broadcast_view
 from .nodes_elemwise import Node
 from .values import Val
 
-# Linker-level knob: 0 = native fp32/fp64 FMA (<= 1e-5 vs BLAS); 1 = bf16 operands / fp32 TMEM accumulation
+# Linker-level knob: 0 = fp32-accurate (<= 1e-5 vs BLAS); 1 = bf16 operands / fp32 TMEM accumulation
 TC_MIN_DIM = 256
+# How precision 0 multiplies large fp32 matrices: "tc6" / "tc3" = tcgen05 with every operand split into three bf16 pieces
+# and 6 / 3 piece products per k-block (include/ptk.h ptk_gemm_tc_split; 6 terms is more accurate than sgemm itself,
+# 3 terms ~4e-6 of the output scale), "simt" = the fp32 FMA kernel.  fp64 and small / skinny products always take FMA.
+import os as _os
+
+FP32_MODE = _os.environ.get("PTK_GEMM_FP32", "tc6")
 
 _workspace = {"buf": None}
 
@@ -63,6 +69,17 @@ def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None
                                     dev.ptr(cbf) if cbf is not None else None, cbf.stride(0) if cbf is not None else 0,
                                     dev.ptr(ws), ws_bytes, st), "ptk_gemm_tc_ex")
         return cbf
+    if precision == 0 and dtype == "float32" and FP32_MODE in ("tc6", "tc3") and min(M, N, K) >= TC_MIN_DIM:
+        ws_bytes = int(L.ptk_gemm_split_workspace_bytes(M, N, K))
+        if dev.alloc_state.arena is not None or dev.alloc_state.measuring:
+            ws = dev.empty_t((ws_bytes,), torch.uint8)
+        else:
+            ws = _get_workspace(ws_bytes)
+        _lib.check(L.ptk_gemm_tc_split(M, N, K, float(alpha), dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B), B.stride(0),
+                                       B.stride(1), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
+                                       dev.ptr(bias) if bias is not None else None, act, 6 if FP32_MODE == "tc6" else 3,
+                                       dev.ptr(ws), ws_bytes, st), "ptk_gemm_tc_split")
+        return None
     if bias is not None or act:
         _lib.check(L.ptk_gemm_bias_act(code, M, N, K, dev.ptr(A), A.stride(0), A.stride(1), dev.ptr(B), B.stride(0),
                                        B.stride(1), dev.ptr(bias) if bias is not None else None, act, dev.ptr(C),

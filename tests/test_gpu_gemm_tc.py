@@ -71,3 +71,56 @@ def test_mlp_chain_bf16_vs_cvm(gpu):
     # and the native-precision linker meets the 1e-5 class bar on the same graph
     f32 = pytensor.function(ins, outs, mode="CUDA")
     np.testing.assert_allclose(f32(*a)[0], ref, rtol=1e-4, atol=1e-5)
+
+
+# ---- fp32-accurate tensor-core GEMM (bf16x3 operand split, ptk_gemm_tc_split): the DEFAULT mode="CUDA" path for large fp32 ----
+def _scale_err(got, ref):
+    return float(np.abs(np.asarray(got, dtype=np.float64) - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (512, 768, 320), (1000, 520, 264), (2500, 2000, 520), (300, 4096, 4096)])
+def test_dot22_fp32_on_tensor_cores_is_more_accurate_than_1e5(gpu, M, N, K):
+    """6 piece products per k-block: the only dropped products are O(2^-24), so the result must sit within ~1e-6 of the
+    output scale of an fp64 product — tighter than two sgemm implementations agree with each other."""
+    rng = np.random.default_rng(43)
+    x, y = pt.fmatrix("x"), pt.fmatrix("y")
+    f = pytensor.function([x, y], pt.dot(x, y), mode="CUDA")
+    xv = rng.standard_normal((M, K)).astype("float32")
+    yv = rng.standard_normal((K, N)).astype("float32")
+    got = f(xv, yv)
+    ref = xv.astype(np.float64) @ yv.astype(np.float64)
+    assert _scale_err(got, ref) < 2e-6, _scale_err(got, ref)
+    f_ref = pytensor.function([x, y], pt.dot(x, y), mode="CVM")
+    exp = f_ref(xv, yv)
+    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5 * np.abs(exp).max())
+
+
+def test_gemm_fp32_split_alpha_beta_strides_bias_tanh(gpu):
+    rng = np.random.default_rng(44)
+    z, x, y, b = pt.fmatrix("z"), pt.fmatrix("x"), pt.fmatrix("y"), pt.fvector("b")
+    outs = [0.5 * z + 2.0 * pt.dot(x.T, y), pt.tanh(pt.dot(x.T, y) + b), pt.dot(x.T[:, ::2], y[::2])]
+    f = pytensor.function([z, x, y, b], outs, mode="CUDA")
+    f_ref = pytensor.function([z, x, y, b], outs, mode="CVM")
+    xv = (rng.standard_normal((640, 300)) / 16).astype("float32")
+    yv = (rng.standard_normal((640, 260)) / 16).astype("float32")
+    zv = rng.standard_normal((300, 260)).astype("float32")
+    bv = rng.standard_normal(260).astype("float32")
+    for g, e in zip(f(zv, xv, yv, bv), f_ref(zv, xv, yv, bv)):
+        np.testing.assert_allclose(g, e, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(e).max())))
+
+
+def test_three_term_split_meets_the_1e5_bar(gpu, monkeypatch):
+    from pytensor_b200.vm import nodes_blas
+
+    monkeypatch.setattr(nodes_blas, "FP32_MODE", "tc3")
+    rng = np.random.default_rng(45)
+    x, y = pt.fmatrix("x"), pt.fmatrix("y")
+    f = pytensor.function([x, y], pt.dot(x, y), mode="CUDA")
+    xv = rng.standard_normal((512, 4096)).astype("float32")
+    yv = rng.standard_normal((4096, 512)).astype("float32")
+    ref = xv.astype(np.float64) @ yv.astype(np.float64)
+    err = _scale_err(f(xv, yv), ref)
+    assert 1e-8 < err < 1e-5, err
+    monkeypatch.setattr(nodes_blas, "FP32_MODE", "simt")
+    f2 = pytensor.function([x, y], pt.dot(x, y), mode="CUDA")
+    assert _scale_err(f2(xv, yv), ref) < 1e-5
