@@ -67,7 +67,7 @@ class ScalarProgram:
         heavy = {"Exp", "Exp2", "Expm1", "Log", "Log2", "Log10", "Log1p", "Tanh", "Sinh", "Cosh", "Sin", "Cos", "Tan",
                  "Pow", "Sigmoid", "Softplus", "Log1mexp", "Erf", "Erfc", "Erfcx", "Erfinv", "Erfcinv", "Gamma",
                  "GammaLn", "ArcSin", "ArcCos", "ArcTan", "ArcTan2", "ArcSinh", "ArcCosh", "ArcTanh", "J0", "J1",
-                 "I0", "I1", "Psi", "Sqrt", "TrueDiv", "Reciprocal"}
+                 "I0", "I1", "Psi", "TriGamma", "GammaInc", "GammaIncC", "BetaInc", "Sqrt", "TrueDiv", "Reciprocal"}
         return sum(1 for i in self.insts if i.op in heavy)
 
 
@@ -292,6 +292,199 @@ OPS = {
     "Gamma": _unary_libm("tgamma"), "GammaLn": _unary_libm("lgamma"),
     "J0": _unary_libm("j0"), "J1": _unary_libm("j1"),
     "I0": _unary_libm("cyl_bessel_i0"), "I1": _unary_libm("cyl_bessel_i1"),
+    # special functions the reference computes in DOUBLE whatever the graph dtype (scalar/math.py:490 `_psi`, :574
+    # `_tri_gamma`, :648 `GammaP`, :695 `GammaQ`, :1371 `BetaInc`) — device versions in SPECIAL_HELPERS below
+    "Psi": lambda a, it, ot: f"ptk_psi((double)({a[0]}))",
+    "TriGamma": lambda a, it, ot: f"ptk_trigamma((double)({a[0]}))",
+    "GammaInc": lambda a, it, ot: f"ptk_gamma_p((double)({a[0]}), (double)({a[1]}))",
+    "GammaIncC": lambda a, it, ot: f"ptk_gamma_q((double)({a[0]}), (double)({a[1]}))",
+    "BetaInc": lambda a, it, ot: f"ptk_betainc((double)({a[0]}), (double)({a[1]}), (double)({a[2]}))",
+}
+
+# which helper blocks (SPECIAL_HELPERS) an op's expression needs
+NEEDS = {"Psi": ("psi",), "TriGamma": ("trigamma",), "GammaInc": ("gammainc",), "GammaIncC": ("gammainc",),
+         "BetaInc": ("betainc",)}
+
+
+# Device restatements of the reference's double-precision special functions.  Emitted in front of a scalar body only when
+# the body uses them (they are fp64-heavy; keeping them out of every other kernel keeps NVRTC time and register use down).
+SPECIAL_HELPERS = {
+    # Psi: Bernardo's AS 103 exactly as the reference evaluates it (scalar/math.py:441-487): truncated Stirling
+    # coefficients, recurrence up to 8.5, +inf at non-positive integers, reflection psi(x) = psi(1-x) - pi*cot(pi*x).
+    "psi": r"""
+#ifndef PTK_HAVE_PSI
+#define PTK_HAVE_PSI
+__device__ inline double ptk_psi(double x) {
+  double acc = 0.0;
+  if (x <= 0.0) {
+    if (x == floor(x)) return __longlong_as_double(0x7ff0000000000000LL);
+    const double px = 3.14159265358979323846 * x;
+    acc = -3.14159265358979323846 * (cos(px) / sin(px));
+    x = 1.0 - x;
+  }
+  if (x <= 1.0e-5) return (-0.5772156649 - 1.0 / x) + acc;
+  double s = 0.0;
+  while (x < 8.5) { s -= 1.0 / x; x += 1.0; }
+  const double r = 1.0 / x, r2 = r * r;
+  s = s + log(x) - 0.5 * r;
+  s = s - r2 * (8.333333333e-2 - r2 * (8.333333333e-3 - r2 * 3.968253968e-3));
+  return s + acc;
+}
+#endif
+""",
+    # TriGamma: AS 121 as in scalar/math.py:529-566 (0 for x <= 0, 1/x^2 below 1e-4, recurrence up to 5, 4-term asymptote)
+    "trigamma": r"""
+#ifndef PTK_HAVE_TRIGAMMA
+#define PTK_HAVE_TRIGAMMA
+__device__ inline double ptk_trigamma(double x) {
+  if (x <= 0.0) return 0.0;
+  if (x <= 0.0001) return 1.0 / x / x;
+  double v = 0.0;
+  while (x < 5.0) { v += 1.0 / x / x; x += 1.0; }
+  const double y = 1.0 / x / x;
+  return v + (0.5 * y + (1.0 + y * (0.1666666667 + y * (-0.03333333333 + y * (0.02380952381 + y * -0.03333333333)))) / x);
+}
+#endif
+""",
+    # Regularised incomplete gamma P / Q (scalar/c_code/gamma.c:228-254): series for x < a+1, modified-Lentz continued
+    # fraction otherwise, same argument checks and limits; ln Gamma(a) from CUDA's lgamma instead of the table+Lanczos
+    # of gamma.c:83-104 (both are accurate far beyond the 1e-5 bar).
+    "gammainc": r"""
+#ifndef PTK_HAVE_GAMMAINC
+#define PTK_HAVE_GAMMAINC
+__device__ inline double ptk_gamma_series(double a, double x) {
+  double term = 1.0 / a, sum = term;
+  for (int i = 0; i < 1024; ++i) {
+    a += 1.0;
+    term *= x / a;
+    sum += term;
+    if (fabs(term) < fabs(sum) * 2.2204460492503131e-16) break;
+  }
+  return sum;
+}
+__device__ inline double ptk_gamma_cfrac(double a, double x) {
+  const double tiny = 2.2204460492503131e-16 * 2.2204460492503131e-16 * 2.2204460492503131e-16;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, f = d;
+  for (int i = 1; i < 1024; ++i) {
+    const double an = i * (a - i);
+    b += 2.0;
+    d = an * d + b;
+    if (fabs(d) < tiny) d = tiny;
+    c = b + an / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double e = d * c;
+    f *= e;
+    if (fabs(e - 1.0) < 2.2204460492503131e-16) break;
+  }
+  return f;
+}
+// which = 0: P (lower), 1: Q (upper)
+__device__ inline double ptk_gamma_pq(double a, double x, int which) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (a <= 0.0 || x < 0.0) return nan;
+  if (x <= 0.0) return which ? 1.0 : 0.0;
+  if (isinf(a)) return isinf(x) ? nan : (which ? 1.0 : 0.0);
+  if (isinf(x)) return which ? 0.0 : 1.0;
+  const double pref = exp(a * log(x) - x - lgamma(a));
+  if (x < a + 1.0) {
+    const double p = ptk_gamma_series(a, x) * pref;
+    return which ? 1.0 - p : p;
+  }
+  const double q = ptk_gamma_cfrac(a, x) * pref;
+  return which ? q : 1.0 - q;
+}
+__device__ inline double ptk_gamma_p(double a, double x) { return ptk_gamma_pq(a, x, 0); }
+__device__ inline double ptk_gamma_q(double a, double x) { return ptk_gamma_pq(a, x, 1); }
+#endif
+""",
+    # Regularised incomplete beta (scalar/c_code/incbet.c:34-93, Cephes `incbet`): power series when b*x <= 1 and
+    # x <= 0.95; otherwise reflect about the mean, pick one of the two continued fractions by the sign of
+    # x(a+b-2)-(a-1), and scale by x^a (1-x)^b / (a B(a,b)) directly or through logarithms when that would overflow.
+    "betainc": r"""
+#ifndef PTK_HAVE_BETAINC
+#define PTK_HAVE_BETAINC
+__device__ inline double ptk_betainc_pseries(double a, double b, double x) {
+  const double ai = 1.0 / a, eps = 1.11022302462515654042e-16;
+  double u = (1.0 - b) * x, t = u, v = u / (a + 1.0), n = 2.0, s = 0.0;
+  const double first = v, stop = eps * ai;
+  while (fabs(v) > stop) {
+    t *= (n - b) * x / n;
+    v = t / (a + n);
+    s += v;
+    n += 1.0;
+  }
+  s += first;
+  s += ai;
+  const double lx = a * log(x);
+  if (a + b < 171.624376956302725 && fabs(lx) < 7.09782712893383996732e2)
+    return s * (tgamma(a + b) / (tgamma(a) * tgamma(b))) * pow(x, a);
+  const double lt = lgamma(a + b) - lgamma(a) - lgamma(b) + lx + log(s);
+  return lt < -7.451332191019412076235e2 ? 0.0 : exp(lt);
+}
+// Forward evaluation of a continued fraction 1/(1+ d1/(1+ d2/(1+ ...))) whose partial numerators come in (odd, even)
+// pairs; `second` selects the expansion in z = x/(1-x).  Numerators and denominators are rescaled by 2^+-52 when they
+// leave [2^-52, 2^52], as Cephes does, so that neither over- nor underflows.
+__device__ inline double ptk_betainc_cf(double a, double b, double x, int second) {
+  const double big = 4.503599627370496e15, biginv = 2.22044604925031308085e-16, thresh = 3.0 * 1.11022302462515654042e-16;
+  const double z = second ? x / (1.0 - x) : x;
+  double k1 = a, k2 = second ? b - 1.0 : a + b, k3 = a, k4 = a + 1.0;
+  double k5 = 1.0, k6 = second ? a + b : b - 1.0, k7 = a + 1.0, k8 = a + 2.0;
+  const double s2 = second ? -1.0 : 1.0, s6 = second ? 1.0 : -1.0;
+  double pm2 = 0.0, qm2 = 1.0, pm1 = 1.0, qm1 = 1.0, ans = 1.0, r = 1.0;
+  for (int n = 0; n < 300; ++n) {
+    double d = -(z * k1 * k2) / (k3 * k4);
+    double pk = pm1 + pm2 * d, qk = qm1 + qm2 * d;
+    pm2 = pm1; pm1 = pk; qm2 = qm1; qm1 = qk;
+    d = (z * k5 * k6) / (k7 * k8);
+    pk = pm1 + pm2 * d; qk = qm1 + qm2 * d;
+    pm2 = pm1; pm1 = pk; qm2 = qm1; qm1 = qk;
+    if (qk != 0.0) r = pk / qk;
+    double t = 1.0;
+    if (r != 0.0) { t = fabs((ans - r) / r); ans = r; }
+    if (t < thresh) break;
+    k1 += 1.0; k2 += s2; k3 += 2.0; k4 += 2.0; k5 += 1.0; k6 += s6; k7 += 2.0; k8 += 2.0;
+    if (fabs(qk) + fabs(pk) > big) { pm2 *= biginv; pm1 *= biginv; qm2 *= biginv; qm1 *= biginv; }
+    if (fabs(qk) < biginv || fabs(pk) < biginv) { pm2 *= big; pm1 *= big; qm2 *= big; qm1 *= big; }
+  }
+  return ans;
+}
+__device__ inline double ptk_betainc(double a, double b, double x) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL), eps = 1.11022302462515654042e-16;
+  if (a <= 0.0 || b <= 0.0 || x < 0.0 || 1.0 < x) return nan;
+  if (x == 0.0) return 0.0;
+  if (x == 1.0) return 1.0;
+  if (b * x <= 1.0 && x <= 0.95) return ptk_betainc_pseries(a, b, x);
+  // at most one reflection: after swapping, x' = 1-x <= b/(a+b) = the new mean, so the second pass never reflects
+  bool flipped = false;
+  double xc = 1.0 - x;
+  if (x > a / (a + b)) {
+    flipped = true;
+    const double t0 = a; a = b; b = t0;
+    const double t1 = x; x = xc; xc = t1;
+    if (b * x <= 1.0 && x <= 0.95) {
+      const double t = ptk_betainc_pseries(a, b, x);
+      return t <= eps ? 1.0 - eps : 1.0 - t;
+    }
+  }
+  const double w = (x * (a + b - 2.0) - (a - 1.0) < 0.0) ? ptk_betainc_cf(a, b, x, 0) : ptk_betainc_cf(a, b, x, 1) / xc;
+  double y = a * log(x), t = b * log(xc);
+  if (a + b < 171.624376956302725 && fabs(y) < 7.09782712893383996732e2 && fabs(t) < 7.09782712893383996732e2) {
+    t = pow(xc, b);
+    t *= pow(x, a);
+    t /= a;
+    t *= w;
+    t *= tgamma(a + b) / (tgamma(a) * tgamma(b));
+  } else {
+    y += t + lgamma(a + b) - lgamma(a) - lgamma(b);
+    y += log(w / a);
+    t = y < -7.451332191019412076235e2 ? 0.0 : exp(y);
+  }
+  if (flipped) return t <= eps ? 1.0 - eps : 1.0 - t;
+  return t;
+}
+#endif
+""",
 }
 
 PRELUDE = r"""
@@ -337,7 +530,13 @@ def emit_body(prog: ScalarProgram, fn_name: str = "ptk_body") -> str:
             raise UnsupportedScalarOp(f"dtype {d} has no device path (the reference's C linker has none for float16/complex either)")
     params = [f"const {CTYPE[d]} i{k}" for k, d in enumerate(prog.in_dtypes)]
     params += [f"{CTYPE[d]}& o{k}" for k, d in enumerate(prog.out_dtypes)]
-    lines = [f"__device__ __forceinline__ void {fn_name}({', '.join(params)}) {{"]
+    need = []
+    for inst in prog.insts:
+        for h in NEEDS.get(inst.op, ()):
+            if h not in need:
+                need.append(h)
+    lines = [SPECIAL_HELPERS[h] for h in need]
+    lines.append(f"__device__ __forceinline__ void {fn_name}({', '.join(params)}) {{")
     for k, inst in enumerate(prog.insts):
         fn = OPS.get(inst.op)
         if fn is None:

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 if [ "${TESTS:-1}" = "1" ]; then
-( time timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -q -m gpu --timeout 300 -x ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
+( time timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -q -m gpu --timeout 300 --maxfail=40 ${PYTEST_ARGS:-} ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
 fi

@@ -129,6 +129,37 @@ def test_binary_float_ops_nan_propagation_and_python_modulo(tmp_path, dtype):
     _check(got, ref, rtol=2e-6 if dtype == "float32" else 1e-13, atol=2e-6 if dtype == "float32" else 1e-14)
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_special_functions_psi_trigamma_gammainc_betainc(tmp_path, dtype):
+    """Psi / TriGamma / GammaInc / GammaIncC / BetaInc (scalar/math.py:403,502,627,674,1342) — the device restatements
+    in codegen/scalar.py::SPECIAL_HELPERS, compiled for the host, against the reference's own C (gamma.c, incbet.c) over
+    the regimes each algorithm switches between, plus the argument checks and limits the reference's tests pin
+    (tests/scalar/test_math.py:34-80: nan and inf arguments)."""
+    pytensor.config.floatX = dtype
+    rng = np.random.default_rng(21)
+    n = 4000
+    x = pt.vector("x", dtype=dtype)
+    xv = np.concatenate([rng.uniform(-30, 60, n - 16), [0.0, -1.0, -2.0, -0.5, -1.5, 1e-6, 1e-5, 9e-5, 1e-4, 8.5, 5.0, 1.0,
+                                                       0.5, 100.0, 1e4, -1e-3]]).astype(dtype)
+    got, ref = _emulate([x], [pt.psi(x), pt.tri_gamma(x)], [xv], tmp_path)
+    _check(got, ref, rtol=1e-5 if dtype == "float32" else 1e-9, atol=1e-6 if dtype == "float32" else 1e-12)
+
+    k, y = pt.vector("k", dtype=dtype), pt.vector("y", dtype=dtype)
+    kv = np.concatenate([rng.uniform(0.05, 40, n - 12), [1, 1, np.inf, 1, np.inf, -1, 1, 0.5, 170, 171.5, 300, 1e-3]]).astype(dtype)
+    yv = np.concatenate([rng.uniform(0, 80, n - 12), [2, np.inf, 1, np.nan, np.inf, 1, -1, 0, 160, 180, 310, 1e-3]]).astype(dtype)
+    (tmp_path / "g").mkdir()  # a fresh directory per graph: dlopen caches handles by path
+    got, ref = _emulate([k, y], [pt.gammainc(k, y), pt.gammaincc(k, y)], [kv, yv], tmp_path / "g")
+    _check(got, ref, rtol=1e-5 if dtype == "float32" else 1e-9, atol=1e-7 if dtype == "float32" else 1e-13)
+
+    a, b, z = pt.vector("a", dtype=dtype), pt.vector("b", dtype=dtype), pt.vector("z", dtype=dtype)
+    av = np.concatenate([rng.uniform(0.05, 30, n - 10), [1, 2, 0.5, 100, 200, 1e-2, 5, -1, 3, 3]]).astype(dtype)
+    bv = np.concatenate([rng.uniform(0.05, 30, n - 10), [1, 3, 0.5, 100, 150, 50, 1e-2, 2, -2, 3]]).astype(dtype)
+    zv = np.concatenate([rng.uniform(0, 1, n - 10), [0.3, 0.0, 1.0, 0.5, 0.6, 0.01, 0.99, 0.5, 0.5, 1.5]]).astype(dtype)
+    (tmp_path / "b").mkdir()
+    got, ref = _emulate([a, b, z], [pt.betainc(a, b, z)], [av, bv, zv], tmp_path / "b")
+    _check(got, ref, rtol=1e-5 if dtype == "float32" else 1e-9, atol=1e-7 if dtype == "float32" else 1e-13)
+
+
 @pytest.mark.parametrize("dtype", ["int8", "int32", "int64", "uint8", "uint32"])
 def test_integer_ops_floor_division_modulo_bitwise_and_true_division(tmp_path, dtype):
     pytensor.config.floatX = "float64"
