@@ -111,6 +111,15 @@ ptk_status   ptk_put_rows(void* dst, const void* y, const int64_t* idx, int64_t 
 ptk_status   ptk_linearize_index(int k, const void* const* idx, const int64_t* dims, int64_t n, int64_t* out,
                                  int* err_flag, void* stream);
 
+/* Boolean-mask indexing (AdvancedSubtensor / AdvancedIncSubtensor with a bool index, tensor/subtensor.py:2026-2051: the
+ * reference turns the mask into `mask.nonzero()` and lets NumPy index): ascending flat positions of the non-zero bytes
+ * of a contiguous mask of n bytes.  ptk_nonzero_count leaves the per-tile exclusive offsets in `workspace`
+ * (ptk_nonzero_workspace_bytes(n) bytes, int64) with the TOTAL in its last int64 — the caller reads that one number back
+ * (the output shape is data dependent), allocates `out[total]` and calls ptk_nonzero_fill with the same workspace. */
+size_t       ptk_nonzero_workspace_bytes(int64_t n);
+ptk_status   ptk_nonzero_count(const void* mask, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+ptk_status   ptk_nonzero_fill(const void* mask, int64_t n, const void* workspace, int64_t* out, void* stream);
+
 /* ---- more glue of the Op library ------------------------------------------------------------
  * ARange (tensor/basic.py:3139; perform = np.arange): out[i] = first + i*delta evaluated in the output type like NumPy's
  * <type>_fill loops (first/delta = the first element and the difference of the first two, computed by the caller);
@@ -164,6 +173,25 @@ size_t       ptk_gemm_split_workspace_bytes(int64_t M, int64_t N, int64_t K);
 ptk_status   ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double alpha, const void* A_f32, int64_t sa0, int64_t sa1,
                       const void* B_f32, int64_t sb0, int64_t sb1, double beta, void* C, int64_t sc0, int64_t sc1,
                       const void* bias, int act, int terms, void* workspace, size_t workspace_bytes, void* stream);
+/* Operands staged ONCE, products chained: the two halves of ptk_gemm_tc_ex / ptk_gemm_tc_split as separate entry points,
+ * for operands that do not change between calls (graph constants, shared weights, the non-sequences of a Scan — the C
+ * linker's sgemm_ has no such state: every call of pytensor/tensor/blas/c_code/codegen.py:463-540 reads fp32 operands) and for
+ * recurrences h <- act(h @ W + b) (Scan inner graphs, scan/scan_perform.pyx:311-541) where the epilogue of step t writes
+ * the staged A operand of step t+1.
+ *   ptk_stage_operand: dst = `pieces` (1 = bf16 | 3 = x1+x2+x3 split) matrices [rows, cols] from fp32 src[r*sr + c*sc],
+ *     row pitch ld (multiple of 8, >= cols), piece i at rows [i*piece_rows, ...); dst >= ptk_stage_bytes(rows, cols, pieces)
+ *     with ld = round_up(cols, 8), piece_rows = round_up(rows, 256).  For the B operand of C = A @ B stage B^T:
+ *     rows = N, cols = K, sr = B's column stride, sc = B's row stride.
+ *   ptk_gemm_tc_staged: C = act(alpha * A @ B + beta * C + bias[N]) from staged A [M,K] / B^T [N,K]; terms 1 (bf16
+ *     operands) | 3 | 6 (fp32-accurate, see ptk_gemm_tc_split; 3 and 6 need 3-piece operands).  C_stage (optional) receives
+ *     out_pieces (1 | 3) staged pieces of the result [M,N] (pitch ldc_stage, piece pitch c_rows). */
+size_t       ptk_stage_bytes(int64_t rows, int64_t cols, int pieces);
+ptk_status   ptk_stage_operand(const void* src_f32, int64_t sr, int64_t sc, int64_t rows, int64_t cols, int pieces,
+                      void* dst, int64_t ld, int64_t piece_rows, void* stream);
+ptk_status   ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double alpha, const void* A_stage, int64_t lda, int64_t a_rows,
+                      const void* B_stage, int64_t ldb, int64_t b_rows, int terms, double beta, void* C, int64_t sc0,
+                      int64_t sc1, const void* bias, int act, void* C_stage, int64_t ldc_stage, int64_t c_rows,
+                      int out_pieces, void* stream);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

@@ -160,6 +160,8 @@ struct EpiParams {
   int M, N, K;
   __nv_bfloat16* Cbf;  // optional bf16 copy of the result, row-major [M, ldcbf] (the next layer's K-major A operand)
   long long ldcbf;
+  int out_pieces;      // pair kernel: 1 = Cbf is a plain bf16 copy; 3 = the three-piece split of the result (piece i at rows
+  long long cbf_rows;  // [i * cbf_rows, ...) of Cbf) — the staged A operand of a following fp32-accurate product
   int split_tail;      // pair kernel: split the units of the last partial round into 256 x 128 halves (PTK_GEMM_SPLIT=0: off)
   // fp32-accurate mode (pair kernel): every fp32 operand is staged as THREE bf16 pieces x = x1 + x2 + x3 (8 mantissa bits
   // each) stacked along the rows of the staging matrix (piece i of A at rows [i * a_rows, ...)); per k-block the kernel
@@ -169,6 +171,13 @@ struct EpiParams {
   //   terms = 1: plain bf16 operands (the CUDA_BF16 mode)
   int terms;
   int a_rows, b_rows;  // row pitch between the stacked pieces
+  // pair kernel: k-blocks per ACCUMULATION CHUNK (0 = the whole K in one chunk).  The tensor core adds into its fp32
+  // accumulator with truncation, a bias that grows linearly with the length of the accumulation chain (measured: ~6e-9 x K
+  // of the output scale, 2.4e-5 at K = 4096 — more than the whole 1e-5 budget of the fp32-accurate mode).  With chunks the
+  // TMEM accumulator only ever holds the sum over `kchunk` k-blocks; the epilogue adds every chunk into C in global memory
+  // with round-to-nearest fp32 adds (the same thread owns the same elements for all chunks of a tile, so the
+  // read-modify-write needs no synchronisation) and applies bias / activation / the bf16 copy after the last chunk.
+  int kchunk;
 };
 // piece indices of the term sequence; a run of `terms` entries ending at index 5 is used
 __device__ __constant__ int kPieceA[6] = {2, 1, 0, 1, 0, 0};
@@ -365,7 +374,9 @@ constexpr int P_STAGES = 6;
 constexpr uint32_t P_A_BYTES = BLOCK_M * BLOCK_K * 2;         // 16 KiB: this CTA's 128 rows of A
 constexpr uint32_t P_B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;   // 16 KiB: this CTA's half of the B tile
 constexpr uint32_t P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;     // 32 KiB
-constexpr uint32_t P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+constexpr int EPI_PITCH = 36;                                  // floats per staged row: 16-byte aligned, conflict-free
+constexpr uint32_t P_EPI_BYTES = 4 * 32 * EPI_PITCH * 4;       // one 32 x 32 fp32 transposition tile per epilogue warp
+constexpr uint32_t P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256 + P_EPI_BYTES;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                // shared::cluster address of the same offset in CTA rank 0
 
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* smem_dst, int32_t c0, int32_t c1) {
@@ -415,6 +426,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full = bars + 2 * P_STAGES;             // [ACC_STAGES] (one per CTA)
   uint64_t* tmem_empty = bars + 2 * P_STAGES + ACC_STAGES;  // [ACC_STAGES] (leader only; 8 arrivals = 4 warps x 2 CTAs)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 2 * ACC_STAGES);
+  float* epi_tiles = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -423,6 +435,8 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_units = m_tiles * n_tiles;
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kchunk = (p.kchunk > 0 && p.kchunk < k_blocks) ? p.kchunk : max(k_blocks, 1);
+  const int n_chunks = max(1, (k_blocks + kchunk - 1) / kchunk);
   const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
   // Wave-quantisation fix: the units of the last, partially filled round are split into two 256 x 128 HALF units when
   // that fills the idle CTA pairs (e.g. 4096^2: 256 units on 74 pairs = 3 full rounds + 34 -> 68 half units, 3.5 rounds
@@ -504,25 +518,28 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t acc_phase = 0;
       for (int sq = unit0; sq < seq_len; sq += unit_stride) {
         const uint32_t idesc = (sq >= full_units) ? idesc_half : idesc_full;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
-        const int n_stages = k_blocks * p.terms;  // piece products of one k-block accumulate into the same tile
-        for (int it = 0; it < n_stages; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int ch = 0; ch < n_chunks; ++ch) {   // one TMEM accumulator per accumulation chunk (EpiParams::kchunk)
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * P_B_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+          const int kb_n = min(kchunk, k_blocks - ch * kchunk);
+          const int n_stages = kb_n * p.terms;  // piece products of one k-block accumulate into the same tile
+          for (int it = 0; it < n_stages; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
+            const uint32_t b_addr = smem_u32(smem_b + stage * P_B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16_2sm(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
-                         (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_f16_2sm(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                           (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free again in BOTH CTAs
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free again in BOTH CTAs
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);      // accumulator complete in both CTAs' TMEM
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);      // accumulator complete in both CTAs' TMEM
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -533,62 +550,108 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int sq = unit0; sq < seq_len; sq += unit_stride) {
       PTK_DECODE_UNIT(sq, tm, ncol0, half)
       const int ncols = half ? BLOCK_N / 2 : BLOCK_N;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const long long row = (long long)tm * 2 * BLOCK_M + (long long)crank * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       float* crow = p.C + row * p.sc0;
+      const bool vec_ok = p.sc1 == 1 && (p.sc0 & 3) == 0 && (((uintptr_t)p.C) & 15) == 0 &&
+                          (p.Cbf == nullptr || ((p.ldcbf & 3) == 0 && (((uintptr_t)p.Cbf) & 7) == 0));
 #pragma unroll 1
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        const long long col0 = (long long)ncol0 + c0;
-        if (row_ok && col0 < p.N) {
-          const bool full = (col0 + 32 <= p.N);
-          if (full && p.sc1 == 1 && p.beta == 0.0f && ((((uintptr_t)(crow + col0)) & 15) == 0)) {
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        // chunk 0 combines with the caller's C (beta), later chunks add onto the partial sum this thread stored before;
+        // bias / activation / the bf16 copy belong to the completed sum
+        const float beta = ch == 0 ? p.beta : 1.0f;
+        const bool last = ch == n_chunks - 1;
+        const float* bias = last ? p.bias : nullptr;
+        const int act = last ? p.act : 0;
+        __nv_bfloat16* cbf = last ? p.Cbf : nullptr;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
+          const long long col0 = (long long)ncol0 + c0;
+          // Row-contiguous fast path (warp-uniform): tcgen05.ld hands every lane one ROW of the 32 x 32 block; going through
+          // a shared-memory tile turns that into 128 contiguous bytes of one row per quarter warp, so every global
+          // load / store instruction of the warp covers 4 full 128-byte lines (the read-modify-write of the accumulation
+          // chunks and the bf16 / three-piece operand copies move whole sectors instead of 16-byte shards of 32 lines).
+          if (vec_ok && col0 + 32 <= p.N) {
+            float* tile = epi_tiles + (warp - 4) * (32 * EPI_PITCH);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              float* vv = reinterpret_cast<float*>(&v);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(tile + lane * EPI_PITCH + j) =
+                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            __syncwarp();
+            const int sub = lane >> 3, cq = (lane & 7) * 4;
+            const long long colv = col0 + cq;
+            float bb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (bias) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x = p.alpha * __uint_as_float(r[j + e]);
-                if (p.bias) x += p.bias[col0 + j + e];
-                if (p.act == 1) x = tanhf(x);
-                vv[e] = x;
-              }
-              *reinterpret_cast<float4*>(crow + col0 + j) = v;
-              if (p.Cbf) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(p.Cbf + row * p.ldcbf + col0 + j) = pk;
+              for (int e = 0; e < 4; ++e) bb[e] = bias[colv + e];
+            }
+            const long long row_base = (long long)tm * 2 * BLOCK_M + (long long)crank * BLOCK_M + q * 32;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 4) {
+              const long long grow = row_base + rr + sub;
+              if (grow < p.M) {
+                float4 v = *reinterpret_cast<const float4*>(tile + (rr + sub) * EPI_PITCH + cq);
+                float* dst = p.C + grow * p.sc0 + colv;
+                float vv[4] = {p.alpha * v.x, p.alpha * v.y, p.alpha * v.z, p.alpha * v.w};
+                if (beta != 0.0f) {
+                  const float4 o = *reinterpret_cast<const float4*>(dst);
+                  vv[0] += beta * o.x; vv[1] += beta * o.y; vv[2] += beta * o.z; vv[3] += beta * o.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  vv[e] += bb[e];
+                  if (act == 1) vv[e] = tanhf(vv[e]);
+                }
+                *reinterpret_cast<float4*>(dst) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                if (cbf) {
+                  for (int pc = 0; pc < p.out_pieces; ++pc) {   // piece pc = bf16 of what the earlier pieces left over
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(cbf + ((long long)pc * p.cbf_rows + grow) * p.ldcbf + colv) = pk;
+                    vv[0] -= __bfloat162float(lo.x); vv[1] -= __bfloat162float(lo.y);
+                    vv[2] -= __bfloat162float(hi.x); vv[3] -= __bfloat162float(hi.y);
+                  }
+                }
               }
             }
-          } else {
+            __syncwarp();
+          } else if (row_ok && col0 < p.N) {
+            {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long col = col0 + j;
-              if (col < p.N) {
-                float* dst = crow + col * p.sc1;
-                float x = p.alpha * __uint_as_float(r[j]);
-                if (p.beta != 0.0f) x += p.beta * (*dst);
-                if (p.bias) x += p.bias[col];
-                if (p.act == 1) x = tanhf(x);
-                *dst = x;
-                if (p.Cbf) p.Cbf[row * p.ldcbf + col] = __float2bfloat16_rn(x);
+              for (int j = 0; j < 32; ++j) {
+                const long long col = col0 + j;
+                if (col < p.N) {
+                  float* dst = crow + col * p.sc1;
+                  float x = p.alpha * __uint_as_float(r[j]);
+                  if (beta != 0.0f) x += beta * (*dst);
+                  if (bias) x += bias[col];
+                  if (act == 1) x = tanhf(x);
+                  *dst = x;
+                  if (cbf) {
+                    for (int pc = 0; pc < p.out_pieces; ++pc) {
+                      const __nv_bfloat16 b = __float2bfloat16_rn(x);
+                      cbf[((long long)pc * p.cbf_rows + row) * p.ldcbf + col] = b;
+                      x -= __bfloat162float(b);
+                    }
+                  }
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);  // 8 arrivals (4 warps x 2 CTAs) free the accumulator
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);  // 8 arrivals (4 warps x 2 CTAs) free the accumulator
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 #undef PTK_DECODE_UNIT
@@ -778,7 +841,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     g_split = (e && e[0] == '0') ? 0 : 1;
   }
   p.split_tail = g_split;
-  p.terms = 1; p.a_rows = 0; p.b_rows = 0;
+  p.terms = 1; p.a_rows = 0; p.b_rows = 0; p.kchunk = 0; p.out_pieces = 1; p.cbf_rows = 0;
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -810,6 +873,91 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     gemm_bf16_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
   }
   PTK_LAUNCH_CHECK("gemm_bf16_tc");
+  return PTK_OK;
+}
+
+// accumulation chunk of the fp32-accurate modes: 8 k-blocks (K = 512) keeps the tensor core's truncation bias near 1e-6 of
+// the output scale; PTK_GEMM_KCHUNK=<k-blocks> overrides (0 = one chunk)
+static int split_kchunk(int64_t K) {
+  static int g_kchunk = -1;
+  if (g_kchunk < 0) {
+    const char* e = getenv("PTK_GEMM_KCHUNK");
+    g_kchunk = e ? atoi(e) : 8;
+    if (g_kchunk < 0) g_kchunk = 8;
+  }
+  const long long kb = (K + BLOCK_K - 1) / BLOCK_K;
+  return (g_kchunk > 0 && kb > g_kchunk + g_kchunk / 4) ? g_kchunk : 0;
+}
+
+// Operand staging on its own (so that an operand that does not change between calls is staged ONCE): dst = `pieces` (1 | 3)
+// bf16 matrices [R, Cc] stacked with a pitch of piece_rows rows, row pitch ld elements, from fp32 src[r*sr + c*sc].
+ptk_status stage_operand(const float* src, int64_t sr, int64_t sc, int64_t R, int64_t Cc, int pieces, void* dst, int64_t ld,
+                         int64_t piece_rows, cudaStream_t st) {
+  if (pieces != 1 && pieces != 3) return fail(PTK_ERR_ARG, "stage_operand: pieces must be 1 or 3");
+  if (ld % 8 != 0 || ld < Cc || ((uintptr_t)dst & 15) != 0) return fail(PTK_ERR_ARG, "stage_operand: pitch must be a multiple of 8 >= cols, base 16-byte aligned");
+  if (R == 0 || Cc == 0) return PTK_OK;
+  dim3 g((unsigned)((Cc + 63) / 64), (unsigned)((R + 63) / 64));
+  if (pieces == 1) convert_bf16_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc);
+  else split_bf16x3_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows);
+  PTK_LAUNCH_CHECK("stage_operand");
+  return PTK_OK;
+}
+
+// The cta_group::2 kernel over operands that are ALREADY staged (see stage_operand): A_stage = pieces of A [M,K] (K-major,
+// pitch lda, piece pitch a_rows rows), B_stage = pieces of B^T [N,K]; terms 1 (plain bf16) | 3 | 6.  C_stage (optional)
+// receives `out_pieces` (1 | 3) staged pieces of the RESULT [M,N] (pitch ldc_stage, piece pitch c_rows) — the A operand
+// of the next product of a chain / recurrence, so that only the very first operand is ever staged by a separate pass.
+ptk_status gemm_tc_staged(int64_t M, int64_t N, int64_t K, float alpha, const void* A_stage, int64_t lda, int64_t a_rows,
+                          const void* B_stage, int64_t ldb, int64_t b_rows, int terms, float beta, float* C, int64_t sc0,
+                          int64_t sc1, const float* bias, int act, void* C_stage, int64_t ldc_stage, int64_t c_rows,
+                          int out_pieces, cudaStream_t st) {
+  if (M == 0 || N == 0) return PTK_OK;
+  if (terms != 1 && terms != 3 && terms != 6) return fail(PTK_ERR_ARG, "gemm_tc_staged: terms must be 1, 3 or 6");
+  if (M > 500000000LL || N > 500000000LL || K > 2147483647LL || K <= 0) return fail(PTK_ERR_ARG, "gemm_tc_staged: bad dims");
+  if (lda % 8 || ldb % 8 || ((uintptr_t)A_stage & 15) || ((uintptr_t)B_stage & 15))
+    return fail(PTK_ERR_ARG, "gemm_tc_staged: operand pitch must be a multiple of 8 elements, base 16-byte aligned");
+  if (C_stage != nullptr && (out_pieces != 1 && out_pieces != 3)) return fail(PTK_ERR_ARG, "gemm_tc_staged: out_pieces must be 1 or 3");
+  if (C_stage != nullptr && (ldc_stage % 8 || ((uintptr_t)C_stage & 15))) return fail(PTK_ERR_ARG, "gemm_tc_staged: misaligned C_stage");
+  const int pa = terms == 1 ? 1 : 3;
+  CUtensorMap ta, tb, tbh;
+  ptk_status s;
+  const uint64_t a_total = (uint64_t)((pa - 1) * a_rows + M), b_total = (uint64_t)((pa - 1) * b_rows + N);
+  if ((s = make_tmap(&ta, A_stage, a_total, (uint64_t)K, (uint64_t)lda, BLOCK_M)) != PTK_OK) return s;
+  if ((s = make_tmap(&tbh, B_stage, b_total, (uint64_t)K, (uint64_t)ldb, BLOCK_N / 4)) != PTK_OK) return s;
+  if ((s = make_tmap(&tb, B_stage, b_total, (uint64_t)K, (uint64_t)ldb, BLOCK_N / 2)) != PTK_OK) return s;
+  EpiParams p;
+  p.alpha = alpha; p.beta = beta; p.C = C; p.sc0 = sc0; p.sc1 = sc1; p.bias = bias; p.act = act;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.Cbf = reinterpret_cast<__nv_bfloat16*>(C_stage);
+  p.ldcbf = ldc_stage;
+  p.out_pieces = C_stage ? out_pieces : 1;
+  p.cbf_rows = c_rows;
+  p.split_tail = 1;
+  p.terms = terms; p.a_rows = terms == 1 ? 0 : (int)a_rows; p.b_rows = terms == 1 ? 0 : (int)b_rows;
+  p.kchunk = terms == 1 ? 0 : split_kchunk(K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  const int sms = std::max(2, ptk::sm_count());
+  const int units = ((m_tiles + 1) / 2) * n_tiles;
+  const int grid = 2 * std::max(1, std::min(units, sms / 2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = P_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
+  PTK_LAUNCH_CHECK("gemm_tc_staged");
   return PTK_OK;
 }
 
@@ -846,8 +994,10 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Cbf = nullptr;
   p.ldcbf = 0;
+  p.out_pieces = 1; p.cbf_rows = 0;
   p.split_tail = 1;
   p.terms = terms; p.a_rows = (int)Mp; p.b_rows = (int)Np;
+  p.kchunk = split_kchunk(K);
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
@@ -905,4 +1055,26 @@ extern "C" ptk_status ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double 
   return ptk::gemm_tc_split(M, N, K, (float)alpha, (const float*)A_f32, sa0, sa1, (const float*)B_f32, sb0, sb1, (float)beta,
                             (float*)C, sc0, sc1, (const float*)bias, act, terms, workspace, workspace_bytes,
                             (cudaStream_t)stream);
+}
+
+extern "C" size_t ptk_stage_bytes(int64_t rows, int64_t cols, int pieces) {
+  const long long ld = (cols + 7) / 8 * 8, pr = (rows + 255) / 256 * 256;
+  return (size_t)(pieces <= 1 ? rows : 3 * pr) * (size_t)ld * 2 + 256;
+}
+
+extern "C" ptk_status ptk_stage_operand(const void* src_f32, int64_t sr, int64_t sc, int64_t rows, int64_t cols, int pieces,
+                                        void* dst, int64_t ld, int64_t piece_rows, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (src_f32 == nullptr || dst == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_stage_operand: null pointer");
+  return ptk::stage_operand((const float*)src_f32, sr, sc, rows, cols, pieces, dst, ld, piece_rows, (cudaStream_t)stream);
+}
+
+extern "C" ptk_status ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double alpha, const void* A_stage, int64_t lda,
+                                         int64_t a_rows, const void* B_stage, int64_t ldb, int64_t b_rows, int terms,
+                                         double beta, void* C, int64_t sc0, int64_t sc1, const void* bias, int act,
+                                         void* C_stage, int64_t ldc_stage, int64_t c_rows, int out_pieces, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (A_stage == nullptr || B_stage == nullptr || C == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_gemm_tc_staged: null operand");
+  return ptk::gemm_tc_staged(M, N, K, (float)alpha, A_stage, lda, a_rows, B_stage, ldb, b_rows, terms, (float)beta, (float*)C,
+                             sc0, sc1, (const float*)bias, act, C_stage, ldc_stage, c_rows, out_pieces, (cudaStream_t)stream);
 }

@@ -211,6 +211,118 @@ __global__ void linearize_index_kernel(LinIdxArgs a, int64_t n, int64_t* __restr
   }
 }
 
+
+// ---- Nonzero (boolean-mask indexing): ascending flat positions of the set bytes of a mask -------------------------------
+// Three passes over NZ_TILE-byte tiles: per-tile counts (16-byte loads, popcount of the "byte != 0" bits), an exclusive scan
+// of the tile counts by one CTA (total appended), and an ordered per-tile compaction (warp ballots keep positions ascending).
+constexpr int NZ_THREADS = 256;
+constexpr int NZ_TILE = NZ_THREADS * 16;  // bytes of mask per tile
+
+__device__ __forceinline__ int nz_count16(const uint8_t* __restrict__ m, int64_t base, int64_t n) {
+  int c = 0;
+  if (base + 16 <= n && ((reinterpret_cast<uintptr_t>(m + base) & 15) == 0)) {
+    const uint4 v = *reinterpret_cast<const uint4*>(m + base);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // a byte is "set" when any of its bits is: fold each byte's bits into its lowest bit, then count
+      unsigned t = w[j];
+      t |= t >> 4; t |= t >> 2; t |= t >> 1;
+      c += __popc(t & 0x01010101u);
+    }
+  } else {
+    for (int j = 0; j < 16; ++j)
+      if (base + j < n && m[base + j]) ++c;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(NZ_THREADS) nonzero_count_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                    int64_t* __restrict__ tile_count, int64_t tiles) {
+  __shared__ int s_part[NZ_THREADS / 32];
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int c = nz_count16(mask, tile * NZ_TILE + (int64_t)threadIdx.x * 16, n);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < NZ_THREADS / 32; ++w) t += s_part[w];
+      tile_count[tile] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// in place: tile_count[i] <- sum of tile_count[0..i) ; tile_count[tiles] <- total
+__global__ void __launch_bounds__(1024) nonzero_scan_kernel(int64_t* __restrict__ tile_count, int64_t tiles) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < tiles; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int64_t v = i < tiles ? tile_count[i] : 0;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = s_warp[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t u = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += u;
+      }
+      s_warp[lane] = winc - w;  // exclusive offset of each warp
+    }
+    __syncthreads();
+    const int64_t carry = s_carry;
+    if (i < tiles) tile_count[i] = carry + s_warp[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_count[tiles] = s_carry;
+}
+
+__global__ void __launch_bounds__(NZ_THREADS) nonzero_fill_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                   const int64_t* __restrict__ tile_offset, int64_t tiles,
+                                                                   int64_t* __restrict__ out) {
+  __shared__ int s_part[NZ_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // thread t owns bytes [16 t, 16 t + 16) of the tile: count, exclusive scan over the CTA, then write in order
+    const int64_t base = tile * NZ_TILE + (int64_t)threadIdx.x * 16;
+    const int c = nz_count16(mask, base, n);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < NZ_THREADS / 32; ++w)
+      if (w < warp) before += s_part[w];
+    int64_t pos = tile_offset[tile] + before + inc - c;
+    if (c) {
+      for (int j = 0; j < 16; ++j)
+        if (base + j < n && mask[base + j]) out[pos++] = base + j;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" ptk_status ptk_linearize_index(int k, const void* const* idx, const int64_t* dims, int64_t n, int64_t* out,
@@ -289,4 +401,35 @@ extern "C" ptk_status ptk_cumop(int dtype, int op, const void* x, void* out, int
     case PTK_U64: return cumop_t<uint64_t>(op, x, out, outer, n, inner, st);
   }
   return fail(PTK_ERR_ARG, "ptk_cumop: dtype must be float32/float64/int64/uint64 (np.cumsum keeps only those)");
+}
+
+extern "C" size_t ptk_nonzero_workspace_bytes(int64_t n) {
+  const int64_t tiles = (n + NZ_TILE - 1) / NZ_TILE;
+  return (size_t)(tiles + 1) * sizeof(int64_t);
+}
+
+extern "C" ptk_status ptk_nonzero_count(const void* mask, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (n < 0) return fail(PTK_ERR_ARG, "ptk_nonzero_count: negative length");
+  if (workspace == nullptr || workspace_bytes < ptk_nonzero_workspace_bytes(n))
+    return fail(PTK_ERR_ARG, "ptk_nonzero_count: workspace too small (see ptk_nonzero_workspace_bytes)");
+  const int64_t tiles = (n + NZ_TILE - 1) / NZ_TILE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tiles) {
+    nonzero_count_kernel<<<grid_for(tiles, 1), NZ_THREADS, 0, st>>>((const uint8_t*)mask, n, (int64_t*)workspace, tiles);
+    PTK_LAUNCH_CHECK("nonzero_count");
+  }
+  nonzero_scan_kernel<<<1, 1024, 0, st>>>((int64_t*)workspace, tiles);
+  PTK_LAUNCH_CHECK("nonzero_scan");
+  return PTK_OK;
+}
+
+extern "C" ptk_status ptk_nonzero_fill(const void* mask, int64_t n, const void* workspace, int64_t* out, void* stream) {
+  PTK_REQUIRE_INIT();
+  const int64_t tiles = (n + NZ_TILE - 1) / NZ_TILE;
+  if (tiles <= 0) return PTK_OK;
+  nonzero_fill_kernel<<<grid_for(tiles, 1), NZ_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t*)mask, n,
+                                                                                    (const int64_t*)workspace, tiles, out);
+  PTK_LAUNCH_CHECK("nonzero_fill");
+  return PTK_OK;
 }

@@ -51,6 +51,15 @@ def fuse_gemm_epilogue(steps, output_slots, opts):
         ew = steps[j]
         if type(ew.impl) is not ElemwiseNode:
             continue
+        pw = ew.impl.prog
+        if (ew.impl.ndim == 2 and len(pw.in_dtypes) == 1 and [q.op for q in pw.insts] == ["Tanh"] and pw.outputs == [("t", 0)]
+                and pw.insts[0].args == [("i", 0)] and pw.out_dtypes == [st.impl.dtype] and pw.in_dtypes == [st.impl.dtype]
+                and tuple(ew.impl.in_bcast[0]) == (False, False)):
+            # tanh(A @ B) without a bias: the same epilogue with a null bias pointer
+            node = GemmBiasActNode(st.impl.dtype, st.impl.precision, 1, name=f"{st.impl.name}+{ew.impl.name}[fused epilogue]")
+            repl[i] = Step(node, [st.ins[0], st.ins[1]], list(ew.outs), origin=ew.origin)
+            drop.add(j)
+            continue
         pat = _bias_act_pattern(ew.impl)
         if pat is None or ew.ins[pat[0]] != s or ew.impl.prog.out_dtypes[0] != st.impl.dtype:
             continue

@@ -137,6 +137,29 @@ def _take_axis(idx_list, ndim):
     return int_axes[0], len(int_axes)
 
 
+def _adv_template(idx_list, index_inputs, op):
+    """(template, kinds) for vm/nodes_advidx.py: per index entry ("s", start, stop, step) with positions into the node's
+    index inputs (or None), or ("a", position); kinds[position] = ("bool" | "int", ndim) for array entries."""
+    tmpl, kinds = [], {}
+    for e in idx_list:
+        if isinstance(e, slice):
+            tmpl.append(("s", e.start, e.stop, e.step))
+        else:
+            t = index_inputs[int(e)].type
+            if t.dtype == "bool":
+                if t.ndim == 0:
+                    raise UnsupportedOp(f"{op}: indexing with scalar booleans")
+                kinds[int(e)] = ("bool", t.ndim)
+            elif t.dtype.startswith(("int", "uint")):
+                kinds[int(e)] = ("int", t.ndim)
+            else:
+                raise UnsupportedOp(f"{op}: index of dtype {t.dtype}")
+            tmpl.append(("a", int(e)))
+    if not kinds:
+        raise UnsupportedOp(f"{op}: advanced indexing without an index array")
+    return tmpl, kinds
+
+
 def lower_node(node, opts):
     """Apply -> Node.  `opts`: dict(gemm_precision=0|1)."""
     op = node.op
@@ -226,17 +249,20 @@ def lower_node(node, opts):
         blk = _take_axis(op.idx_list, node.inputs[0].type.ndim)
         if (blk is None or len(node.inputs) != 1 + blk[1]
                 or any(i.type.dtype == "bool" or i.type.dtype.startswith("float") for i in node.inputs[1:])):
-            raise UnsupportedOp(f"{op}: integer index arrays on consecutive axes with all other axes taken in full "
-                                "are supported (no boolean masks, no partial slices mixed in)")
+            from pytensor_b200.vm.nodes_advidx import AdvIndexNode
+
+            return AdvIndexNode(*_adv_template(op.idx_list, node.inputs[1:], op), name=str(op))
         return nb.TakeNode(blk[0], name=str(op), naxes=blk[1])
     if isinstance(op, AdvancedIncSubtensor):
         blk = _take_axis(op.idx_list, node.inputs[0].type.ndim)
         if (blk is None or len(node.inputs) != 2 + blk[1]
-                or any(i.type.dtype == "bool" or i.type.dtype.startswith("float") for i in node.inputs[2:])):
-            raise UnsupportedOp(f"{op}: integer index arrays on consecutive axes with all other axes taken in full "
-                                "are supported (no boolean masks, no partial slices mixed in)")
-        if op.ignore_duplicates and not op.set_instead_of_inc:
-            raise UnsupportedOp(f"{op}: ignore_duplicates increments")
+                or any(i.type.dtype == "bool" or i.type.dtype.startswith("float") for i in node.inputs[2:])
+                or (op.ignore_duplicates and not op.set_instead_of_inc)):
+            from pytensor_b200.vm.nodes_advidx import AdvIndexPutNode
+
+            tmpl, kinds = _adv_template(op.idx_list, node.inputs[2:], op)
+            return AdvIndexPutNode(tmpl, kinds, bool(op.inplace), bool(op.set_instead_of_inc), bool(op.ignore_duplicates),
+                                   node.outputs[0].type.dtype, name=str(op))
         return nb.PutNode(blk[0], bool(op.inplace), bool(op.set_instead_of_inc), node.outputs[0].type.dtype,
                           name=str(op), naxes=blk[1])
 

@@ -36,6 +36,9 @@ def lower_scan(node, opts):
     out_ndims = [o.type.ndim for o in node.outputs]
     generic = ScanNode(info, program, out_dtypes, out_ndims, destroy, name=str(op))
     if opts.get("fuse", True):
+        rec = try_matmul_recurrence(node, info, program, generic, opts)
+        if rec is not None:
+            return rec
         try:
             from pytensor_b200.link.cuda.lower_scan_fused import try_fused_elemwise_scan
 
@@ -45,3 +48,38 @@ def lower_scan(node, opts):
         except ImportError:
             pass
     return generic
+
+
+def try_matmul_recurrence(node, info, program, generic, opts):
+    """h <- act(h @ W + b) with one sit-sot state and nothing else in the loop: ScanMatmulRecurrenceNode, else None."""
+    from pytensor_b200.vm.nodes_scan_matmul import ScanMatmulRecurrenceNode
+
+    if (info["n_seqs"] or info["mit_mot_in_slices"] or info["mit_sot_in_slices"] or info["sit_sot_in_slices"] != [(-1,)]
+            or info["n_nit_sot"] or info["n_untraced_sit_sot"] or info["as_while"]):
+        return None
+    if len(program.steps) != 1 or len(program.inputs) != 1 + info["n_non_seqs"]:
+        return None
+    st = program.steps[0]
+    kind = type(st.impl).__name__
+    if kind not in ("GemmBiasActNode", "Dot22Node") or getattr(st.impl, "scalar", False):
+        return None
+    if list(program.outputs) != [st.outs[0]] or st.ins[0] != program.inputs[0] or program.inputs[0] in st.ins[1:]:
+        return None
+    dtype = st.impl.dtype
+    if dtype not in ("float32", "float64") or node.outputs[0].type.ndim != 3:
+        return None
+    first_non_seq = generic.nit_sot_arg_offset + info["n_nit_sot"]
+
+    def source(slot):
+        if slot in program.constants:
+            return ("const", program.constants[slot])
+        if slot in program.inputs:
+            return ("in", first_non_seq + program.inputs.index(slot) - 1)
+        return False
+
+    w_src = source(st.ins[1])
+    bias_src = source(st.ins[2]) if (kind == "GemmBiasActNode" and len(st.ins) > 2) else None
+    if w_src is False or bias_src is False:
+        return None
+    act = st.impl.act if kind == "GemmBiasActNode" else 0
+    return ScanMatmulRecurrenceNode(generic, w_src, bias_src, act, st.impl.precision, dtype, name=str(node.op))

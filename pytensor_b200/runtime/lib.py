@@ -71,6 +71,9 @@ SIGNATURES = {
     "ptk_put_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p,
                              c_void_p]),
     "ptk_linearize_index": (c_int, [c_int, POINTER(c_void_p), _i64p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ptk_nonzero_workspace_bytes": (c_size_t, [c_int64]),
+    "ptk_nonzero_count": (c_int, [c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "ptk_nonzero_fill": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ptk_arange": (c_int, [c_int, c_void_p, c_int64, c_double, c_double, c_int64, c_int64, c_void_p]),
     "ptk_argmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "ptk_cumop": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -86,6 +89,11 @@ SIGNATURES = {
     "ptk_gemm_split_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "ptk_gemm_tc_split": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                   c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ptk_stage_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "ptk_stage_operand": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+    "ptk_gemm_tc_staged": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                   c_int, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
+                                   c_int, c_void_p]),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -118,6 +126,10 @@ class _TraceLib:
             return lambda M, N, K: 6 * ((M + 255) // 256 * 256 + (N + 255) // 256 * 256) * ((K + 7) // 8 * 8) + 1024
         if name == "ptk_put_rows_workspace_bytes":
             return lambda n_dst, n_idx: 4 * (n_dst + 1 + n_idx) + 64
+        if name == "ptk_stage_bytes":
+            return lambda r, c, p: (r if p <= 1 else 3 * ((r + 255) // 256 * 256)) * ((c + 7) // 8 * 8) * 2 + 256
+        if name == "ptk_nonzero_workspace_bytes":
+            return lambda n: 8 * ((n + 4095) // 4096 + 1)
         if name == "ptk_last_error":
             return lambda: b""
         return lambda *a, **k: 0

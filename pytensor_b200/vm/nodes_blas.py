@@ -100,6 +100,59 @@ def gemv(dtype, alpha, A, x, beta, y):
                "ptk_gemv")
 
 
+# ---- operands staged once, products chained (include/ptk.h: ptk_stage_operand / ptk_gemm_tc_staged) -----------------------
+class Staged:
+    """A matrix in the tensor-core kernel's operand layout: `pieces` (1 = bf16, 3 = bf16x3 split) K-major matrices
+    [rows, cols] stacked with a pitch of `piece_rows` rows in one device buffer."""
+
+    __slots__ = ("buf", "rows", "cols", "ld", "piece_rows", "pieces")
+
+    def __init__(self, rows, cols, pieces):
+        self.rows, self.cols, self.pieces = int(rows), int(cols), int(pieces)
+        self.ld = (self.cols + 7) // 8 * 8
+        self.piece_rows = (self.rows + 255) // 256 * 256
+        nbytes = int(_lib.lib().ptk_stage_bytes(self.rows, self.cols, self.pieces))
+        self.buf = dev.empty_t((nbytes,), torch.uint8)
+
+    @property
+    def ptr(self):
+        return (dev.ptr(self.buf) + 255) & ~255
+
+
+def stage_operand(t: torch.Tensor, pieces: int, transposed: bool = False) -> Staged:
+    """fp32 matrix -> Staged (one kernel).  `transposed`: stage t^T — the B operand of A @ B is staged as B^T [N, K]."""
+    R, C = (t.shape[1], t.shape[0]) if transposed else (t.shape[0], t.shape[1])
+    sr, sc = (t.stride(1), t.stride(0)) if transposed else (t.stride(0), t.stride(1))
+    st = Staged(R, C, pieces)
+    _lib.check(_lib.lib().ptk_stage_operand(dev.ptr(t), sr, sc, R, C, pieces, st.ptr, st.ld, st.piece_rows, dev.stream_ptr()),
+               "ptk_stage_operand")
+    return st
+
+
+def tc_plan(dtype, precision, M, N, K):
+    """(pieces, terms) of the tensor-core path this product takes, or None for the FMA kernels."""
+    if dtype != "float32" or min(M, N, K) < TC_MIN_DIM:
+        return None
+    if precision == 1:
+        return 1, 1
+    if FP32_MODE in ("tc6", "tc3"):
+        return 3, 6 if FP32_MODE == "tc6" else 3
+    return None
+
+
+def gemm_staged(A: Staged, B: Staged, terms, alpha, beta, C, bias=None, act=0, out: Staged | None = None):
+    """C = act(alpha * A @ B + beta * C + bias) from staged operands; `out` receives the staged pieces of the result."""
+    M, K, N = A.rows, A.cols, B.rows
+    if B.cols != K or tuple(C.shape) != (M, N):
+        raise ValueError(f"gemm_staged: shape mismatch ({M},{K}) @ ({B.cols},{N}) -> {tuple(C.shape)}")
+    _lib.check(_lib.lib().ptk_gemm_tc_staged(M, N, K, float(alpha), A.ptr, A.ld, A.piece_rows, B.ptr, B.ld, B.piece_rows,
+                                             int(terms), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
+                                             dev.ptr(bias) if bias is not None else None, int(act),
+                                             out.ptr if out is not None else None, out.ld if out is not None else 0,
+                                             out.piece_rows if out is not None else 0, out.pieces if out is not None else 1,
+                                             dev.stream_ptr()), "ptk_gemm_tc_staged")
+
+
 class Dot22Node(Node):
     emit_bf16 = False  # set by the fusion pass when the only consumer is another tensor-core GEMM taking this as A
 
@@ -243,11 +296,14 @@ class GemmBiasActNode(Node):
         self.dtype, self.precision, self.act, self.name = dtype, precision, act, name
 
     def run(self, vals):
-        A, B, bias = vals[0].dev(), vals[1].dev(), vals[2].dev()
+        A, B = vals[0].dev(), vals[1].dev()
+        bias = vals[2].dev() if len(vals) > 2 else None  # (two inputs: act(A @ B), no bias)
         M, N = A.shape[0], B.shape[1]
-        if bias.shape[-1] != N:
-            raise ValueError(f"{self.name}: bias of shape {tuple(bias.shape)} does not match N={N}")
-        b1 = bias.reshape(-1) if bias.is_contiguous() else dev.contiguous(bias).reshape(-1)
+        b1 = None
+        if bias is not None:
+            if bias.shape[-1] != N:
+                raise ValueError(f"{self.name}: bias of shape {tuple(bias.shape)} does not match N={N}")
+            b1 = bias.reshape(-1) if bias.is_contiguous() else dev.contiguous(bias).reshape(-1)
         out = dev.empty((M, N), self.dtype)
         if out.numel():
             if A.shape[1] == 0:

@@ -456,7 +456,7 @@ class Executor:
         _lib.check(L.ptk_sync_stream(sp2), "sync")
         plan.pop("keep", None)
         self.chunked_calls += 1
-        return [Val(h=h) for h in host_out]
+        return [Val(h=h, aux="fresh") for h in host_out]
 
     def _capture(self, e, inputs):
         import torch
@@ -629,7 +629,9 @@ def outputs_to_host(out_vals, device_outputs=False, copy_device=False, sink=None
     pending = []
     for v in out_vals:
         if v.h is not None and v.d is None:
-            res.append(np.array(v.h, copy=True))  # host-only values (shape vectors ...): a fresh object per call
+            # host-only values (shape vectors ...) are cached inside the VM: hand out a fresh object per call.  The
+            # chunked host pipeline's results (aux == "fresh": page-locked arrays it filled for THIS call) already are.
+            res.append(np.asarray(v.h) if isinstance(v.aux, str) and v.aux == "fresh" else np.array(v.h, copy=True))
         elif device_outputs:
             res.append(dev.clone(v.d) if copy_device else v.d)
         else:

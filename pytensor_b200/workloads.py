@@ -154,17 +154,20 @@ def cfg5_logp_grad(B=1 << 20, n=1024, J=64, K=8, dtype="float32", packed=False):
         "bytes": B * P * 4 + n * (K + 2) * 4 + (1 + P) * 4, "P": P, "name": "cfg5_logp_grad"}
 
 
-def metric_graph(n=64, layers=84, scan_steps=16):
-    """The 256-node class metric graph: 84 x tanh(h@W+b), a 16-step Scan, a final Sum."""
+def metric_graph(n=64, layers=84, scan_steps=16, dtype="float32"):
+    """The 256-node class metric graph: 84 x tanh(h@W+b), a 16-step Scan, a final Sum.
+    `dtype="float64"`: the same graph over the same (float32-valued) numbers in double — the bench's yardstick for how far
+    two fp32 evaluations of this 84-layer chain may legitimately sit apart."""
     pytensor, pt = _pt()
-    x = pt.fmatrix("x")
-    Ws = [pt.fmatrix(f"W{i}") for i in range(layers)]
-    bs = [pt.fvector(f"b{i}") for i in range(layers)]
-    a = pt.fvector("a")
+    x = pt.matrix("x", dtype=dtype)
+    Ws = [pt.matrix(f"W{i}", dtype=dtype) for i in range(layers)]
+    bs = [pt.vector(f"b{i}", dtype=dtype) for i in range(layers)]
+    a = pt.vector("a", dtype=dtype)
     h = x
     for W, b in zip(Ws, bs):
         h = pt.tanh(pt.dot(h, W) + b)
-    hs = pytensor.scan(lambda h, a: pt.tanh(h * a + np.float32(0.1)), outputs_info=[h], non_sequences=[a],
+    c01 = np.asarray(np.float32(0.1), dtype=dtype)
+    hs = pytensor.scan(lambda h, a: pt.tanh(h * a + c01), outputs_info=[h], non_sequences=[a],
                        n_steps=scan_steps, return_updates=False)
     out = hs[-1].sum(axis=0)
 
@@ -174,6 +177,6 @@ def metric_graph(n=64, layers=84, scan_steps=16):
         args += [(rng.standard_normal((n, n)) / np.sqrt(n)).astype("float32") for _ in range(layers)]
         args += [(rng.standard_normal(n) * 0.1).astype("float32") for _ in range(layers)]
         args += [rng.uniform(0.5, 1.5, n).astype("float32")]
-        return args
+        return [v.astype(dtype) for v in args]
 
     return [x, *Ws, *bs, a], [out], make_args, {"name": "metric_graph"}

@@ -79,6 +79,10 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { re
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
   const int lane = threadIdx.x & 31; return emu_exchange(v, lane + d < 32 ? (int)threadIdx.x + d : (int)threadIdx.x);
 }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = threadIdx.x & 31; return emu_exchange(v, lane - d >= 0 ? (int)threadIdx.x - d : (int)threadIdx.x);
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 """
 
 

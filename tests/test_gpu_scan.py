@@ -37,6 +37,54 @@ def test_cfg4_matmul_recurrence_general_loop(gpu):
     ins, outs, make_args, _ = W.cfg4_scan(64, 32, 20, matmul=True)
     f, _ = compare_cuda_and_cvm(ins, outs, make_args(), rtol=1e-4, atol=1e-5)
     assert not _is_fused(f)
+    # h <- tanh(h @ W + b) alone in the loop: a chain of GEMM launches writing straight into the tap buffer
+    assert any(type(st.impl).__name__ == "ScanMatmulRecurrenceNode" for st in f.vm.executor.program.steps)
+
+
+def _contractive(args, gain=0.6):
+    # |W| scaled below the edge of chaos: rounding differences between two sgemm implementations must decay, not grow
+    args = list(args)
+    args[1] = (args[1] * gain).astype("float32")
+    return args
+
+
+@pytest.mark.parametrize("full_trace", [False, True])
+@pytest.mark.parametrize("rows,cols,steps", [(300, 256, 9), (512, 384, 25)])
+def test_matmul_recurrence_on_tensor_cores_chained_operands(gpu, rows, cols, steps, full_trace):
+    """dims >= 256: the fp32-accurate tcgen05 path — W staged once, every step's epilogue writes the three-piece staged
+    operand of the next step (nodes_scan_matmul.py); final state (2-slot circular buffer) and full trace, vs the C linker."""
+    pytensor.config.floatX = "float32"
+    from pytensor_b200 import workloads as W
+
+    ins, outs, make_args, _ = W.cfg4_scan(rows, cols, steps, matmul=True, full_trace=full_trace)
+    f, _ = compare_cuda_and_cvm(ins, outs, _contractive(make_args()), rtol=1e-5, atol=1e-5)
+    assert any(type(st.impl).__name__ == "ScanMatmulRecurrenceNode" for st in f.vm.executor.program.steps)
+
+
+def test_matmul_recurrence_variants(gpu):
+    pytensor.config.floatX = "float32"
+    rng = np.random.default_rng(61)
+    h0, Wm = pt.fmatrix("h0"), pt.fmatrix("W")
+    n = pt.lscalar("n")
+    h0v = rng.standard_normal((260, 256)).astype("float32")
+    Wv = (rng.standard_normal((256, 256)) * 0.03).astype("float32")
+    # no bias, no activation, symbolic n_steps (0, 1 and many), last three states only (truncated buffer)
+    hs = scan(lambda h, W: pt.dot(h, W), outputs_info=[h0], non_sequences=[Wm], n_steps=n, return_updates=False)
+    for steps in (0, 1, 7):
+        outs = [hs] if steps == 0 else [hs, hs[-1]]
+        compare_cuda_and_cvm([h0, Wm, n], outs, [h0v, Wv, steps], rtol=1e-5, atol=1e-5)
+    hs = scan(lambda h, W: pt.tanh(pt.dot(h, W)), outputs_info=[h0], non_sequences=[Wm], n_steps=12, return_updates=False)
+    f, _ = compare_cuda_and_cvm([h0, Wm], [hs[-3:]], [h0v, Wv], rtol=1e-5, atol=1e-5)
+    assert any(type(st.impl).__name__ == "ScanMatmulRecurrenceNode" for st in f.vm.executor.program.steps)
+    # bf16 tensor-core mode: the chained operand is the bf16 copy; compared at bf16 accuracy
+    f16 = pytensor.function([h0, Wm], hs[-1], mode="CUDA_BF16")
+    ref = pytensor.function([h0, Wm], hs[-1], mode="CVM")(h0v, Wv)
+    assert np.abs(f16(h0v, Wv) - ref).max() < 2e-2
+    # fp64 state: FMA kernel per step, still in place
+    pytensor.config.floatX = "float64"
+    g0, Wd = pt.dmatrix("g0"), pt.dmatrix("Wd")
+    gs = scan(lambda h, W: pt.tanh(pt.dot(h, W)), outputs_info=[g0], non_sequences=[Wd], n_steps=5, return_updates=False)
+    compare_cuda_and_cvm([g0, Wd], [gs, gs[-1]], [h0v[:, :64].astype("float64"), Wv[:64, :64].astype("float64")])
 
 
 def test_sequences_mit_sot_nit_sot(gpu):

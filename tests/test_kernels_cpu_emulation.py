@@ -383,3 +383,48 @@ def test_skinny_gemm_small_k_kernel_v2(tmp_path, M, N, K, KM, beta):
 def test_skinny_gemm_small_n_kernel_v2(tmp_path, M, N_act, NT, K, beta, R):
     """The R-rows-per-warp variant: row groups that run past M, fewer rows than one group, K spanning several sweeps."""
     _smalln_case(tmp_path, "gemm_smalln_v2_kernel", M, N_act, NT, K, beta, R=R)
+
+
+# ---- boolean-mask compaction (ptk_nonzero_count / ptk_nonzero_fill, csrc/ptk_misc.cu) -----------------------------------
+def _nonzero_sources():
+    import re
+
+    text = open(os.path.join(CSRC, "ptk_misc.cu")).read()
+    consts = "\n".join(re.findall(r"^constexpr int NZ_[A-Z]+ = [^;]+;", text, re.M))
+    i = text.index("__device__ __forceinline__ int nz_count16")
+    helper = text[i:text.index("\n}\n", i) + 3]
+    shim = "struct alignas(16) uint4 { unsigned x, y, z, w; };\n"
+    return shim + consts + "\n" + helper
+
+
+@pytest.mark.parametrize("n,density,misalign", [(0, 0.5, 0), (1, 1.0, 0), (37, 0.5, 0), (4096, 0.3, 0), (4097, 0.9, 0),
+                                                (3 * 4096 + 123, 0.05, 3), (9000, 0.0, 0), (70001, 0.6, 1)])
+def test_nonzero_count_scan_fill_kernels(tmp_path, n, density, misalign):
+    """np.flatnonzero of a byte mask through the three device passes (tile counts with 16-byte loads and the byte-fold
+    popcount, single-CTA exclusive scan with carried totals, ordered per-tile compaction), tails and unaligned bases."""
+    rng = np.random.default_rng(n + 1)
+    raw = np.zeros(n + 64, dtype=np.uint8)
+    mask = raw[misalign:misalign + n]
+    mask[:] = (rng.random(n) < density) * rng.integers(1, 256, size=n)  # "true" is any non-zero byte
+    pre = _nonzero_sources()
+    TILE = 4096
+    tiles = (n + TILE - 1) // TILE
+    ws = np.full(tiles + 1, -7, dtype=np.int64)
+    if tiles:
+        k = EmulatedKernel(pre + extract_static_kernel(os.path.join(CSRC, "ptk_misc.cu"), "nonzero_count_kernel"),
+                           "nonzero_count_kernel", tmp_path, threaded=True)
+        k.launch(min(tiles, 3), 256, [_ptr(mask), ctypes.c_longlong(n), _ptr(ws), ctypes.c_longlong(tiles)])
+        per_tile = [int(np.count_nonzero(mask[t * TILE:(t + 1) * TILE])) for t in range(tiles)]
+        assert ws[:tiles].tolist() == per_tile
+    k = EmulatedKernel(extract_static_kernel(os.path.join(CSRC, "ptk_misc.cu"), "nonzero_scan_kernel"), "nonzero_scan_kernel",
+                       tmp_path, threaded=True)
+    k.launch(1, 1024, [_ptr(ws), ctypes.c_longlong(tiles)])
+    expect = np.flatnonzero(mask)
+    assert ws[tiles] == expect.size
+    if tiles:
+        assert ws[:tiles].tolist() == np.concatenate([[0], np.cumsum(per_tile)[:-1]]).tolist()
+        out = np.full(max(expect.size, 1), -1, dtype=np.int64)
+        k = EmulatedKernel(pre + extract_static_kernel(os.path.join(CSRC, "ptk_misc.cu"), "nonzero_fill_kernel"),
+                           "nonzero_fill_kernel", tmp_path, threaded=True)
+        k.launch(min(tiles, 2), 256, [_ptr(mask), ctypes.c_longlong(n), _ptr(ws), ctypes.c_longlong(tiles), _ptr(out)])
+        np.testing.assert_array_equal(out[:expect.size], expect)

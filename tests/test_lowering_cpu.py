@@ -11,6 +11,12 @@ from pytensor_b200 import workloads as W
 from pytensor_b200.precompile import trace_function
 
 
+def pytensor_b200_mode(**kw):
+    from pytensor_b200.link.cuda import cuda_mode
+
+    return cuda_mode(**kw)
+
+
 def _steps(f):
     return [type(st.impl).__name__ for st in f.vm.executor.program.steps]
 
@@ -53,10 +59,26 @@ def test_cfg4_scan_lowers_to_the_persistent_kernel():
     f = pytensor.function(ins, outs, mode="CUDA")
     assert "ScanFusedElemwiseNode" in _steps(f)
     assert trace_function(f, mk()) == 1  # ONE launch for all 100 steps
+    # h <- tanh(h @ W + b): a chain of GEMM launches, one per step, each writing into the tap buffer (FMA kernel at this size)
     ins, outs, mk, _ = W.cfg4_scan(64, 64, 10, matmul=True)
     f = pytensor.function(ins, outs, mode="CUDA")
-    assert "ScanNode" in _steps(f)
-    trace_function(f, mk())
+    assert "ScanMatmulRecurrenceNode" in _steps(f)
+    assert trace_function(f, mk()) <= 10 + 6
+    # tensor-core sizes: W and the initial state staged once (2 launches), then ONE launch per step
+    ins, outs, mk, _ = W.cfg4_scan(512, 256, 12, matmul=True)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    assert "ScanMatmulRecurrenceNode" in _steps(f)
+    n_tc = trace_function(f, mk())
+    f_loop = pytensor.function(ins, outs, mode=pytensor_b200_mode(fuse=False))
+    assert "ScanNode" in _steps(f_loop)  # the general device loop stays available
+    assert n_tc <= 12 + 2 + 6
+    # anything else in the loop keeps the general node
+    import pytensor.tensor as pt2
+
+    h0, Wm = pt2.fmatrix("h0"), pt2.fmatrix("W")
+    hs = pytensor.scan(lambda h, W: pt2.tanh(pt2.dot(h, W)) * 0.5 + h, outputs_info=[h0], non_sequences=[Wm], n_steps=3,
+                       return_updates=False)
+    assert "ScanNode" in _steps(pytensor.function([h0, Wm], hs[-1], mode="CUDA"))
 
 
 def test_cfg5_and_metric_graph_lower():
