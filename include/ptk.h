@@ -134,6 +134,19 @@ ptk_status   ptk_argmax(int dtype, const void* x, int64_t* out, int64_t outer, i
  * line (bit-exact); inner == 1: warp scan (integers exact, floats within rounding). */
 ptk_status   ptk_cumop(int dtype, int op, const void* x, void* out, int64_t outer, int64_t n, int64_t inner, void* stream);
 
+/* ---- random draws (RandomVariable, tensor/random/op.py:49; perform :457-468 draws from a host
+ *      numpy Generator) ---------------------------------------------------------------------------------------------------
+ * out[i] (i < n, contiguous) = one draw of distribution `dist` with parameters p0[i*s0], p1[i*s1], p2[i*s2] (float64 device
+ * arrays; stride 0 = one value for all, 1 = one per output element; NULL = the distribution's default).  Counter-based
+ * Philox4x32-10 stream per element, keyed by (key, seed): same key/seed => same draws.  dist: 0 uniform(low, high),
+ * 1 normal(loc, scale), 2 halfnormal(loc, scale), 3 lognormal(mean, sigma), 4 exponential(scale), 5 laplace(loc, scale),
+ * 6 logistic(loc, scale), 7 gumbel(loc, scale), 8 cauchy(loc, scale), 9 bernoulli(p), 10 gamma(shape, scale),
+ * 11 beta(a, b), 12 integers[low, high), 13 weibull(shape), 14 pareto(shape, scale), 15 halfcauchy(loc, scale),
+ * 16 invgamma(shape, scale), 17 studentt(df, loc, scale).  The values are NOT numpy's (its PCG64 rejection samplers are
+ * sequential): parity with the reference is distributional. */
+ptk_status   ptk_random_fill(int dist, int dtype, void* out, int64_t n, uint64_t key, uint64_t seed, const void* p0, int64_t s0,
+                             const void* p1, int64_t s1, const void* p2, int64_t s2, void* stream);
+
 /* ---- BLAS family (A5/A6: Gemm tensor/blas/gemm.py:76, Dot22 :248, Dot22Scalar :298, Gemv tensor/blas/gemv.py:16,
  *      Ger tensor/blas/ger.py:8; the C linker calls sgemm_/dgemm_/sgemv_/dgemv_ at blas/c_code/codegen.py:463-805) */
 /* C[M,N] = alpha * A[M,K] @ B[K,N] + beta * C, arbitrary element strides, dtype PTK_F32 | PTK_F64.
@@ -182,16 +195,27 @@ ptk_status   ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double alpha, co
  *     row pitch ld (multiple of 8, >= cols), piece i at rows [i*piece_rows, ...); dst >= ptk_stage_bytes(rows, cols, pieces)
  *     with ld = round_up(cols, 8), piece_rows = round_up(rows, 256).  For the B operand of C = A @ B stage B^T:
  *     rows = N, cols = K, sr = B's column stride, sc = B's row stride.
+ *     aligned != 0 (3 pieces, default pitches): the LEADING piece of every row is an integer multiple (|.| <= 128) of a
+ *     per-row power of two, so that the A1 x B1 products of a dot product accumulate EXACTLY in the tensor core's fp32
+ *     accumulator (which truncates otherwise: a systematic shrink of ~1e-7 per MMA of the accumulation chain) — the
+ *     operand layout ptk_gemm_tc_staged's exact_main mode expects for both A and B.
  *   ptk_gemm_tc_staged: C = act(alpha * A @ B + beta * C + bias[N]) from staged A [M,K] / B^T [N,K]; terms 1 (bf16
- *     operands) | 3 | 6 (fp32-accurate, see ptk_gemm_tc_split; 3 and 6 need 3-piece operands).  C_stage (optional) receives
- *     out_pieces (1 | 3) staged pieces of the result [M,N] (pitch ldc_stage, piece pitch c_rows). */
+ *     operands) | 3 | 6 (fp32-accurate, see ptk_gemm_tc_split; 3 and 6 need 3-piece operands).  exact_main != 0 (both
+ *     operands staged `aligned`): A1 x B1 accumulates in its own TMEM accumulator, exactly, in chunks of K <= 1024; the
+ *     correction products in a second one; the epilogue adds them with round-to-nearest.  C_stage (optional) receives
+ *     out_pieces (1 | 3) staged pieces of the result [M,N] (pitch ldc_stage, piece pitch c_rows); out_exp != PTK_STAGE_NO_EXP
+ *     aligns the leading output piece to that fixed exponent (results known to lie in [-1, 1], e.g. tanh: out_exp = 6),
+ *     which makes the pieces a valid `aligned` A operand of a following exact_main product.
+ *   ptk_gemm_exact_main_default: 1 unless PTK_GEMM_EXACT=0 — what ptk_gemm_tc_split uses. */
+#define PTK_STAGE_NO_EXP (-100000)
 size_t       ptk_stage_bytes(int64_t rows, int64_t cols, int pieces);
-ptk_status   ptk_stage_operand(const void* src_f32, int64_t sr, int64_t sc, int64_t rows, int64_t cols, int pieces,
+ptk_status   ptk_stage_operand(const void* src_f32, int64_t sr, int64_t sc, int64_t rows, int64_t cols, int pieces, int aligned,
                       void* dst, int64_t ld, int64_t piece_rows, void* stream);
 ptk_status   ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double alpha, const void* A_stage, int64_t lda, int64_t a_rows,
                       const void* B_stage, int64_t ldb, int64_t b_rows, int terms, double beta, void* C, int64_t sc0,
                       int64_t sc1, const void* bias, int act, void* C_stage, int64_t ldc_stage, int64_t c_rows,
-                      int out_pieces, void* stream);
+                      int out_pieces, int exact_main, int out_exp, void* stream);
+int          ptk_gemm_exact_main_default(void);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

@@ -57,15 +57,23 @@ def _block_reduce_code(tpr: int) -> str:
     return f"""
     #pragma unroll
     for (int m = 16; m > 0; m >>= 1) acc = ptk_red(acc, ptk_shfl_xor<ACC>(acc, m));
-    __shared__ ACC s_part[{tpr // 32}];
+    __shared__ ACC s_part[8];                 // one partial per warp of the CTA; a row owns {tpr // 32} consecutive warps
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {{
+    if ((threadIdx.x & (TPR - 1)) == 0) {{
       #pragma unroll
-      for (int w = 1; w < {tpr // 32}; ++w) acc = ptk_red(acc, s_part[w]);
+      for (int w = 1; w < {tpr // 32}; ++w) acc = ptk_red(acc, s_part[(threadIdx.x >> 5) + w]);
     }}
     __syncthreads();
 """
+
+
+def _k3_min_blocks() -> int:
+    """CTAs per SM the row kernel is compiled for (register cap 65536 / (256 * n)): 4 leaves 64 registers — enough for
+    the two-trip software pipeline of a 2-input Composite with a couple of spilled words; PTK_K3_MINB overrides (A/B)."""
+    import os
+
+    return int(os.environ.get("PTK_K3_MINB", "4"))
 
 
 def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: tuple, red_op: str, acc_dtype: str,
@@ -90,21 +98,63 @@ def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: 
     params += ["long long rows", "long long cols", "int nsplit"]
     rows_per_block = 256 // tpr
 
-    ld = []
-    for k, d in enumerate(prog.in_dtypes):
-        T = CTYPE[d]
-        if col_modes[k] == 1:
-            ld.append(f"        const PVec<{T}, VW> vi{k} = ptk_ldv<{T}, VW>(pi{k} + r * rsi{k} + c);")
+    # Row base pointers are formed once per row (64-bit); the column walk uses 32-bit vector indices (the launcher keeps
+    # cols < 2^31) and no integer division: VW and TPR are powers of two, the split bounds only exist when nsplit > 1.
+    base_in = "\n".join(f"      const {CTYPE[d]}* q{k} = pi{k} + r * rsi{k};" for k, d in enumerate(prog.in_dtypes))
+    base_out = "\n".join(f"      {CTYPE[prog.out_dtypes[k]]}* w{k} = po{k} + r * rso{k};" for k in stored)
+
+    def loads(tag, cexpr):
+        out = []
+        for k, d in enumerate(prog.in_dtypes):
+            T = CTYPE[d]
+            if col_modes[k] == 1:
+                out.append(f"          const PVec<{T}, VW> v{tag}{k} = ptk_ldv<{T}, VW>(q{k} + {cexpr});")
+        return "\n".join(out)
+
+    row_scalars = "\n".join(f"      const {CTYPE[d]} s{k} = q{k}[0];" for k, d in enumerate(prog.in_dtypes) if col_modes[k] != 1)
+    # (A float32 map output is promoted element by element: adding the VW lanes of a vector in fp32 first would save
+    # conversions but breaks the reference's "fp32 sums accumulate in float64" contract on cancelling sums — measured 2e-6
+    # on a 200000-term row, tests/test_gpu_careduce.py::test_fp32_sum_accumulates_in_fp64.)
+    presum = False
+
+    def compute(tag, cexpr):
+        call_in = [f"v{tag}{k}.v[e]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
+        decl = "\n".join(f"          PVec<{CTYPE[d]}, VW> o{tag}{k};" for k, d in enumerate(prog.out_dtypes))
+        call_out = [f"o{tag}{k}.v[e]" for k in range(n_map)]
+        st_ = "\n".join(f"          ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(w{k} + {cexpr}, o{tag}{k});" for k in stored)
+        if presum:
+            terms = [f"o{tag}0.v[{e}]" for e in range(vw)]
+            while len(terms) > 1:
+                terms = [f"({terms[q]} + {terms[q + 1]})" for q in range(0, len(terms), 2)]
+            red = f"          acc = ptk_red(acc, (ACC){terms[0]});"
+            body = f"""          #pragma unroll
+          for (int e = 0; e < VW; ++e) ptk_body({', '.join(call_in + call_out)});
+{red}"""
         else:
-            ld.append(f"        const {T} vi{k} = pi{k}[r * rsi{k}];")
-    call_in = [f"vi{k}.v[e]" if col_modes[k] == 1 else f"vi{k}" for k in range(n_in)]
-    out_decl = "\n".join(f"        PVec<{CTYPE[d]}, VW> vo{k};" for k, d in enumerate(prog.out_dtypes))
-    call_out = [f"vo{k}.v[e]" for k in range(n_map)]
-    st = "\n".join(f"        ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(po{k} + r * rso{k} + c, vo{k});" for k in stored)
-    # scalar tail (cols % VW)
-    tail_in = [f"pi{k}[r * rsi{k} + c]" if col_modes[k] == 1 else f"pi{k}[r * rsi{k}]" for k in range(n_in)]
-    tail_tmp = "\n".join(f"        {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
-    tail_st = "\n".join(f"        po{k}[r * rso{k} + c] = to{k};" for k in stored)
+            body = f"""          #pragma unroll
+          for (int e = 0; e < VW; ++e) {{
+            ptk_body({', '.join(call_in + call_out)});
+            acc = ptk_red(acc, (ACC)o{tag}0.v[e]);
+          }}"""
+        return f"{decl}\n{body}\n{st_}"
+
+    vec_in = [k for k in range(n_in) if col_modes[k] == 1]
+
+    def pin_loads(tag, base, ea, eb):
+        out = []
+        for k in vec_in:
+            T = CTYPE[prog.in_dtypes[k]]
+            out.append(f"            v{tag}a{k} = ptk_ldv_pin<{T}, VW>({base}{k} + {ea});")
+            out.append(f"            v{tag}b{k} = ptk_ldv_pin<{T}, VW>({base}{k} + {eb});")
+        return "\n".join(out)
+
+    pipe_decl = "\n".join(f"  PVec<{CTYPE[prog.in_dtypes[k]]}, VW> vpa{k}, vpb{k}, vna{k}, vnb{k};" for k in vec_in)
+    next_row_ptrs = "\n".join(f"            const {CTYPE[prog.in_dtypes[k]]}* z{k} = pi{k} + r2 * rsi{k};" for k in vec_in)
+    advance = "\n".join(f"          vpa{k} = vna{k}; vpb{k} = vnb{k};" for k in vec_in)
+
+    tail_in = [f"q{k}[c]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
+    tail_tmp = "\n".join(f"          {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
+    tail_st = "\n".join(f"          w{k}[c] = to{k};" for k in stored)
 
     return f"""{PRELUDE}
 {_VEC_HELPERS}
@@ -116,31 +166,66 @@ typedef {OUT} OUT;
 #define VW {vw}
 #define TPR {tpr}
 
-extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
-  const int lane_in_row = threadIdx.x % TPR;
+extern "C" __global__ void __launch_bounds__(256, {_k3_min_blocks()}) {name}({', '.join(params)}) {{
+  const int lane_in_row = threadIdx.x & (TPR - 1);
   const int row_in_block = threadIdx.x / TPR;
-  const long long ncv = cols / VW;                       // vector chunks per row
-  const long long per_split = (ncv + nsplit - 1) / nsplit;
-  const int split = blockIdx.y;
-  const long long cv_lo = (long long)split * per_split;
-  const long long cv_hi = (cv_lo + per_split < ncv) ? (cv_lo + per_split) : ncv;
+  const int ncv = (int)(cols / VW);                      // vector chunks per row (VW is a power of two: a shift)
+  int cv_lo = 0, cv_hi = ncv;
+  if (nsplit > 1) {{
+    const int per_split = (ncv + nsplit - 1) / nsplit;
+    cv_lo = (int)blockIdx.y * per_split;
+    cv_hi = (cv_lo + per_split < ncv) ? (cv_lo + per_split) : ncv;
+  }}
+  const bool last_split = (int)blockIdx.y == nsplit - 1;
+{pipe_decl}
+  bool primed = false;   // vpa* / vpb* already hold the first trip of the row this thread starts next
   for (long long rb = (long long)blockIdx.x * {rows_per_block}; rb < rows; rb += (long long)gridDim.x * {rows_per_block}) {{
     const long long r = rb + row_in_block;
     ACC acc = (ACC){literal(acc_dtype, identity)};
     if (r < rows) {{
-      for (long long cv = cv_lo + lane_in_row; cv < cv_hi; cv += TPR) {{
-        const long long c = cv * VW;
-{chr(10).join(ld)}
-{out_decl}
-        #pragma unroll
-        for (int e = 0; e < VW; ++e) {{
-          ptk_body({', '.join(call_in + call_out)});
-          acc = ptk_red(acc, (ACC)vo0.v[e]);
+{base_in}
+{base_out}
+{row_scalars}
+      int cv = cv_lo + lane_in_row;
+      // Software pipeline over trips of two vectors: the (pinned) loads of trip t+1 are issued before trip t is computed,
+      // and the last trip of a row issues the first trip of this thread's NEXT row, so the memory system always has a
+      // trip in flight per thread while the scalar bodies run.
+      if (cv + TPR < cv_hi) {{
+        if (!primed) {{
+{pin_loads('p', 'q', 'cv * VW', '(cv + TPR) * VW')}
         }}
-{st}
+        primed = false;
+        for (;;) {{
+          const int nx = cv + 2 * TPR;
+          const bool more = nx + TPR < cv_hi;
+          const long long r2 = r + (long long)gridDim.x * {rows_per_block};
+          if (more) {{
+{pin_loads('n', 'q', 'nx * VW', '(nx + TPR) * VW')}
+          }} else if (r2 < rows) {{
+{next_row_ptrs}
+            const int c2 = cv_lo + lane_in_row;
+{pin_loads('n', 'z', 'c2 * VW', '(c2 + TPR) * VW')}
+            primed = true;
+          }}
+          const int ca = cv * VW, cb = (cv + TPR) * VW;
+          {{
+{compute('pa', 'ca')}
+{compute('pb', 'cb')}
+          }}
+          cv = nx;
+{advance}
+          if (!more) break;
+        }}
       }}
-      if (split == nsplit - 1) {{
-        for (long long c = ncv * VW + lane_in_row; c < cols; c += TPR) {{
+      for (; cv < cv_hi; cv += TPR) {{
+        const int ca = cv * VW;
+        {{
+{loads('a', 'ca')}
+{compute('a', 'ca')}
+        }}
+      }}
+      if (last_split) {{
+        for (int c = ncv * VW + lane_in_row; c < (int)cols; c += TPR) {{
 {tail_tmp}
           ptk_body({', '.join(tail_in + [f'to{k}' for k in range(n_map)])});
           acc = ptk_red(acc, (ACC)to0);
@@ -151,11 +236,11 @@ extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
 {_block_reduce_code(tpr)}
     if (lane_in_row == 0 && r < rows) {{
       if (nsplit == 1) reinterpret_cast<OUT*>(pred)[r] = (OUT)acc;
-      else reinterpret_cast<ACC*>(pred)[r * nsplit + split] = acc;
+      else reinterpret_cast<ACC*>(pred)[r * nsplit + split_of_block()] = acc;
     }}
   }}
 }}
-"""
+""".replace("split_of_block()", "(int)blockIdx.y")
 
 
 def gen_finish_kernel(name: str, red_op: str, acc_dtype: str, out_dtype: str, identity) -> str:

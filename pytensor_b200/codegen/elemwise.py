@@ -27,6 +27,23 @@ template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv(const
 template <typename T, int N> __device__ __forceinline__ void ptk_stv(T* p, const PVec<T, N>& v) {
   *reinterpret_cast<PVec<T, N>*>(p) = v;
 }
+// A load the compiler may not move: issued exactly where it is written (`asm volatile`), so that the software pipeline of
+// the fused map+row-reduce kernel really has the NEXT trip's data in flight while the current trip is computed (left to
+// itself the compiler sinks plain loads down to their first use to save registers).
+template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv_pin(const T* p) {
+  PVec<T, N> r;
+  if constexpr (sizeof(PVec<T, N>) % 16 == 0) {
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PVec<T, N>) / 16); ++i)
+      asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w) : "l"(s + i));
+  } else {
+    r = *reinterpret_cast<const PVec<T, N>*>(p);
+  }
+  return r;
+}
 """
 
 

@@ -178,7 +178,16 @@ struct EpiParams {
   // with round-to-nearest fp32 adds (the same thread owns the same elements for all chunks of a tile, so the
   // read-modify-write needs no synchronisation) and applies bias / activation / the bf16 copy after the last chunk.
   int kchunk;
+  // pair kernel, fp32-accurate mode with an error-free leading piece (see row_scale_exp_kernel): the A1 x B1 products go
+  // to the accumulator at TMEM columns [0, 256), the correction products to the one at [256, 512); the epilogue adds the
+  // two (round to nearest).  Both buffers form ONE accumulator stage, so the epilogue of a chunk does not overlap the
+  // next chunk's MMAs.
+  int exact_main;
+  // staged output pieces (Cbf, out_pieces == 3): leading piece aligned to the fixed exponent out_exp (operands known to lie
+  // in [-1, 1]) so that it can feed an exact-main product; PTK_NO_EXP: ordinary bf16 split
+  int out_exp;
 };
+#define PTK_NO_EXP (-100000)
 // piece indices of the term sequence; a run of `terms` entries ending at index 5 is used
 __device__ __constant__ int kPieceA[6] = {2, 1, 0, 1, 0, 0};
 __device__ __constant__ int kPieceB[6] = {0, 1, 2, 0, 1, 0};
@@ -437,6 +446,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kchunk = (p.kchunk > 0 && p.kchunk < k_blocks) ? p.kchunk : max(k_blocks, 1);
   const int n_chunks = max(1, (k_blocks + kchunk - 1) / kchunk);
+  const int n_acc = p.exact_main ? 1 : ACC_STAGES;   // exact_main: both TMEM buffers belong to one accumulator stage
   const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
   // Wave-quantisation fix: the units of the last, partially filled round are split into two 256 x 128 HALF units when
   // that fills the idle CTA pairs (e.g. 4096^2: 256 units on 74 pairs = 3 full rounds + 34 -> 68 half units, 3.5 rounds
@@ -522,6 +532,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+          const uint32_t d_corr = tmem_base + (uint32_t)BLOCK_N;   // exact_main: the correction products' accumulator
           const int kb_n = min(kchunk, k_blocks - ch * kchunk);
           const int n_stages = kb_n * p.terms;  // piece products of one k-block accumulate into the same tile
           for (int it = 0; it < n_stages; ++it) {
@@ -529,16 +540,20 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
             const uint32_t b_addr = smem_u32(smem_b + stage * P_B_BYTES);
+            // term order within a k-block: the correction products first, A1 x B1 last (kPieceA / kPieceB)
+            const bool to_corr = p.exact_main && (it % p.terms) != p.terms - 1;
+            const uint32_t d_use = to_corr ? d_corr : d_tmem;
+            const bool first = p.exact_main ? (to_corr ? it == 0 : it == p.terms - 1) : it == 0;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma_f16_2sm(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
-                           (it > 0 || k > 0) ? 1u : 0u);
+              umma_f16_2sm(d_use, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                           (!first || k > 0) ? 1u : 0u);
             }
             umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free again in BOTH CTAs
             if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);      // accumulator complete in both CTAs' TMEM
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
@@ -571,7 +586,15 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
           tmem_ld_32x32b_x32(taddr, r);
-          tmem_ld_wait();
+          if (p.exact_main) {
+            uint32_t r2[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            tmem_ld_wait();
+          }
           const long long col0 = (long long)ncol0 + c0;
           // Row-contiguous fast path (warp-uniform): tcgen05.ld hands every lane one ROW of the 32 x 32 block; going through
           // a shared-memory tile turns that into 128 contiguous bytes of one row per quarter warp, so every global
@@ -592,16 +615,26 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               for (int e = 0; e < 4; ++e) bb[e] = bias[colv + e];
             }
             const long long row_base = (long long)tm * 2 * BLOCK_M + (long long)crank * BLOCK_M + q * 32;
+            // the old values of all 8 row groups are requested before any of them is used (and before any store of this
+            // block, which the compiler could not prove disjoint): one memory round trip per 32 x 32 block, not eight
+            float4 old[8];
+            if (beta != 0.0f) {
 #pragma unroll
-            for (int rr = 0; rr < 32; rr += 4) {
+              for (int g = 0; g < 8; ++g) {
+                const long long grow = row_base + 4 * g + sub;
+                old[g] = grow < p.M ? __ldcg(reinterpret_cast<const float4*>(p.C + grow * p.sc0 + colv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int rr = 4 * g;
               const long long grow = row_base + rr + sub;
               if (grow < p.M) {
                 float4 v = *reinterpret_cast<const float4*>(tile + (rr + sub) * EPI_PITCH + cq);
                 float* dst = p.C + grow * p.sc0 + colv;
                 float vv[4] = {p.alpha * v.x, p.alpha * v.y, p.alpha * v.z, p.alpha * v.w};
                 if (beta != 0.0f) {
-                  const float4 o = *reinterpret_cast<const float4*>(dst);
-                  vv[0] += beta * o.x; vv[1] += beta * o.y; vv[2] += beta * o.z; vv[3] += beta * o.w;
+                  vv[0] += beta * old[g].x; vv[1] += beta * old[g].y; vv[2] += beta * old[g].z; vv[3] += beta * old[g].w;
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -611,6 +644,20 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 *reinterpret_cast<float4*>(dst) = make_float4(vv[0], vv[1], vv[2], vv[3]);
                 if (cbf) {
                   for (int pc = 0; pc < p.out_pieces; ++pc) {   // piece pc = bf16 of what the earlier pieces left over
+                    if (pc == 0 && p.out_exp != PTK_NO_EXP) {     // aligned leading piece (exact in bf16)
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float lead = scalbnf(rintf(scalbnf(vv[e], p.out_exp)), -p.out_exp);
+                        vv[e] -= lead;
+                        reinterpret_cast<float*>(&v)[e] = lead;
+                      }
+                      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                      uint2 pk;
+                      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                      *reinterpret_cast<uint2*>(cbf + ((long long)pc * p.cbf_rows + grow) * p.ldcbf + colv) = pk;
+                      continue;
+                    }
                     __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -637,7 +684,9 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                   *dst = x;
                   if (cbf) {
                     for (int pc = 0; pc < p.out_pieces; ++pc) {
-                      const __nv_bfloat16 b = __float2bfloat16_rn(x);
+                      const __nv_bfloat16 b = (pc == 0 && p.out_exp != PTK_NO_EXP)
+                                                  ? __float2bfloat16_rn(scalbnf(rintf(scalbnf(x, p.out_exp)), -p.out_exp))
+                                                  : __float2bfloat16_rn(x);
                       cbf[((long long)pc * p.cbf_rows + row) * p.ldcbf + col] = b;
                       x -= __bfloat162float(b);
                     }
@@ -650,7 +699,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);  // 8 arrivals (4 warps x 2 CTAs) free the accumulator
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -763,6 +812,100 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
   }
 }
 
+// ---- error-free leading piece (fp32-accurate mode, "exact main term") ---------------------------------------------------
+// The tensor core truncates when it adds into its fp32 accumulator; over a chain of MMAs that is a systematic shrink of the
+// result (~1e-7 per MMA of the chain, measured) which, unlike rounding noise, adds up coherently through chained layers.
+// Truncation cannot bite when every partial sum is exactly representable: the LEADING piece of each operand is therefore
+// taken as an integer multiple of a per-row power of two, x1 = rint(x * 2^s) * 2^-s with |rint| <= 128 (s = 6 - ilogb of
+// the row's largest magnitude; a row of A, a column of B).  All products A1[i,k] * B1[k,j] of one output element are then
+// integers (<= 2^14) on the common unit 2^-(s_i + s_j): up to 1024 of them sum exactly in fp32.  The remainder x - x1 is
+// exact in fp32 and is split into two ordinary bf16 pieces; the five correction products go to a second accumulator, whose
+// own truncation shrink is 2^-7 of the total.
+__global__ void __launch_bounds__(256) row_scale_exp_kernel(const float* __restrict__ src, long long sr, long long sc,
+                                                            long long R, long long Cc, int* __restrict__ sexp) {
+  const int lane = threadIdx.x & 31;
+  if (sc == 1 || sr != 1) {   // rows are (or might as well be) walked by a warp each
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < R; r += nwarps) {
+      float m = 0.0f;
+      for (long long c = lane; c < Cc; c += 32) m = fmaxf(m, fabsf(src[r * sr + c * sc]));
+#pragma unroll
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) sexp[r] = (m > 0.0f && m < __int_as_float(0x7f800000)) ? 6 - ilogbf(m) : 0;
+    }
+  } else {                    // unit stride ALONG r: consecutive threads take consecutive rows, every load coalesces
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
+      float m = 0.0f;
+      for (long long c = 0; c < Cc; ++c) m = fmaxf(m, fabsf(src[r + c * sc]));
+      sexp[r] = (m > 0.0f && m < __int_as_float(0x7f800000)) ? 6 - ilogbf(m) : 0;
+    }
+  }
+}
+
+// piece 0 = rint(x * 2^s[r]) * 2^-s[r] (exact in bf16), pieces 1, 2 = bf16 split of the exact remainder; same tiling and
+// output layout as split_bf16x3_kernel.  fixed_exp != INT_MIN: use that exponent for every row (operands known to lie in
+// [-1, 1], e.g. tanh outputs written by a previous product's epilogue) instead of sexp.
+__global__ void __launch_bounds__(256) split_aligned_kernel(const float* __restrict__ src, long long sr, long long sc,
+                                                            __nv_bfloat16* __restrict__ dst, long long ld, long long R,
+                                                            long long Cc, long long piece_rows, const int* __restrict__ sexp) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool col_fast = (sc == 1) || (sr != 1);
+  if (col_fast) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + ty + 8 * i, c = c0 + tx + 32 * h;
+        tile[ty + 8 * i][tx + 32 * h] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + tx + 32 * h, c = c0 + ty + 8 * i;
+        tile[tx + 32 * h][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    if (r < R && c < Cc) {
+      const int sx = sexp[r];
+      float v[2] = {tile[ty + 8 * i][2 * tx], (c + 1 < Cc) ? tile[ty + 8 * i][2 * tx + 1] : 0.0f};
+      __nv_bfloat16 pc[3][2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float lead = scalbnf(rintf(scalbnf(v[e], sx)), -sx);   // |rint| <= 128: exact in bf16; x - lead exact in fp32
+        pc[0][e] = __float2bfloat16_rn(lead);
+        float rem = v[e] - lead;
+        if (!(fabsf(v[e]) < __int_as_float(0x7f800000))) rem = 0.0f;  // inf / NaN ride in the leading piece only
+        pc[1][e] = __float2bfloat16_rn(rem);
+        rem -= __bfloat162float(pc[1][e]);
+        pc[2][e] = __float2bfloat16_rn(rem);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        __nv_bfloat16* d = dst + (k * piece_rows + r) * ld + c;
+        if (c + 1 < ld) {
+          __nv_bfloat162 pk;
+          pk.x = pc[k][0];
+          pk.y = pc[k][1];
+          *reinterpret_cast<__nv_bfloat162*>(d) = pk;
+        } else {
+          *d = pc[k][0];
+        }
+      }
+    }
+  }
+}
+
 ptk_status make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {pitch_elems * 2};
@@ -787,7 +930,17 @@ size_t gemm_tc_workspace(int64_t M, int64_t N, int64_t K) {
 
 size_t gemm_tc_split_workspace(int64_t M, int64_t N, int64_t K) {
   long long Kp = round_up(K, 8), Mp = round_up(M, 256), Np = round_up(N, 256);
-  return (size_t)(round_up(3 * Mp * Kp * 2, 256) + round_up(3 * Np * Kp * 2, 256) + 256);
+  return (size_t)(round_up(3 * Mp * Kp * 2, 256) + round_up(3 * Np * Kp * 2, 256) + round_up(4 * (M + N), 256) + 256);
+}
+
+// error-free leading pieces on/off for the fp32-accurate mode (PTK_GEMM_EXACT=0: plain bf16x3 split, one accumulator)
+static int exact_main_default() {
+  static int g = -1;
+  if (g < 0) {
+    const char* e = getenv("PTK_GEMM_EXACT");
+    g = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g;
 }
 
 static int g_cluster = -1;  // -1: read PTK_GEMM_CLUSTER once (default 2)
@@ -841,7 +994,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     g_split = (e && e[0] == '0') ? 0 : 1;
   }
   p.split_tail = g_split;
-  p.terms = 1; p.a_rows = 0; p.b_rows = 0; p.kchunk = 0; p.out_pieces = 1; p.cbf_rows = 0;
+  p.terms = 1; p.a_rows = 0; p.b_rows = 0; p.kchunk = 0; p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP;
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -878,27 +1031,42 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
 
 // accumulation chunk of the fp32-accurate modes: 8 k-blocks (K = 512) keeps the tensor core's truncation bias near 1e-6 of
 // the output scale; PTK_GEMM_KCHUNK=<k-blocks> overrides (0 = one chunk)
-static int split_kchunk(int64_t K) {
+static int split_kchunk(int64_t K, int exact) {
   static int g_kchunk = -1;
   if (g_kchunk < 0) {
     const char* e = getenv("PTK_GEMM_KCHUNK");
-    g_kchunk = e ? atoi(e) : 8;
-    if (g_kchunk < 0) g_kchunk = 8;
+    g_kchunk = e ? atoi(e) : -1;
   }
   const long long kb = (K + BLOCK_K - 1) / BLOCK_K;
-  return (g_kchunk > 0 && kb > g_kchunk + g_kchunk / 4) ? g_kchunk : 0;
+  if (exact) {
+    // 1024 products of integers <= 128 x 128 sum to at most 2^24: exactly representable; longer K goes in chunks of 16 k-blocks
+    const int c = g_kchunk > 0 ? std::min(g_kchunk, 16) : 16;
+    return kb > c ? c : 0;
+  }
+  const int c = g_kchunk >= 0 ? g_kchunk : 8;
+  return (c > 0 && kb > c + c / 4) ? c : 0;
 }
 
 // Operand staging on its own (so that an operand that does not change between calls is staged ONCE): dst = `pieces` (1 | 3)
 // bf16 matrices [R, Cc] stacked with a pitch of piece_rows rows, row pitch ld elements, from fp32 src[r*sr + c*sc].
 ptk_status stage_operand(const float* src, int64_t sr, int64_t sc, int64_t R, int64_t Cc, int pieces, void* dst, int64_t ld,
-                         int64_t piece_rows, cudaStream_t st) {
+                         int64_t piece_rows, int aligned, int* sexp, cudaStream_t st) {
   if (pieces != 1 && pieces != 3) return fail(PTK_ERR_ARG, "stage_operand: pieces must be 1 or 3");
+  if (aligned && (pieces != 3 || sexp == nullptr)) return fail(PTK_ERR_ARG, "stage_operand: aligned staging needs 3 pieces and the exponent scratch");
   if (ld % 8 != 0 || ld < Cc || ((uintptr_t)dst & 15) != 0) return fail(PTK_ERR_ARG, "stage_operand: pitch must be a multiple of 8 >= cols, base 16-byte aligned");
   if (R == 0 || Cc == 0) return PTK_OK;
   dim3 g((unsigned)((Cc + 63) / 64), (unsigned)((R + 63) / 64));
-  if (pieces == 1) convert_bf16_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc);
-  else split_bf16x3_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows);
+  if (pieces == 1) {
+    convert_bf16_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc);
+  } else if (aligned) {
+    const bool warp_rows = (sc == 1) || (sr != 1);
+    const long long thr = warp_rows ? R * 32 : R;
+    const unsigned gb = (unsigned)std::max<long long>(1, std::min<long long>((thr + 255) / 256, (long long)ptk::sm_count() * 16));
+    row_scale_exp_kernel<<<gb, 256, 0, st>>>(src, sr, sc, R, Cc, sexp);
+    split_aligned_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows, sexp);
+  } else {
+    split_bf16x3_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows);
+  }
   PTK_LAUNCH_CHECK("stage_operand");
   return PTK_OK;
 }
@@ -910,7 +1078,7 @@ ptk_status stage_operand(const float* src, int64_t sr, int64_t sc, int64_t R, in
 ptk_status gemm_tc_staged(int64_t M, int64_t N, int64_t K, float alpha, const void* A_stage, int64_t lda, int64_t a_rows,
                           const void* B_stage, int64_t ldb, int64_t b_rows, int terms, float beta, float* C, int64_t sc0,
                           int64_t sc1, const float* bias, int act, void* C_stage, int64_t ldc_stage, int64_t c_rows,
-                          int out_pieces, cudaStream_t st) {
+                          int out_pieces, int exact_main, int out_exp, cudaStream_t st) {
   if (M == 0 || N == 0) return PTK_OK;
   if (terms != 1 && terms != 3 && terms != 6) return fail(PTK_ERR_ARG, "gemm_tc_staged: terms must be 1, 3 or 6");
   if (M > 500000000LL || N > 500000000LL || K > 2147483647LL || K <= 0) return fail(PTK_ERR_ARG, "gemm_tc_staged: bad dims");
@@ -932,9 +1100,12 @@ ptk_status gemm_tc_staged(int64_t M, int64_t N, int64_t K, float alpha, const vo
   p.ldcbf = ldc_stage;
   p.out_pieces = C_stage ? out_pieces : 1;
   p.cbf_rows = c_rows;
+  p.exact_main = 0; p.out_exp = PTK_NO_EXP;
   p.split_tail = 1;
   p.terms = terms; p.a_rows = terms == 1 ? 0 : (int)a_rows; p.b_rows = terms == 1 ? 0 : (int)b_rows;
-  p.kchunk = terms == 1 ? 0 : split_kchunk(K);
+  p.exact_main = (terms != 1 && exact_main) ? 1 : 0;
+  p.out_exp = (C_stage && out_pieces == 3) ? out_exp : PTK_NO_EXP;
+  p.kchunk = terms == 1 ? 0 : split_kchunk(K, p.exact_main);
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
@@ -975,12 +1146,12 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   __nv_bfloat16* Abf = reinterpret_cast<__nv_bfloat16*>(w);
   __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(w + round_up(3 * Mp * Kp * 2, 256));
+  const int exact = exact_main_default();
   {
-    dim3 ga((unsigned)((K + 63) / 64), (unsigned)((M + 63) / 64));
-    split_bf16x3_kernel<<<ga, 256, 0, st>>>(A, sa0, sa1, Abf, Kp, M, K, Mp);
-    dim3 gb((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64));
-    split_bf16x3_kernel<<<gb, 256, 0, st>>>(B, sb1, sb0, Bbf, Kp, N, K, Np);  // B[K,N] -> Bt[N,K] pieces
-    PTK_LAUNCH_CHECK("split_bf16x3");
+    int* sexp = reinterpret_cast<int*>(w + round_up(3 * Mp * Kp * 2, 256) + round_up(3 * Np * Kp * 2, 256));
+    ptk_status ss;
+    if ((ss = stage_operand(A, sa0, sa1, M, K, 3, Abf, Kp, Mp, exact, sexp, st)) != PTK_OK) return ss;
+    if ((ss = stage_operand(B, sb1, sb0, N, K, 3, Bbf, Kp, Np, exact, sexp + M, st)) != PTK_OK) return ss;  // B[K,N] -> Bt[N,K]
   }
   CUtensorMap ta, tb, tbh;
   ptk_status s;
@@ -994,10 +1165,11 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Cbf = nullptr;
   p.ldcbf = 0;
-  p.out_pieces = 1; p.cbf_rows = 0;
+  p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP;
   p.split_tail = 1;
   p.terms = terms; p.a_rows = (int)Mp; p.b_rows = (int)Np;
-  p.kchunk = split_kchunk(K);
+  p.exact_main = exact;
+  p.kchunk = split_kchunk(K, exact);
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
@@ -1059,22 +1231,35 @@ extern "C" ptk_status ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double 
 
 extern "C" size_t ptk_stage_bytes(int64_t rows, int64_t cols, int pieces) {
   const long long ld = (cols + 7) / 8 * 8, pr = (rows + 255) / 256 * 256;
-  return (size_t)(pieces <= 1 ? rows : 3 * pr) * (size_t)ld * 2 + 256;
+  const size_t mats = (size_t)(pieces <= 1 ? rows : 3 * pr) * (size_t)ld * 2;
+  return (mats + 255) / 256 * 256 + (pieces <= 1 ? 0 : (size_t)rows * 4) + 256;   // + the per-row exponents of an aligned split
 }
 
 extern "C" ptk_status ptk_stage_operand(const void* src_f32, int64_t sr, int64_t sc, int64_t rows, int64_t cols, int pieces,
-                                        void* dst, int64_t ld, int64_t piece_rows, void* stream) {
+                                        int aligned, void* dst, int64_t ld, int64_t piece_rows, void* stream) {
   PTK_REQUIRE_INIT();
   if (src_f32 == nullptr || dst == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_stage_operand: null pointer");
-  return ptk::stage_operand((const float*)src_f32, sr, sc, rows, cols, pieces, dst, ld, piece_rows, (cudaStream_t)stream);
+  int* sexp = nullptr;
+  if (aligned) {
+    if (pieces != 3 || ld != (cols + 7) / 8 * 8 || piece_rows != (rows + 255) / 256 * 256)
+      return ptk::fail(PTK_ERR_ARG, "ptk_stage_operand: aligned staging uses the default pitch / piece pitch of ptk_stage_bytes");
+    const size_t mats = (size_t)(3 * piece_rows) * (size_t)ld * 2;
+    sexp = reinterpret_cast<int*>((char*)dst + (mats + 255) / 256 * 256);
+  }
+  return ptk::stage_operand((const float*)src_f32, sr, sc, rows, cols, pieces, dst, ld, piece_rows, aligned, sexp,
+                            (cudaStream_t)stream);
 }
 
 extern "C" ptk_status ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double alpha, const void* A_stage, int64_t lda,
                                          int64_t a_rows, const void* B_stage, int64_t ldb, int64_t b_rows, int terms,
                                          double beta, void* C, int64_t sc0, int64_t sc1, const void* bias, int act,
-                                         void* C_stage, int64_t ldc_stage, int64_t c_rows, int out_pieces, void* stream) {
+                                         void* C_stage, int64_t ldc_stage, int64_t c_rows, int out_pieces, int exact_main,
+                                         int out_exp, void* stream) {
   PTK_REQUIRE_INIT();
   if (A_stage == nullptr || B_stage == nullptr || C == nullptr) return ptk::fail(PTK_ERR_ARG, "ptk_gemm_tc_staged: null operand");
   return ptk::gemm_tc_staged(M, N, K, (float)alpha, A_stage, lda, a_rows, B_stage, ldb, b_rows, terms, (float)beta, (float*)C,
-                             sc0, sc1, (const float*)bias, act, C_stage, ldc_stage, c_rows, out_pieces, (cudaStream_t)stream);
+                             sc0, sc1, (const float*)bias, act, C_stage, ldc_stage, c_rows, out_pieces, exact_main,
+                             out_exp == PTK_STAGE_NO_EXP ? PTK_NO_EXP : out_exp, (cudaStream_t)stream);
 }
+
+extern "C" int ptk_gemm_exact_main_default(void) { return ptk::exact_main_default(); }

@@ -82,9 +82,11 @@ def mark_bf16_chains(steps):
     tc = (Dot22Node, GemmBiasActNode)
     producers = {o: st for st in steps for o in st.outs}
     for st in steps:
-        if isinstance(st.impl, tc) and st.impl.precision == 1:
+        if isinstance(st.impl, tc) and st.impl.dtype == "float32":
             src = producers.get(st.ins[0])
-            if src is not None and isinstance(src.impl, tc) and src.impl.precision == 1:
+            # bf16 mode: a bf16 copy; fp32-accurate mode: the three-piece split (used when the weights are resident)
+            if src is not None and isinstance(src.impl, tc) and src.impl.precision == st.impl.precision \
+                    and src.impl.dtype == "float32":
                 src.impl.emit_bf16 = True
     return steps
 

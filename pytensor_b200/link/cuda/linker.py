@@ -99,6 +99,7 @@ class CudaVM:
                     and last.is_contiguous()):
                 dev.to_device_async(a, out=last)
                 dev.synchronize()  # the host array is dropped from the cell below: the copy must have completed
+                dev.bump_version(last)   # same object, new content: staged copies of the old value are stale
                 t = last
             else:
                 t = dev.to_device(a)
@@ -124,6 +125,7 @@ class CudaVM:
                         and cur.is_contiguous():
                     dev.to_device_async(h, out=cur)
                     dev.synchronize()
+                    dev.bump_version(cur)
                     res[j] = cur
                 else:
                     res[j] = dev.to_device(h)
@@ -132,8 +134,10 @@ class CudaVM:
             same_layout = cur_ok and tuple(cur.shape) == tuple(src.shape) and cur.dtype == src.dtype
             if same_layout and cur.data_ptr() == src.data_ptr() and cur.stride() == src.stride():
                 res[j] = cur  # computed in place on the variable's buffer (destroy_map on a mutable input)
+                dev.bump_version(cur)
             elif same_layout and cur.untyped_storage().data_ptr() != src.untyped_storage().data_ptr():
                 dev.copy_strided(cur, src)
+                dev.bump_version(cur)
                 res[j] = cur
             else:  # new shape, or a view overlapping the old value: give the variable a new buffer
                 res[j] = dev.clone(src)

@@ -298,6 +298,18 @@ def lower_node(node, opts):
                                 f"{nx.CumOpNode.SUPPORTED} keep the declared output type")
         return nx.CumOpNode(op.axis, op.mode, x.type.dtype, name=str(op))
 
+    from pytensor.tensor.random.op import RandomVariable
+
+    if isinstance(op, RandomVariable):
+        from pytensor_b200.vm.nodes_random import DIST, RandomVariableNode
+        from pytensor.tensor.type_other import NoneTypeT
+
+        if op.name not in DIST or op.ndim_supp != 0 or len(node.inputs) - 2 != DIST[op.name][1]:
+            raise UnsupportedOp(f"{op}: random variable '{op.name}' has no device sampler (supported: {sorted(DIST)})")
+        if op.dtype not in ("float32", "float64", "int64", "int32", "int16", "int8", "uint8", "bool"):
+            raise UnsupportedOp(f"{op}: draws of dtype {op.dtype}")
+        return RandomVariableNode(op.name, op.dtype, bool(op.inplace), isinstance(node.inputs[1].type, NoneTypeT), name=str(op))
+
     if cname == "BatchedDot":
         dt = node.outputs[0].type.dtype
         if dt not in ("float32", "float64"):

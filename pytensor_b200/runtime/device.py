@@ -304,3 +304,26 @@ def to_host(t, sync: bool = True) -> np.ndarray:
 
 def synchronize() -> None:
     _lib.check(_lib.lib().ptk_sync_stream(stream_ptr()), "sync")
+
+
+def bump_version(t) -> None:
+    """Tell torch (and the VM's staged-operand cache, which keys on `Tensor._version`) that `t` was written through a raw
+    pointer (a libptk kernel or memcpy)."""
+    if isinstance(t, torch.Tensor) and not t.is_meta:
+        try:
+            torch.autograd.graph.increment_version(t)
+        except Exception:  # noqa: BLE001  (inference tensors)
+            pass
+
+
+class unmanaged:
+    """Context: allocations inside live outside any capture arena / measuring pass (persistent buffers)."""
+
+    def __enter__(self):
+        st = alloc_state
+        self._saved = (st.arena, st.measuring)
+        st.arena, st.measuring = None, False
+        return self
+
+    def __exit__(self, *a):
+        alloc_state.arena, alloc_state.measuring = self._saved

@@ -74,6 +74,8 @@ SIGNATURES = {
     "ptk_nonzero_workspace_bytes": (c_size_t, [c_int64]),
     "ptk_nonzero_count": (c_int, [c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "ptk_nonzero_fill": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ptk_random_fill": (c_int, [c_int, c_int, c_void_p, c_int64, ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_int64, c_void_p,
+                                c_int64, c_void_p, c_int64, c_void_p]),
     "ptk_arange": (c_int, [c_int, c_void_p, c_int64, c_double, c_double, c_int64, c_int64, c_void_p]),
     "ptk_argmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "ptk_cumop": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -90,10 +92,12 @@ SIGNATURES = {
     "ptk_gemm_tc_split": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                   c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ptk_stage_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "ptk_stage_operand": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+    "ptk_stage_operand": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64,
+                                  c_void_p]),
     "ptk_gemm_tc_staged": (c_int, [c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                    c_int, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
-                                   c_int, c_void_p]),
+                                   c_int, c_int, c_int, c_void_p]),
+    "ptk_gemm_exact_main_default": (c_int, []),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -122,12 +126,14 @@ class _TraceLib:
             return lambda: 148
         if name == "ptk_gemm_workspace_bytes":
             return lambda M, N, K, p: 2 * (M * K + N * K) + 1024
-        if name == "ptk_gemm_split_workspace_bytes":
-            return lambda M, N, K: 6 * ((M + 255) // 256 * 256 + (N + 255) // 256 * 256) * ((K + 7) // 8 * 8) + 1024
         if name == "ptk_put_rows_workspace_bytes":
             return lambda n_dst, n_idx: 4 * (n_dst + 1 + n_idx) + 64
         if name == "ptk_stage_bytes":
-            return lambda r, c, p: (r if p <= 1 else 3 * ((r + 255) // 256 * 256)) * ((c + 7) // 8 * 8) * 2 + 256
+            return lambda r, c, p: (r if p <= 1 else 3 * ((r + 255) // 256 * 256)) * ((c + 7) // 8 * 8) * 2 + 512 + 4 * r
+        if name == "ptk_gemm_exact_main_default":
+            return lambda: 1
+        if name == "ptk_gemm_split_workspace_bytes":
+            return lambda M, N, K: 6 * ((M + 255) // 256 * 256 + (N + 255) // 256 * 256) * ((K + 7) // 8 * 8) + 4 * (M + N) + 1024
         if name == "ptk_nonzero_workspace_bytes":
             return lambda n: 8 * ((n + 4095) // 4096 + 1)
         if name == "ptk_last_error":

@@ -37,7 +37,7 @@ def _scalar(v: Val) -> float:
     return float(np.asarray(v.host()).reshape(-1)[0])
 
 
-def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None, want_bf16=False):
+def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None, want_bf16=False, b_key=None):
     """C = alpha*A@B + beta*C (or act(A@B + bias) when bias/act given) through the C-ABI.
     Tensor-core path extras: `a_bf16` = an already staged bf16 copy of A (skips the staging pass); `want_bf16` returns a
     bf16 copy of C (torch.bfloat16 container) for the next layer, else None."""
@@ -49,6 +49,31 @@ def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None
     use_tc = precision == 1 and dtype == "float32" and min(M, N, K) >= TC_MIN_DIM
     code = _lib.DTYPE_CODE[dtype]
     st = dev.stream_ptr()
+    plan = tc_plan(dtype, precision, M, N, K) if b_key is not None else None
+    if plan is not None:
+        # resident weights: B comes from the staged-operand cache, only A is staged per call (or chained from the
+        # previous layer's epilogue in the bf16 mode)
+        pieces, terms = plan
+        Bst = staged_weight(b_key, B, pieces)
+        if Bst is not None:
+            if isinstance(a_bf16, Staged):
+                ok = (a_bf16.pieces, a_bf16.rows, a_bf16.cols, a_bf16.aligned) == (pieces, M, K, Bst.aligned)
+                Ast = a_bf16 if ok else stage_operand(A, pieces, aligned=Bst.aligned)
+            elif pieces == 1 and a_bf16 is not None and a_bf16.shape[0] == M and a_bf16.shape[1] >= K \
+                    and a_bf16.stride(1) == 1 and a_bf16.stride(0) % 8 == 0 and dev.ptr(a_bf16) % 16 == 0:
+                Ast = Staged.wrap(a_bf16, M, K)
+            else:
+                Ast = stage_operand(A, pieces, aligned=Bst.aligned)
+            ret = cst = None
+            if want_bf16 and pieces == 1:
+                ret = dev.empty_t((M, (N + 7) // 8 * 8), torch.bfloat16)
+                cst = Staged.wrap(ret, M, N)
+            elif want_bf16 and can_chain_pieces(act):
+                ret = cst = Staged(M, N, pieces, aligned=exact_main())   # the three-piece operand of the next product
+            gemm_staged(Ast, Bst, terms, alpha, beta, C, bias=bias, act=act, out=cst)
+            return ret
+    if isinstance(a_bf16, Staged):
+        a_bf16 = None   # (a chained three-piece operand is only usable together with a resident B)
     if use_tc:
         ws_bytes = int(L.ptk_gemm_workspace_bytes(M, N, K, 1))
         if dev.alloc_state.arena is not None or dev.alloc_state.measuring:
@@ -105,9 +130,19 @@ class Staged:
     """A matrix in the tensor-core kernel's operand layout: `pieces` (1 = bf16, 3 = bf16x3 split) K-major matrices
     [rows, cols] stacked with a pitch of `piece_rows` rows in one device buffer."""
 
-    __slots__ = ("buf", "rows", "cols", "ld", "piece_rows", "pieces")
+    __slots__ = ("buf", "rows", "cols", "ld", "piece_rows", "pieces", "in_graph", "aligned")
 
-    def __init__(self, rows, cols, pieces):
+    @classmethod
+    def wrap(cls, t: torch.Tensor, rows, cols):
+        """A caller-provided row-major bf16 matrix (pitch multiple of 8, 16-byte aligned) as a one-piece operand."""
+        st = cls.__new__(cls)
+        st.rows, st.cols, st.pieces, st.ld, st.piece_rows, st.buf, st.in_graph = int(rows), int(cols), 1, int(t.stride(0)), 0, t, False
+        st.aligned = False
+        return st
+
+    def __init__(self, rows, cols, pieces, aligned=False):
+        self.in_graph = False
+        self.aligned = bool(aligned) and int(pieces) == 3   # leading piece on a per-row power-of-two grid (exact main term)
         self.rows, self.cols, self.pieces = int(rows), int(cols), int(pieces)
         self.ld = (self.cols + 7) // 8 * 8
         self.piece_rows = (self.rows + 255) // 256 * 256
@@ -116,16 +151,26 @@ class Staged:
 
     @property
     def ptr(self):
+        if self.buf.dtype != torch.uint8:   # a caller-provided bf16 matrix used as is (already 16-byte aligned)
+            return dev.ptr(self.buf)
         return (dev.ptr(self.buf) + 255) & ~255
 
 
-def stage_operand(t: torch.Tensor, pieces: int, transposed: bool = False) -> Staged:
-    """fp32 matrix -> Staged (one kernel).  `transposed`: stage t^T — the B operand of A @ B is staged as B^T [N, K]."""
+def exact_main() -> bool:
+    """fp32-accurate products use error-free leading pieces (include/ptk.h) unless PTK_GEMM_EXACT=0."""
+    return bool(_lib.lib().ptk_gemm_exact_main_default())
+
+
+def stage_operand(t: torch.Tensor, pieces: int, transposed: bool = False, aligned: bool | None = None) -> Staged:
+    """fp32 matrix -> Staged.  `transposed`: stage t^T — the B operand of A @ B is staged as B^T [N, K].  `aligned`
+    (default: whatever the fp32-accurate mode uses): 3-piece split with the leading piece on a per-row power-of-two grid."""
     R, C = (t.shape[1], t.shape[0]) if transposed else (t.shape[0], t.shape[1])
     sr, sc = (t.stride(1), t.stride(0)) if transposed else (t.stride(0), t.stride(1))
-    st = Staged(R, C, pieces)
-    _lib.check(_lib.lib().ptk_stage_operand(dev.ptr(t), sr, sc, R, C, pieces, st.ptr, st.ld, st.piece_rows, dev.stream_ptr()),
-               "ptk_stage_operand")
+    if aligned is None:
+        aligned = pieces == 3 and exact_main()
+    st = Staged(R, C, pieces, aligned)
+    _lib.check(_lib.lib().ptk_stage_operand(dev.ptr(t), sr, sc, R, C, pieces, 1 if st.aligned else 0, st.ptr, st.ld,
+                                            st.piece_rows, dev.stream_ptr()), "ptk_stage_operand")
     return st
 
 
@@ -140,17 +185,74 @@ def tc_plan(dtype, precision, M, N, K):
     return None
 
 
+NO_EXP = -100000   # PTK_STAGE_NO_EXP
+
+
+def can_chain_pieces(act) -> bool:
+    """May a product's epilogue write the three-piece operand of the next fp32-accurate product?  With error-free leading
+    pieces only when the result is known to lie in [-1, 1] (tanh): the leading piece then sits on the fixed grid 2^-6."""
+    return (not exact_main()) or act == 1
+
+
 def gemm_staged(A: Staged, B: Staged, terms, alpha, beta, C, bias=None, act=0, out: Staged | None = None):
     """C = act(alpha * A @ B + beta * C + bias) from staged operands; `out` receives the staged pieces of the result."""
     M, K, N = A.rows, A.cols, B.rows
     if B.cols != K or tuple(C.shape) != (M, N):
         raise ValueError(f"gemm_staged: shape mismatch ({M},{K}) @ ({B.cols},{N}) -> {tuple(C.shape)}")
+    exact = 1 if (terms != 1 and A.aligned and B.aligned) else 0
+    out_exp = NO_EXP
+    if out is not None and out.pieces == 3 and out.aligned:
+        if act != 1:
+            raise ValueError("gemm_staged: an aligned three-piece output needs a bounded activation (tanh)")
+        out_exp = 6
     _lib.check(_lib.lib().ptk_gemm_tc_staged(M, N, K, float(alpha), A.ptr, A.ld, A.piece_rows, B.ptr, B.ld, B.piece_rows,
                                              int(terms), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
                                              dev.ptr(bias) if bias is not None else None, int(act),
                                              out.ptr if out is not None else None, out.ld if out is not None else 0,
                                              out.piece_rows if out is not None else 0, out.pieces if out is not None else 1,
-                                             dev.stream_ptr()), "ptk_gemm_tc_staged")
+                                             exact, out_exp, dev.stream_ptr()), "ptk_gemm_tc_staged")
+
+
+# ---- staged weights stay resident ---------------------------------------------------------------------------------------
+# A B operand whose content the VM knows to be unchanged (Val.key: graph constants, caller-owned device tensors that are the
+# same object at the same torch version as in the previous calls, device-resident shared variables between updates) is
+# staged ONCE and the staged copy is reused by every later call / graph capture; PTK_STAGE_CACHE=0 turns this off.
+STAGE_CACHE_ON = _os.environ.get("PTK_STAGE_CACHE", "1") != "0"
+STAGE_CACHE_BYTES = int(_os.environ.get("PTK_STAGE_CACHE_MB", "8192")) << 20
+_stage_cache: dict = {}   # (key, pieces, shape, strides) -> Staged   (insertion order = LRU order)
+_stage_cache_stats = {"hits": 0, "misses": 0, "bytes": 0}
+
+
+def staged_weight(key, t: torch.Tensor, pieces: int) -> Staged | None:
+    """The resident staged copy of B (as B^T) for content identity `key`, staging it on first sight; None = not cacheable."""
+    if key is None or not STAGE_CACHE_ON or _lib.TRACE_ONLY:
+        return None
+    ck = (key, pieces, tuple(t.shape), tuple(t.stride()))
+    st = _stage_cache.get(ck)
+    if st is not None:
+        _stage_cache[ck] = _stage_cache.pop(ck)  # most recently used last
+        _stage_cache_stats["hits"] += 1
+        st.in_graph = st.in_graph or dev.alloc_state.capturing
+        return st
+    _stage_cache_stats["misses"] += 1
+    with dev.unmanaged():          # persistent: outlives the call, never part of a capture arena
+        if dev.alloc_state.capturing:
+            # stage NOW on a side stream (the operand was complete before the capture began), not as a node of the graph
+            side = dev._side_stream()
+            with torch.cuda.stream(side):
+                st = stage_operand(t, pieces, transposed=True)
+            _lib.check(_lib.lib().ptk_sync_stream(side.cuda_stream), "sync")
+        else:
+            st = stage_operand(t, pieces, transposed=True)
+    st.in_graph = dev.alloc_state.capturing
+    _stage_cache[ck] = st
+    _stage_cache_stats["bytes"] += st.buf.numel()
+    if _stage_cache_stats["bytes"] > STAGE_CACHE_BYTES:
+        for old in [k for k, v in _stage_cache.items() if not v.in_graph and k != ck]:   # oldest first; buffers a captured
+            _stage_cache_stats["bytes"] -= _stage_cache.pop(old).buf.numel()             # graph reads are never dropped
+            if _stage_cache_stats["bytes"] <= STAGE_CACHE_BYTES:
+                break
+    return st
 
 
 class Dot22Node(Node):
@@ -170,7 +272,7 @@ class Dot22Node(Node):
                                                        dev.stream_ptr()), "memset")
             else:
                 aux = gemm(self.dtype, alpha, A, B, 0.0, out, self.precision, a_bf16=vals[0].aux,
-                           want_bf16=self.emit_bf16)
+                           want_bf16=self.emit_bf16, b_key=vals[1].key)
         return [Val(d=out, aux=aux)]
 
 
@@ -201,7 +303,7 @@ class GemmNode(Node):
                 else:
                     gemm(self.dtype, 0.0, out[:, :1], out[:1, :], beta, out, 0)
             else:
-                gemm(self.dtype, alpha, X, Y, beta, out, self.precision)
+                gemm(self.dtype, alpha, X, Y, beta, out, self.precision, b_key=y.key)
         return [Val(d=out)]
 
 
@@ -309,7 +411,7 @@ class GemmBiasActNode(Node):
             if A.shape[1] == 0:
                 raise NotImplementedError("fused bias epilogue with K == 0")
             aux = gemm(self.dtype, 1.0, A, B, 0.0, out, self.precision, bias=b1, act=self.act, a_bf16=vals[0].aux,
-                       want_bf16=self.emit_bf16)
+                       want_bf16=self.emit_bf16, b_key=vals[1].key)
             return [Val(d=out, aux=aux)]
         return [Val(d=out)]
 

@@ -35,7 +35,7 @@ class Node:
 
     # Nodes are plain data + caches of device handles; only the data is pickled (a lowered Program can be shipped to a
     # box that has torch + libptk but no host framework).
-    _TRANSIENT = ("_kernels", "_fn", "_const_cache", "_flag", "_plans")
+    _TRANSIENT = ("_kernels", "_fn", "_const_cache", "_flag", "_plans", "_occupancy")
 
     def __getstate__(self):
         d = dict(self.__dict__)
@@ -514,6 +514,7 @@ class ElemwiseReduceNode(Node):
         self.prog = ScalarProgram(list(p.in_dtypes), [p.out_dtypes[k] for k in order], list(p.consts), list(p.insts),
                                   [p.outputs[k] for k in order])
         self._kernels = {}
+        self._occupancy = {}
 
     def _unfused(self, vals):
         outs = self.ew.run(vals)
@@ -573,7 +574,15 @@ class ElemwiseReduceNode(Node):
         if any(m != 1 for m in col_modes[len(ins):]):
             return self._unfused_given(vals, ins, outs)
         sms = _lib.sm_count()
-        tpr = 256 if cols >= 1024 else 32
+        if cols >= (1 << 31):
+            return self._unfused_given(vals, ins, outs)   # the fused kernel walks a row with 32-bit vector indices
+        # threads per row: more elements per thread amortise the per-row reduction (shuffles, shared memory, barriers)
+        # — 128 when that still leaves at least 4 row blocks per SM, the full CTA for long rows of short matrices
+        tpr = 32 if cols < 1024 else (128 if (cols < 16384 and rows >= sms * 8) else 256)
+        import os as _os
+
+        if _os.environ.get("PTK_K3_TPR"):   # developer A/B switch
+            tpr = int(_os.environ["PTK_K3_TPR"])
         rows_per_block = 256 // tpr
         row_blocks = (rows + rows_per_block - 1) // rows_per_block
         if row_blocks < sms:  # too few rows to fill the GPU with one CTA-row mapping: keep the two-kernel path
@@ -596,7 +605,19 @@ class ElemwiseReduceNode(Node):
         args += [c_longlong(ksts[j][0]) for j in range(len(ins))]
         args += [c_longlong(ksts[len(ins) + self.order[k]][0]) for k in stored]
         args += [c_longlong(rows), c_longlong(cols), c_int(1)]
-        gx = min(row_blocks, sms * 16)
+        # persistent CTAs: exactly as many as are resident at once, each striding over the row blocks — the prologue is
+        # paid once per CTA, and with the blocks dealt round-robin every SM ends up within one row block of the average
+        if getattr(self, "_occupancy", None) is None:   # (unpickled programs)
+            self._occupancy = {}
+        occ = self._occupancy.get(key)
+        if occ is None:
+            nb = ctypes.c_int(0)
+            if _lib.TRACE_ONLY:
+                nb.value = 4
+            else:
+                _lib.check(_lib.lib().ptk_func_max_active_blocks(fn, 256, 0, ctypes.byref(nb)), "occupancy")
+            occ = self._occupancy[key] = max(1, nb.value)
+        gx = min(row_blocks, sms * occ)
         jit.launch(fn, (gx, 1), (256,), jit.KernelArgs(args), 0, dev.stream_ptr())
         res = [Val(d=o) if o is not None else None for o in outs]
         if not self.store_reduced_input:

@@ -61,10 +61,16 @@ class ScanMatmulRecurrenceNode(Node):
             pieces, terms = plan
             Wst = nblas.stage_operand(W, pieces, transposed=True)
             cur = nblas.stage_operand(out[(pos - 1) % S], pieces)
-            nxt = nblas.Staged(M, N, pieces)
+            # the epilogue writes the next step's operand when it can: always in the bf16 mode; in the fp32-accurate mode
+            # with error-free leading pieces only for a bounded activation (tanh) — otherwise one staging pass per step
+            chain = pieces == 1 or nblas.can_chain_pieces(self.act)
+            nxt = nblas.Staged(M, N, pieces, aligned=cur.aligned) if chain else None
             for _ in range(n_steps):
                 nblas.gemm_staged(cur, Wst, terms, 1.0, 0.0, out[pos], bias=bias, act=self.act, out=nxt)
-                cur, nxt = nxt, cur
+                if chain:
+                    cur, nxt = nxt, cur
+                else:
+                    cur = nblas.stage_operand(out[pos], pieces)
                 pos = (pos + 1) % S
         else:
             for _ in range(n_steps):

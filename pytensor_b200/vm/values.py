@@ -16,12 +16,16 @@ from ..runtime import device as dev
 
 
 class Val:
-    __slots__ = ("h", "d", "aux")
+    __slots__ = ("h", "d", "aux", "key")
 
-    def __init__(self, h=None, d=None, aux=None):
+    def __init__(self, h=None, d=None, aux=None, key=None):
         self.h = h
         self.d = d
         self.aux = aux  # optional device-side companion of `d` (e.g. the bf16 copy a tensor-core GEMM emitted)
+        # identity of the CONTENT when the VM knows it cannot have changed since it last saw this key (a graph constant;
+        # a caller-owned device tensor that is the same object at the same torch version as in the previous calls):
+        # lets a tensor-core GEMM reuse the staged copy of a weight matrix instead of re-staging it (nodes_blas.py)
+        self.key = key
 
     # ---- metadata without forcing a transfer ----
     @property
@@ -76,4 +80,6 @@ def wrap(x) -> Val:
         if x.is_cuda or x.is_meta:
             return Val(d=x)
         return Val(h=x.numpy())
+    if isinstance(x, np.random.Generator):
+        return Val(h=x)   # RNG state stays a host object (vm/nodes_random.py)
     return Val(h=np.asarray(x))

@@ -135,6 +135,17 @@ class Program:
         self.stream_of = stream_of
         self.n_streams = max(stream_of) + 1 if stream_of else 1
 
+    def weight_inputs(self):
+        """{position in `inputs`: slot} of the program inputs (and the set of constant slots) that some GEMM node reads
+        directly as its B operand — the candidates for the staged-operand cache (nodes_blas.staged_weight)."""
+        if not hasattr(self, "_weight_inputs"):
+            b_pos = {"Dot22Node": 1, "GemmBiasActNode": 1, "GemmNode": 3}
+            slots = {st.ins[b_pos[type(st.impl).__name__]] for st in self.steps
+                     if type(st.impl).__name__ in b_pos and len(st.ins) > b_pos[type(st.impl).__name__]}
+            self._weight_inputs = ({k: s for k, s in enumerate(self.inputs) if s in slots},
+                                   {s for s in self.constants if s in slots})
+        return self._weight_inputs
+
     def streamable(self):
         """True when every step is row-independent along axis 0: fused Elemwise over non-broadcast operands, and
         reductions that keep axis 0.  Such a program can be run chunk by chunk along axis 0, which lets the executor
@@ -250,6 +261,12 @@ class Executor:
         self.vals = [None] * program.n_slots
         for s, arr in program.constants.items():
             self.vals[s] = Val(h=np.asarray(arr))
+        w_in, w_const = program.weight_inputs()
+        for s in w_const:
+            self.vals[s].key = ("const", id(program), s)   # a graph constant never changes: its staged copy stays resident
+        self._w_in = w_in
+        self._w_track = {}    # input position -> [tensor object (strong ref), torch version, identical calls in a row, volatile]
+        self._w_keys = {}     # input position -> content key of THIS call (stable inputs only)
         self.position_of_error = -1
         self.time_nodes = False
         n = max([len(program.steps)] + [st.origin + 1 for st in program.steps])
@@ -273,11 +290,50 @@ class Executor:
                 if not x.is_cuda:
                     return None
                 sig.append(("d", x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype))
+            elif isinstance(x, np.random.Generator):
+                return None   # random draws are keyed per call: never a CUDA graph
             else:
                 a = np.asarray(x)
                 small = tuple(a.reshape(-1).tolist()) if a.size <= 8 else None
                 sig.append(("h", a.shape, a.dtype.str, small))
         return tuple(sig)
+
+    def _track_weights(self, inputs):
+        """Which B operands of this call are KNOWN to hold what they held on the previous calls: the same caller-owned
+        torch tensor object (kept alive here, so its address cannot be recycled) at the same `Tensor._version` for the
+        third call in a row.  A tensor whose version ever moves between calls is treated as volatile from then on
+        (training-style in-place updates: staging it inside the graph is the right thing).  Returns the keys as a
+        hashable tuple — part of the graph signature, because a graph captured over a resident staged copy must only be
+        replayed for exactly that content."""
+        keys = self._w_keys
+        keys.clear()
+        for k in self._w_in:
+            x = inputs[k]
+            tr = self._w_track.get(k)
+            if not hasattr(x, "is_cuda") or not x.is_cuda:
+                if tr is not None:
+                    self._w_track.pop(k)
+                continue
+            v = x._version
+            if tr is None or tr[0] is not x:
+                self._w_track[k] = [x, v, 0, tr[3] if tr is not None and tr[0] is x else False]
+                continue
+            if tr[1] != v:
+                tr[1], tr[2], tr[3] = v, 0, True
+                continue
+            tr[2] += 1
+            if tr[2] >= 2 and not tr[3]:
+                keys[k] = ("in", id(x), v)
+        return tuple(sorted(keys.items())) if keys else ()
+
+    def _wrap_inputs(self, inputs):
+        vals = self.vals
+        keys = self._w_keys
+        for k, (s, x) in enumerate(zip(self.program.inputs, inputs)):
+            v = wrap(x)
+            if keys and k in keys and v.key is None:
+                v.key = keys[k]
+            vals[s] = v
 
     def run(self, inputs):
         """Outermost executors own the error-word sink of the call; nested ones (OpFromGraph, Scan bodies, pipeline
@@ -301,6 +357,7 @@ class Executor:
         from ..runtime import lib as _lib
 
         self.last_from_graph = False
+        wkeys = self._track_weights(inputs) if self._w_in else ()
         if (not self.use_graph or _lib.TRACE_ONLY or self.time_nodes or self.event_log is not None
                 or dev.alloc_state.capturing or dev.alloc_state.measuring):
             return self._run_eager(inputs)
@@ -312,19 +369,21 @@ class Executor:
         # metadata cannot change under us) -> skip building the signature
         ids = tuple(map(id, inputs))
         hit = self._id_cache.get(ids)
-        if hit is not None and hit[1].stage == 2:
+        if hit is not None and hit[1].stage == 2 and hit[2] == wkeys:
             e = hit[1]
             sig = None
         else:
             sig = self._signature(inputs)
             if sig is None:
                 return self._run_eager(inputs)
+            if wkeys:
+                sig = sig + (("resident", wkeys),)   # graphs over resident staged weights are content-specific
             e = self._graphs.get(sig)
             if e is not None and e.stage == 2 and all(
                     (hasattr(x, "is_cuda") or np.asarray(x).size > 8) for x in inputs):
                 if len(self._id_cache) > 16:
                     self._id_cache.clear()
-                self._id_cache[ids] = (list(inputs), e)  # strong refs keep the ids from being recycled
+                self._id_cache[ids] = (list(inputs), e, wkeys)  # strong refs keep the ids from being recycled
         if e is None:
             if len(self._graphs) >= self.MAX_GRAPHS:
                 self._graph_misses += 1
@@ -534,8 +593,7 @@ class Executor:
             self._side_streams.append(torch.cuda.Stream())
         streams = [main] + self._side_streams[: p.n_streams - 1]
         vals = self.vals
-        for s, x in zip(p.inputs, inputs):
-            vals[s] = wrap(x)
+        self._wrap_inputs(inputs)
         fork = torch.cuda.Event()
         fork.record(main)
         for sd in streams[1:]:
@@ -575,8 +633,7 @@ class Executor:
     def _run_eager(self, inputs):
         p = self.program
         vals = self.vals
-        for s, x in zip(p.inputs, inputs):
-            vals[s] = wrap(x)
+        self._wrap_inputs(inputs)
         timing = self.time_nodes
         for i, st in enumerate(p.steps):
             try:
@@ -628,7 +685,9 @@ def outputs_to_host(out_vals, device_outputs=False, copy_device=False, sink=None
     res = []
     pending = []
     for v in out_vals:
-        if v.h is not None and v.d is None:
+        if isinstance(v.h, np.random.Generator):
+            res.append(v.h)   # the advanced generator of a RandomVariable node goes back as the object it is
+        elif v.h is not None and v.d is None:
             # host-only values (shape vectors ...) are cached inside the VM: hand out a fresh object per call.  The
             # chunked host pipeline's results (aux == "fresh": page-locked arrays it filled for THIS call) already are.
             res.append(np.asarray(v.h) if isinstance(v.aux, str) and v.aux == "fresh" else np.array(v.h, copy=True))

@@ -40,9 +40,10 @@ for M, N, K in [(4096, 4096, 4096), (2048, 2048, 8192), (512, 768, 320), (2500, 
     d = (C.double() - ref)
     err = (d.abs().max() / ref.abs().max()).item()
     bias = (d.mean() / ref.abs().mean()).item()
+    shrink = ((d * ref).sum() / (ref * ref).sum()).item()   # least-squares slope of the error against the exact result
     sg = torch.matmul(A, B)  # cuBLAS sgemm for scale: what a RN fp32 GEMM gets
     torch.backends.cuda.matmul.allow_tf32 = False
     err_sg = ((sg.double() - ref).abs().max() / ref.abs().max()).item()
     print(f"kchunk={os.environ.get('PTK_GEMM_KCHUNK', 'default')} terms={terms} M={M} N={N} K={K}: {ms*1e3:8.1f} us "
-          f"{2*M*N*K/ms/1e9:6.0f} TF/s(fp32-equiv)  max err/scale {err:.2e} (cuBLAS fp32: {err_sg:.2e})  mean signed err {bias:+.1e}",
+          f"{2*M*N*K/ms/1e9:6.0f} TF/s(fp32-equiv)  max err/scale {err:.2e} (cuBLAS fp32: {err_sg:.2e})  mean signed err {bias:+.1e}  shrink {shrink:+.2e}  exact={os.environ.get('PTK_GEMM_EXACT', '1')}",
           flush=True)

@@ -51,6 +51,7 @@ template <typename T, int N> static inline PVec<T, N> ptk_ldv(const T* p) {
 template <typename T, int N> static inline void ptk_stv(T* p, const PVec<T, N>& v) {
   emu_check_align(p, sizeof(T) * N); std::memcpy(p, &v, sizeof(v));
 }
+template <typename T, int N> static inline PVec<T, N> ptk_ldv_pin(const T* p) { return ptk_ldv<T, N>(p); }
 """
 
 

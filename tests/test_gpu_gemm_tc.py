@@ -126,3 +126,45 @@ def test_three_term_split_meets_the_1e5_bar(gpu, monkeypatch):
     monkeypatch.setattr(nodes_blas, "FP32_MODE", "simt")
     f2 = pytensor.function([x, y], pt.dot(x, y), mode="CUDA")
     assert _scale_err(f2(xv, yv), ref) < 1e-5
+
+
+# ---- resident staged weights (nodes_blas.staged_weight, Executor._track_weights) ------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_resident_weights_follow_the_tensor_version(gpu, precision):
+    """A weight matrix handed over as the same device tensor object at the same torch version is staged once and the staged
+    copy stays resident (also inside the captured graph); an in-place change through torch, or another tensor object, must be
+    seen by the very next call.  Constants are resident from the first call."""
+    import torch
+
+    from pytensor_b200.link.cuda import cuda_mode
+    from pytensor_b200.runtime import device as dev
+    from pytensor_b200.vm import nodes_blas
+
+    pytensor.config.floatX = "float32"
+    rng = np.random.default_rng(46)
+    x, W1, W2, b = pt.fmatrix("x"), pt.fmatrix("W1"), pt.fmatrix("W2"), pt.fvector("b")
+    Wc = (rng.standard_normal((384, 256)) / 20).astype("float32")
+    out = pt.dot(pt.tanh(pt.dot(pt.tanh(pt.dot(x, W1) + b), W2)), pt.constant(Wc))
+    f = pytensor.function([x, W1, W2, b], out, mode=cuda_mode(device_outputs=True, gemm_precision=precision), trust_input=True)
+    f_ref = pytensor.function([x, W1, W2, b], out, mode="CVM")
+    xv = rng.standard_normal((300, 320)).astype("float32")
+    W1v = (rng.standard_normal((320, 512)) / 18).astype("float32")
+    W2v = (rng.standard_normal((512, 384)) / 22).astype("float32")
+    bv = (rng.standard_normal(512) * 0.1).astype("float32")
+    tol = dict(rtol=1e-5, atol=1e-5) if precision == "fp32" else dict(rtol=0, atol=2e-2)
+    d = [dev.to_device(v) for v in (xv, W1v, W2v, bv)]
+    h0 = nodes_blas._stage_cache_stats["hits"]
+    for call in range(7):   # eager+measure, capture, (keys appear) measure, capture, replays
+        np.testing.assert_allclose(dev.to_host(f(*d)), f_ref(xv, W1v, W2v, bv), **tol)
+    assert nodes_blas._stage_cache_stats["hits"] > h0, "weights were never served from the resident cache"
+    assert f.vm.executor.last_from_graph
+    # in-place change through torch: version moves, the next call must see the new values
+    d[1].mul_(0.5)
+    torch.cuda.synchronize()
+    for call in range(4):
+        np.testing.assert_allclose(dev.to_host(f(*d)), f_ref(xv, W1v * np.float32(0.5), W2v, bv), **tol)
+    # another tensor object of the same shape
+    W2b = (W2v * np.float32(-1.0)).astype("float32")
+    d[2] = dev.to_device(W2b)
+    for call in range(4):
+        np.testing.assert_allclose(dev.to_host(f(*d)), f_ref(xv, W1v * np.float32(0.5), W2b, bv), **tol)

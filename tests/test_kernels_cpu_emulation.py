@@ -188,7 +188,8 @@ from pytensor_b200.codegen import careduce as cg_red  # noqa: E402
 
 
 @pytest.mark.parametrize("rows,cols,tpr,vw,store", [(9, 64, 32, 4, True), (3, 1024, 256, 4, True), (10, 70, 32, 1, True),
-                                                     (5, 260, 32, 4, False), (2, 2052, 256, 4, True)])
+                                                     (5, 260, 32, 4, False), (2, 2052, 256, 4, True), (5, 2060, 128, 4, True),
+                                                     (7, 1024, 64, 4, False)])
 def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store):
     """The bench's dominant kernel shape (gen_row_kernel): map over (rows, cols), store the map result (or not), reduce each
     row with fp64 accumulation — warp-shuffle tree, cross-warp combine through shared memory for TPR = 256, scalar tail for
@@ -209,7 +210,8 @@ def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store):
     args = [_ptr(a), _ptr(b), _ptr(c)] + ([_ptr(e)] if store else []) + [_ptr(r), c_longlong(cols), c_longlong(1), c_longlong(cols)] \
         + ([c_longlong(cols)] if store else []) + [c_longlong(rows), c_longlong(cols), c_int(1)]
     rows_per_block = 256 // tpr
-    k.launch(((rows + rows_per_block - 1) // rows_per_block, 1), 256, args)
+    # fewer CTAs than row blocks: the persistent launch (CTAs stride over the row blocks) is what the VM uses
+    k.launch((min(2, (rows + rows_per_block - 1) // rows_per_block), 1), 256, args)
     expect = np.tanh(a * b[:, None] + c)
     if store:
         np.testing.assert_allclose(e, expect, rtol=2e-6, atol=1e-7)
@@ -428,3 +430,52 @@ def test_nonzero_count_scan_fill_kernels(tmp_path, n, density, misalign):
                            "nonzero_fill_kernel", tmp_path, threaded=True)
         k.launch(min(tiles, 2), 256, [_ptr(mask), ctypes.c_longlong(n), _ptr(ws), ctypes.c_longlong(tiles), _ptr(out)])
         np.testing.assert_array_equal(out[:expect.size], expect)
+
+
+# ---- error-free leading pieces of the fp32-accurate GEMM (row_scale_exp_kernel / split_aligned_kernel, ptk_gemm_tc.cu) ------
+BF16_SHIM = r"""
+#include <cmath>
+struct __nv_bfloat16 { unsigned short u; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  unsigned int b; std::memcpy(&b, &f, 4);
+  if ((b & 0x7fffffffu) > 0x7f800000u) { __nv_bfloat16 n; n.u = (unsigned short)((b >> 16) | 0x40); return n; }
+  b += 0x7fffu + ((b >> 16) & 1u);   // round to nearest even on the dropped 16 bits
+  __nv_bfloat16 r; r.u = (unsigned short)(b >> 16); return r;
+}
+static inline float __bfloat162float(__nv_bfloat16 h) { unsigned int b = (unsigned int)h.u << 16; float f; std::memcpy(&f, &b, 4); return f; }
+"""
+
+
+@pytest.mark.parametrize("R,Cc,row_major", [(70, 130, True), (130, 70, False), (64, 64, True), (5, 9, False)])
+def test_aligned_three_piece_split_is_exact_and_on_the_row_grid(tmp_path, R, Cc, row_major):
+    """x = x1 + x2 + x3 to 2^-23 of the row's largest magnitude; x1 * 2^s is an integer of magnitude <= 128 with
+    s = 6 - ilogb(row max), so that the A1 x B1 products of a dot product are integers on one common unit."""
+    rng = np.random.default_rng(R * 1000 + Cc)
+    x = (rng.standard_normal((R, Cc)) * np.exp(rng.uniform(-6, 6, (R, 1)))).astype(np.float32)
+    x[1 % R, :] = 0.0                       # an all-zero row
+    x[2 % R, 3 % Cc] = 1e-30                # tiny next to the row maximum
+    src = np.ascontiguousarray(x if row_major else x.T)   # the kernel reads src[r * sr + c * sc]
+    sr, sc = (Cc, 1) if row_major else (1, R)
+    text = open(os.path.join(CSRC, "ptk_gemm_tc.cu")).read()
+    assert "row_scale_exp_kernel" in text
+    sexp = np.full(R, -99, dtype=np.int32)
+    k1 = EmulatedKernel(BF16_SHIM + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "row_scale_exp_kernel"),
+                        "row_scale_exp_kernel", tmp_path, threaded=True)
+    k1.launch(2, 256, [_ptr(src), c_longlong(sr), c_longlong(sc), c_longlong(R), c_longlong(Cc), _ptr(sexp)])
+    rowmax = np.abs(x).max(axis=1)
+    expect_s = np.where(rowmax > 0, 6 - np.floor(np.log2(np.where(rowmax > 0, rowmax, 1.0))).astype(np.int64), 0)
+    np.testing.assert_array_equal(sexp, expect_s)
+    ld, pr = (Cc + 7) // 8 * 8, (R + 255) // 256 * 256
+    dst = np.zeros((3 * pr, ld), dtype=np.uint16)
+    k2 = EmulatedKernel(BF16_SHIM + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "split_aligned_kernel"),
+                        "split_aligned_kernel", tmp_path, threaded=True)
+    k2.launch(((Cc + 63) // 64, (R + 63) // 64), 256, [_ptr(src), c_longlong(sr), c_longlong(sc), _ptr(dst), c_longlong(ld),
+                                                     c_longlong(R), c_longlong(Cc), c_longlong(pr), _ptr(sexp)])
+    pieces = [(dst[k * pr:k * pr + R, :Cc].astype(np.uint32) << 16).view(np.float32).astype(np.float64) for k in range(3)]
+    lead_units = pieces[0] * np.exp2(sexp.astype(np.float64))[:, None]
+    assert np.all(lead_units == np.rint(lead_units)) and np.abs(lead_units).max() <= 128
+    err = np.abs(pieces[0] + pieces[1] + pieces[2] - x.astype(np.float64))
+    assert np.all(err <= np.maximum(rowmax[:, None].astype(np.float64) * 2.0 ** -23, 1e-45))
+    # every product of two leading pieces is an integer on the unit 2^-(s_i + s_j): 1024 of them stay below 2^24
+    assert 128 * 128 * 1024 <= 2 ** 24
