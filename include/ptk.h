@@ -195,16 +195,17 @@ ptk_status   ptk_gemm_tc_split(int64_t M, int64_t N, int64_t K, double alpha, co
  *     row pitch ld (multiple of 8, >= cols), piece i at rows [i*piece_rows, ...); dst >= ptk_stage_bytes(rows, cols, pieces)
  *     with ld = round_up(cols, 8), piece_rows = round_up(rows, 256).  For the B operand of C = A @ B stage B^T:
  *     rows = N, cols = K, sr = B's column stride, sc = B's row stride.
- *     aligned != 0 (3 pieces, default pitches): the LEADING piece of every row is an integer multiple (|.| <= 128) of a
+ *     aligned != 0 (3 pieces, default pitches): the LEADING piece of every row is an integer multiple (|.| <= 2^b, b from `cols`) of a
  *     per-row power of two, so that the A1 x B1 products of a dot product accumulate EXACTLY in the tensor core's fp32
  *     accumulator (which truncates otherwise: a systematic shrink of ~1e-7 per MMA of the accumulation chain) — the
  *     operand layout ptk_gemm_tc_staged's exact_main mode expects for both A and B.
  *   ptk_gemm_tc_staged: C = act(alpha * A @ B + beta * C + bias[N]) from staged A [M,K] / B^T [N,K]; terms 1 (bf16
  *     operands) | 3 | 6 (fp32-accurate, see ptk_gemm_tc_split; 3 and 6 need 3-piece operands).  exact_main != 0 (both
- *     operands staged `aligned`): A1 x B1 accumulates in its own TMEM accumulator, exactly, in chunks of K <= 1024; the
+ *     operands staged `aligned`): A1 x B1 accumulates in its own TMEM accumulator — exactly while its partial sums stay below
+ *     2^24 units (always for K <= 1024; see ptk_gemm_tc.cu lead_bits_for), in chunks only beyond K = 16384; the
  *     correction products in a second one; the epilogue adds them with round-to-nearest.  C_stage (optional) receives
  *     out_pieces (1 | 3) staged pieces of the result [M,N] (pitch ldc_stage, piece pitch c_rows); out_exp != PTK_STAGE_NO_EXP
- *     aligns the leading output piece to that fixed exponent (results known to lie in [-1, 1], e.g. tanh: out_exp = 6),
+ *     aligns the leading output piece to that fixed exponent (results known to lie in [-1, 1], e.g. tanh),
  *     which makes the pieces a valid `aligned` A operand of a following exact_main product.
  *   ptk_gemm_exact_main_default: 1 unless PTK_GEMM_EXACT=0 — what ptk_gemm_tc_split uses. */
 #define PTK_STAGE_NO_EXP (-100000)
@@ -216,6 +217,9 @@ ptk_status   ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double alpha, c
                       int64_t sc1, const void* bias, int act, void* C_stage, int64_t ldc_stage, int64_t c_rows,
                       int out_pieces, int exact_main, int out_exp, void* stream);
 int          ptk_gemm_exact_main_default(void);
+/* Width b of the aligned leading piece for a contraction of length K (|leading integer| <= 2^b; 7 today for every K);
+ * out_exp of a chained tanh epilogue feeding a product of contraction length K' is ptk_gemm_lead_bits(K') - 1. */
+int          ptk_gemm_lead_bits(int64_t K);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

@@ -68,12 +68,22 @@ def _block_reduce_code(tpr: int) -> str:
 """
 
 
+def _k3_pipeline() -> str:
+    """How the row kernel keeps memory busy while the scalar bodies run: "none" (occupancy only: 40 registers, 6 CTAs per SM),
+    "l2" (same, plus an L2 prefetch of the next trip), "regs" (register software pipeline with pinned loads: 64-68
+    registers, 3-4 CTAs per SM — measured SLOWER on cfg2, 43.5-44.7 us vs 39.1 us: the long dependent scalar chains need the
+    warps more than the loads need the head start).  PTK_K3_PIPE overrides."""
+    import os
+
+    return os.environ.get("PTK_K3_PIPE", "none")
+
+
 def _k3_min_blocks() -> int:
     """CTAs per SM the row kernel is compiled for (register cap 65536 / (256 * n)): 4 leaves 64 registers — enough for
     the two-trip software pipeline of a 2-input Composite with a couple of spilled words; PTK_K3_MINB overrides (A/B)."""
     import os
 
-    return int(os.environ.get("PTK_K3_MINB", "4"))
+    return int(os.environ.get("PTK_K3_MINB", {"regs": "4", "l2": "6"}.get(_k3_pipeline(), "1")))
 
 
 def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: tuple, red_op: str, acc_dtype: str,
@@ -152,6 +162,75 @@ def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: 
     next_row_ptrs = "\n".join(f"            const {CTYPE[prog.in_dtypes[k]]}* z{k} = pi{k} + r2 * rsi{k};" for k in vec_in)
     advance = "\n".join(f"          vpa{k} = vna{k}; vpb{k} = vnb{k};" for k in vec_in)
 
+    pipe = _k3_pipeline()
+    if pipe == "regs":
+        main_loop = f"""      int cv = cv_lo + lane_in_row;
+      // Software pipeline over trips of two vectors: the (pinned) loads of trip t+1 are issued before trip t is computed,
+      // and the last trip of a row issues the first trip of this thread's NEXT row, so the memory system always has a
+      // trip in flight per thread while the scalar bodies run.
+      if (cv + TPR < cv_hi) {{
+        if (!primed) {{
+{pin_loads('p', 'q', 'cv * VW', '(cv + TPR) * VW')}
+        }}
+        primed = false;
+        for (;;) {{
+          const int nx = cv + 2 * TPR;
+          const bool more = nx + TPR < cv_hi;
+          const long long r2 = r + (long long)gridDim.x * {rows_per_block};
+          if (more) {{
+{pin_loads('n', 'q', 'nx * VW', '(nx + TPR) * VW')}
+          }} else if (r2 < rows) {{
+{next_row_ptrs}
+            const int c2 = cv_lo + lane_in_row;
+{pin_loads('n', 'z', 'c2 * VW', '(c2 + TPR) * VW')}
+            primed = true;
+          }}
+          const int ca = cv * VW, cb = (cv + TPR) * VW;
+          {{
+{compute('pa', 'ca')}
+{compute('pb', 'cb')}
+          }}
+          cv = nx;
+{advance}
+          if (!more) break;
+        }}
+      }}
+"""
+    else:
+        if pipe == "l2":
+            # ask L2 for the trip after this one (and, on a row's last trip, for the first trip of the thread's next row):
+            # no registers, one instruction per 128-byte line (lanes 0, 8, 16, 24 of a warp cover its 512 contiguous bytes)
+            pf_lines = []
+            for k in vec_in:
+                pf_lines.append(f"          ptk_prefetch_l2(pfq{k} + pfa); ptk_prefetch_l2(pfq{k} + pfb);")
+            pf_ptr = "\n".join(f"          const {CTYPE[prog.in_dtypes[k]]}* pfq{k} = more ? q{k} : pi{k} + r2 * rsi{k};" for k in vec_in)
+            prefetch = f"""        if ((threadIdx.x & 7) == 0) {{{{
+          const int nx = cv + 2 * TPR;
+          const bool more = nx + TPR < cv_hi;
+          const long long r2 = r + (long long)gridDim.x * {rows_per_block};
+          if (more || r2 < rows) {{{{
+            const int pfa = (more ? nx : cv_lo + lane_in_row) * VW, pfb = pfa + TPR * VW;
+{pf_ptr}
+{chr(10).join(pf_lines)}
+          }}}}
+        }}}}"""
+            pf_note = "; the NEXT trip's lines are requested from L2 first (prefetch.global.L2)"
+        else:
+            prefetch, pf_note = "", ""
+        main_loop = f"""      int cv = cv_lo + lane_in_row;
+      // two vectors per trip{pf_note}
+      for (; cv + TPR < cv_hi; cv += 2 * TPR) {{
+        const int ca = cv * VW, cb = (cv + TPR) * VW;
+{prefetch}
+        {{
+{loads('a', 'ca')}
+{loads('b', 'cb')}
+{compute('a', 'ca')}
+{compute('b', 'cb')}
+        }}
+      }}
+"""
+
     tail_in = [f"q{k}[c]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
     tail_tmp = "\n".join(f"          {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
     tail_st = "\n".join(f"          w{k}[c] = to{k};" for k in stored)
@@ -186,37 +265,7 @@ extern "C" __global__ void __launch_bounds__(256, {_k3_min_blocks()}) {name}({',
 {base_in}
 {base_out}
 {row_scalars}
-      int cv = cv_lo + lane_in_row;
-      // Software pipeline over trips of two vectors: the (pinned) loads of trip t+1 are issued before trip t is computed,
-      // and the last trip of a row issues the first trip of this thread's NEXT row, so the memory system always has a
-      // trip in flight per thread while the scalar bodies run.
-      if (cv + TPR < cv_hi) {{
-        if (!primed) {{
-{pin_loads('p', 'q', 'cv * VW', '(cv + TPR) * VW')}
-        }}
-        primed = false;
-        for (;;) {{
-          const int nx = cv + 2 * TPR;
-          const bool more = nx + TPR < cv_hi;
-          const long long r2 = r + (long long)gridDim.x * {rows_per_block};
-          if (more) {{
-{pin_loads('n', 'q', 'nx * VW', '(nx + TPR) * VW')}
-          }} else if (r2 < rows) {{
-{next_row_ptrs}
-            const int c2 = cv_lo + lane_in_row;
-{pin_loads('n', 'z', 'c2 * VW', '(c2 + TPR) * VW')}
-            primed = true;
-          }}
-          const int ca = cv * VW, cb = (cv + TPR) * VW;
-          {{
-{compute('pa', 'ca')}
-{compute('pb', 'cb')}
-          }}
-          cv = nx;
-{advance}
-          if (!more) break;
-        }}
-      }}
+{main_loop}
       for (; cv < cv_hi; cv += TPR) {{
         const int ca = cv * VW;
         {{

@@ -27,6 +27,7 @@ template <typename T, int N> __device__ __forceinline__ PVec<T, N> ptk_ldv(const
 template <typename T, int N> __device__ __forceinline__ void ptk_stv(T* p, const PVec<T, N>& v) {
   *reinterpret_cast<PVec<T, N>*>(p) = v;
 }
+__device__ __forceinline__ void ptk_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // A load the compiler may not move: issued exactly where it is written (`asm volatile`), so that the software pipeline of
 // the fused map+row-reduce kernel really has the NEXT trip's data in flight while the current trip is computed (left to
 // itself the compiler sinks plain loads down to their first use to save registers).

@@ -178,7 +178,7 @@ struct EpiParams {
   // with round-to-nearest fp32 adds (the same thread owns the same elements for all chunks of a tile, so the
   // read-modify-write needs no synchronisation) and applies bias / activation / the bf16 copy after the last chunk.
   int kchunk;
-  // pair kernel, fp32-accurate mode with an error-free leading piece (see row_scale_exp_kernel): the A1 x B1 products go
+  // pair kernel, fp32-accurate mode with an error-free leading piece (see row_absmax_kernel): the A1 x B1 products go
   // to the accumulator at TMEM columns [0, 256), the correction products to the one at [256, 512); the epilogue adds the
   // two (round to nearest).  Both buffers form ONE accumulator stage, so the epilogue of a chunk does not overlap the
   // next chunk's MMAs.
@@ -816,31 +816,58 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
 // The tensor core truncates when it adds into its fp32 accumulator; over a chain of MMAs that is a systematic shrink of the
 // result (~1e-7 per MMA of the chain, measured) which, unlike rounding noise, adds up coherently through chained layers.
 // Truncation cannot bite when every partial sum is exactly representable: the LEADING piece of each operand is therefore
-// taken as an integer multiple of a per-row power of two, x1 = rint(x * 2^s) * 2^-s with |rint| <= 128 (s = 6 - ilogb of
+// taken as an integer multiple of a per-row power of two, x1 = rint(x * 2^s) * 2^-s with |rint| <= 2^b (s = b - 1 - ilogb of
 // the row's largest magnitude; a row of A, a column of B).  All products A1[i,k] * B1[k,j] of one output element are then
-// integers (<= 2^14) on the common unit 2^-(s_i + s_j): up to 1024 of them sum exactly in fp32.  The remainder x - x1 is
+// integers (<= 2^2b, b = 7: lead_bits_for) on the common unit 2^-(s_i + s_j), and they sum exactly in fp32 as long as the
+// partial sums stay below 2^24 units; the operand carries b + 16 = 23 bits plus sign through its three pieces.  The remainder x - x1 is
 // exact in fp32 and is split into two ordinary bf16 pieces; the five correction products go to a second accumulator, whose
 // own truncation shrink is 2^-7 of the total.
-__global__ void __launch_bounds__(256) row_scale_exp_kernel(const float* __restrict__ src, long long sr, long long sc,
-                                                            long long R, long long Cc, int* __restrict__ sexp) {
-  const int lane = threadIdx.x & 31;
-  if (sc == 1 || sr != 1) {   // rows are (or might as well be) walked by a warp each
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = warp; r < R; r += nwarps) {
-      float m = 0.0f;
-      for (long long c = lane; c < Cc; c += 32) m = fmaxf(m, fabsf(src[r * sr + c * sc]));
+// Pass 1: largest magnitude of every row, as the bit pattern of a non-negative float (ordered like an unsigned integer):
+// 64 x 64 tiles through shared memory exactly like the split kernels (coalesced whichever source stride is 1), four
+// threads per tile row, one atomicMax per tile row.  `maxbits` must be zeroed beforehand.  NaN / inf count as "no scale".
+__global__ void __launch_bounds__(256) row_absmax_kernel(const float* __restrict__ src, long long sr, long long sc,
+                                                         long long R, long long Cc, unsigned int* __restrict__ maxbits) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool col_fast = (sc == 1) || (sr != 1);
+  if (col_fast) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) sexp[r] = (m > 0.0f && m < __int_as_float(0x7f800000)) ? 6 - ilogbf(m) : 0;
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + ty + 8 * i, c = c0 + tx + 32 * h;
+        tile[ty + 8 * i][tx + 32 * h] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
     }
-  } else {                    // unit stride ALONG r: consecutive threads take consecutive rows, every load coalesces
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
-      float m = 0.0f;
-      for (long long c = 0; c < Cc; ++c) m = fmaxf(m, fabsf(src[r + c * sc]));
-      sexp[r] = (m > 0.0f && m < __int_as_float(0x7f800000)) ? 6 - ilogbf(m) : 0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long r = r0 + tx + 32 * h, c = c0 + ty + 8 * i;
+        tile[tx + 32 * h][ty + 8 * i] = (r < R && c < Cc) ? src[r * sr + c * sc] : 0.0f;
+      }
     }
   }
+  __syncthreads();
+  const int row = threadIdx.x >> 2, part = threadIdx.x & 3;
+  float m = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = fabsf(tile[row][part * 16 + j]);
+    m = (v > m) ? v : m;   // NaN never wins; +inf does (and then disables the scale below)
+  }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  if (part == 0 && r0 + row < R && m > 0.0f) atomicMax(maxbits + r0 + row, __float_as_uint(m));
+}
+
+// per-row scale exponent from the row maximum: (lead_bits - 1) - ilogb(max), so that |x| * 2^s < 2^lead_bits; 0 for empty /
+// non-finite rows
+__device__ __forceinline__ int scale_exp_of(unsigned int bits, int lead_bits) {
+  const float m = __uint_as_float(bits);
+  return (m > 0.0f && m < __int_as_float(0x7f800000)) ? (lead_bits - 1) - ilogbf(m) : 0;
 }
 
 // piece 0 = rint(x * 2^s[r]) * 2^-s[r] (exact in bf16), pieces 1, 2 = bf16 split of the exact remainder; same tiling and
@@ -848,7 +875,8 @@ __global__ void __launch_bounds__(256) row_scale_exp_kernel(const float* __restr
 // [-1, 1], e.g. tanh outputs written by a previous product's epilogue) instead of sexp.
 __global__ void __launch_bounds__(256) split_aligned_kernel(const float* __restrict__ src, long long sr, long long sc,
                                                             __nv_bfloat16* __restrict__ dst, long long ld, long long R,
-                                                            long long Cc, long long piece_rows, const int* __restrict__ sexp) {
+                                                            long long Cc, long long piece_rows,
+                                                            const unsigned int* __restrict__ maxbits, int lead_bits) {
   __shared__ float tile[64][65];
   const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -877,7 +905,7 @@ __global__ void __launch_bounds__(256) split_aligned_kernel(const float* __restr
   for (int i = 0; i < 8; ++i) {
     const long long r = r0 + ty + 8 * i, c = c0 + 2 * tx;
     if (r < R && c < Cc) {
-      const int sx = sexp[r];
+      const int sx = scale_exp_of(maxbits[r], lead_bits);
       float v[2] = {tile[ty + 8 * i][2 * tx], (c + 1 < Cc) ? tile[ty + 8 * i][2 * tx + 1] : 0.0f};
       __nv_bfloat16 pc[3][2];
 #pragma unroll
@@ -934,6 +962,17 @@ size_t gemm_tc_split_workspace(int64_t M, int64_t N, int64_t K) {
 }
 
 // error-free leading pieces on/off for the fp32-accurate mode (PTK_GEMM_EXACT=0: plain bf16x3 split, one accumulator)
+// Leading-piece width: |rint(x * 2^s)| <= 2^7.  Products are then integers <= 2^14 and every partial sum below 2^24 units is
+// exact: always for K <= 1024, and for longer contractions unless more than a thousand near-maximal products line up in
+// sign — past 2^24 the accumulator merely drops its lowest one or two unit bits (a 2^-24-level effect, no worse than the
+// plain split, and only on such data).  Measured alternative (width shrinking with K so that exactness is unconditional:
+// 6 bits at K = 4096, 5 at 8192): max error 2.5e-6 / 9.3e-6 of the output scale instead of 6e-7 — the operand then only
+// carries b + 16 bits — so the width stays 7 and the accumulation is cut into chunks only beyond K = 16384.
+static int lead_bits_for(int64_t K) {
+  (void)K;
+  return 7;
+}
+
 static int exact_main_default() {
   static int g = -1;
   if (g < 0) {
@@ -1039,9 +1078,9 @@ static int split_kchunk(int64_t K, int exact) {
   }
   const long long kb = (K + BLOCK_K - 1) / BLOCK_K;
   if (exact) {
-    // 1024 products of integers <= 128 x 128 sum to at most 2^24: exactly representable; longer K goes in chunks of 16 k-blocks
-    const int c = g_kchunk > 0 ? std::min(g_kchunk, 16) : 16;
-    return kb > c ? c : 0;
+    const long long cap = 256;   // k-blocks (K = 16384) per accumulation, see lead_bits_for
+    const long long c = g_kchunk > 0 ? std::min<long long>(g_kchunk, cap) : cap;
+    return kb > c ? (int)c : 0;
   }
   const int c = g_kchunk >= 0 ? g_kchunk : 8;
   return (c > 0 && kb > c + c / 4) ? c : 0;
@@ -1059,11 +1098,10 @@ ptk_status stage_operand(const float* src, int64_t sr, int64_t sc, int64_t R, in
   if (pieces == 1) {
     convert_bf16_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc);
   } else if (aligned) {
-    const bool warp_rows = (sc == 1) || (sr != 1);
-    const long long thr = warp_rows ? R * 32 : R;
-    const unsigned gb = (unsigned)std::max<long long>(1, std::min<long long>((thr + 255) / 256, (long long)ptk::sm_count() * 16));
-    row_scale_exp_kernel<<<gb, 256, 0, st>>>(src, sr, sc, R, Cc, sexp);
-    split_aligned_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows, sexp);
+    PTK_CUDA(cudaMemsetAsync(sexp, 0, (size_t)R * 4, st));
+    row_absmax_kernel<<<g, 256, 0, st>>>(src, sr, sc, R, Cc, reinterpret_cast<unsigned int*>(sexp));
+    split_aligned_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows,
+                                            reinterpret_cast<const unsigned int*>(sexp), lead_bits_for(Cc));
   } else {
     split_bf16x3_kernel<<<g, 256, 0, st>>>(src, sr, sc, (__nv_bfloat16*)dst, ld, R, Cc, piece_rows);
   }
@@ -1146,7 +1184,7 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   __nv_bfloat16* Abf = reinterpret_cast<__nv_bfloat16*>(w);
   __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(w + round_up(3 * Mp * Kp * 2, 256));
-  const int exact = exact_main_default();
+  const int exact = terms == 6 ? exact_main_default() : 0;   // (3 terms need the 8-bit leading pieces of the plain split)
   {
     int* sexp = reinterpret_cast<int*>(w + round_up(3 * Mp * Kp * 2, 256) + round_up(3 * Np * Kp * 2, 256));
     ptk_status ss;
@@ -1263,3 +1301,5 @@ extern "C" ptk_status ptk_gemm_tc_staged(int64_t M, int64_t N, int64_t K, double
 }
 
 extern "C" int ptk_gemm_exact_main_default(void) { return ptk::exact_main_default(); }
+
+extern "C" int ptk_gemm_lead_bits(int64_t K) { return ptk::lead_bits_for(K); }

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) random_kernel(int dist, OUT* __restrict__
       case BETA: { const double ga = g.gamma(a), gb = g.gamma(b); x = ga / (ga + gb); } break;
       case INTEGERS: x = floor(a + (b - a) * g.uniform()); if (x >= b) x = b - 1.0; break;   // [low, high)
       case WEIBULL: x = pow(-log(g.uniform()), 1.0 / a); break;                  // a = shape
-      case PARETO: x = b * (pow(g.uniform(), -1.0 / a) - 1.0); break;            // numpy's Lomax form, a = shape, b = scale
+      case PARETO: x = b * pow(g.uniform(), -1.0 / a); break;                    // scipy's form (x >= scale), a = shape, b = scale
       case STUDENTT: { const double z = g.normal(), ch = 2.0 * g.gamma(0.5 * a); x = b + c * z / sqrt(ch / a); } break;  // a=df
       default: x = 0.0;
     }

@@ -98,6 +98,7 @@ SIGNATURES = {
                                    c_int, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
                                    c_int, c_int, c_int, c_void_p]),
     "ptk_gemm_exact_main_default": (c_int, []),
+    "ptk_gemm_lead_bits": (c_int, [c_int64]),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -132,6 +133,8 @@ class _TraceLib:
             return lambda r, c, p: (r if p <= 1 else 3 * ((r + 255) // 256 * 256)) * ((c + 7) // 8 * 8) * 2 + 512 + 4 * r
         if name == "ptk_gemm_exact_main_default":
             return lambda: 1
+        if name == "ptk_gemm_lead_bits":
+            return lambda K: 7
         if name == "ptk_gemm_split_workspace_bytes":
             return lambda M, N, K: 6 * ((M + 255) // 256 * 256 + (N + 255) // 256 * 256) * ((K + 7) // 8 * 8) + 4 * (M + N) + 1024
         if name == "ptk_nonzero_workspace_bytes":

@@ -69,7 +69,7 @@ def gemm(dtype, alpha, A, B, beta, C, precision=0, bias=None, act=0, a_bf16=None
                 ret = dev.empty_t((M, (N + 7) // 8 * 8), torch.bfloat16)
                 cst = Staged.wrap(ret, M, N)
             elif want_bf16 and can_chain_pieces(act):
-                ret = cst = Staged(M, N, pieces, aligned=exact_main())   # the three-piece operand of the next product
+                ret = cst = Staged(M, N, pieces, aligned=Bst.aligned)   # the three-piece operand of the next product
             gemm_staged(Ast, Bst, terms, alpha, beta, C, bias=bias, act=act, out=cst)
             return ret
     if isinstance(a_bf16, Staged):
@@ -167,7 +167,7 @@ def stage_operand(t: torch.Tensor, pieces: int, transposed: bool = False, aligne
     R, C = (t.shape[1], t.shape[0]) if transposed else (t.shape[0], t.shape[1])
     sr, sc = (t.stride(1), t.stride(0)) if transposed else (t.stride(0), t.stride(1))
     if aligned is None:
-        aligned = pieces == 3 and exact_main()
+        aligned = pieces == 3 and exact_main() and FP32_MODE == "tc6"   # (the 3-term variant needs 8-bit leading pieces)
     st = Staged(R, C, pieces, aligned)
     _lib.check(_lib.lib().ptk_stage_operand(dev.ptr(t), sr, sc, R, C, pieces, 1 if st.aligned else 0, st.ptr, st.ld,
                                             st.piece_rows, dev.stream_ptr()), "ptk_stage_operand")
@@ -191,7 +191,7 @@ NO_EXP = -100000   # PTK_STAGE_NO_EXP
 def can_chain_pieces(act) -> bool:
     """May a product's epilogue write the three-piece operand of the next fp32-accurate product?  With error-free leading
     pieces only when the result is known to lie in [-1, 1] (tanh): the leading piece then sits on the fixed grid 2^-6."""
-    return (not exact_main()) or act == 1
+    return (not exact_main()) or FP32_MODE != "tc6" or act == 1
 
 
 def gemm_staged(A: Staged, B: Staged, terms, alpha, beta, C, bias=None, act=0, out: Staged | None = None):
@@ -204,7 +204,7 @@ def gemm_staged(A: Staged, B: Staged, terms, alpha, beta, C, bias=None, act=0, o
     if out is not None and out.pieces == 3 and out.aligned:
         if act != 1:
             raise ValueError("gemm_staged: an aligned three-piece output needs a bounded activation (tanh)")
-        out_exp = 6
+        out_exp = int(_lib.lib().ptk_gemm_lead_bits(N)) - 1   # the result is the A operand of a contraction over N
     _lib.check(_lib.lib().ptk_gemm_tc_staged(M, N, K, float(alpha), A.ptr, A.ld, A.piece_rows, B.ptr, B.ld, B.piece_rows,
                                              int(terms), float(beta), dev.ptr(C), C.stride(0), C.stride(1),
                                              dev.ptr(bias) if bias is not None else None, int(act),
@@ -228,12 +228,17 @@ def staged_weight(key, t: torch.Tensor, pieces: int) -> Staged | None:
     if key is None or not STAGE_CACHE_ON or _lib.TRACE_ONLY:
         return None
     ck = (key, pieces, tuple(t.shape), tuple(t.stride()))
-    st = _stage_cache.get(ck)
-    if st is not None:
-        _stage_cache[ck] = _stage_cache.pop(ck)  # most recently used last
-        _stage_cache_stats["hits"] += 1
-        st.in_graph = st.in_graph or dev.alloc_state.capturing
-        return st
+    ent = _stage_cache.get(ck)
+    if ent is not None:
+        st, owner = ent
+        # keys of caller-owned tensors contain id(tensor): only valid while THAT object is alive — a new tensor can be
+        # handed the id of a dead one, so a hit must also be a hit on the object itself
+        if owner is None or owner() is t:
+            _stage_cache[ck] = _stage_cache.pop(ck)  # most recently used last
+            _stage_cache_stats["hits"] += 1
+            st.in_graph = st.in_graph or dev.alloc_state.capturing
+            return st
+        _stage_cache_stats["bytes"] -= _stage_cache.pop(ck)[0].buf.numel()
     _stage_cache_stats["misses"] += 1
     with dev.unmanaged():          # persistent: outlives the call, never part of a capture arena
         if dev.alloc_state.capturing:
@@ -245,13 +250,14 @@ def staged_weight(key, t: torch.Tensor, pieces: int) -> Staged | None:
         else:
             st = stage_operand(t, pieces, transposed=True)
     st.in_graph = dev.alloc_state.capturing
-    _stage_cache[ck] = st
+    import weakref
+
+    _stage_cache[ck] = (st, weakref.ref(t) if key[0] == "in" else None)
     _stage_cache_stats["bytes"] += st.buf.numel()
-    if _stage_cache_stats["bytes"] > STAGE_CACHE_BYTES:
-        for old in [k for k, v in _stage_cache.items() if not v.in_graph and k != ck]:   # oldest first; buffers a captured
-            _stage_cache_stats["bytes"] -= _stage_cache.pop(old).buf.numel()             # graph reads are never dropped
-            if _stage_cache_stats["bytes"] <= STAGE_CACHE_BYTES:
-                break
+    # entries whose tensor died can never hit again; beyond the budget the oldest go, except buffers a captured graph reads
+    for old in [k for k, (v, w) in _stage_cache.items() if k != ck and not v.in_graph
+                and ((w is not None and w() is None) or _stage_cache_stats["bytes"] > STAGE_CACHE_BYTES)]:
+        _stage_cache_stats["bytes"] -= _stage_cache.pop(old)[0].buf.numel()
     return st
 
 

@@ -222,6 +222,11 @@ class _GraphEntry:
                 pass
 
 
+import itertools as _itertools
+
+_executor_uid = _itertools.count(1)
+
+
 class Executor:
     """Runs a Program.  `run(input_values) -> list of output Vals` (no host conversion).
 
@@ -261,9 +266,11 @@ class Executor:
         self.vals = [None] * program.n_slots
         for s, arr in program.constants.items():
             self.vals[s] = Val(h=np.asarray(arr))
+        self._uid = next(_executor_uid)
         w_in, w_const = program.weight_inputs()
         for s in w_const:
-            self.vals[s].key = ("const", id(program), s)   # a graph constant never changes: its staged copy stays resident
+            # a graph constant never changes: its staged copy stays resident (a process-unique number, not id(): ids recycle)
+            self.vals[s].key = ("const", self._uid, s)
         self._w_in = w_in
         self._w_track = {}    # input position -> [tensor object (strong ref), torch version, identical calls in a row, volatile]
         self._w_keys = {}     # input position -> content key of THIS call (stable inputs only)

@@ -25,6 +25,9 @@ elif which == "cfg4":
     ins, outs, mk, meta = W.cfg4_scan(8192, 512, 1000)
 elif which == "cfg4full":
     ins, outs, mk, meta = W.cfg4_scan(8192, 512, 1000, full_trace=True)
+elif which == "cfg4mm":
+    ins, outs, mk, meta = W.cfg4_scan(8192, 512, int(os.environ.get("T", "40")), matmul=True)
+    kw = dict(gemm_precision=os.environ.get("PREC", "bf16"))
 elif which == "cfg5":
     ins, outs, mk, meta = W.cfg5_logp_grad(B=1 << 17, n=1024, J=64, K=8)
 elif which == "metric":

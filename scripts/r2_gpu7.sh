@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+( for m in none l2; do PTK_K3_PIPE=$m timeout 200 python scripts/k3_probe.py 2>&1 | grep PTK_K3 | sed "s/^/pipe=$m /"; done ) > gpurun_out/k3_probe3.txt
+cat gpurun_out/k3_probe3.txt
+( PTK_GEMM_EXACT=1 timeout 300 python scripts/gemm_split_probe.py 6 2>&1 | tail -6 ) > gpurun_out/split_probe6.txt 2>&1
+cat gpurun_out/split_probe6.txt
+( timeout 1500 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_scan.py tests/test_gpu_blas.py tests/test_gpu_random.py tests/test_gpu_careduce.py -q -m gpu --timeout 300 --maxfail=30 ) > gpurun_out/pytest_new6.log 2>&1
+tail -8 gpurun_out/pytest_new6.log
+( timeout 1200 python bench.py --steps 20 --warmup 5 --skip cfg5,k1,cfg4 ) > gpurun_out/bench7.json 2> gpurun_out/bench7.err; echo "bench exit $?"
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/bench7.json'))
+print("value", d["value"], "e2e", d["e2e"]["value"], "roofline", d["roofline"]["frac"], d["roofline"]["per_launch_event_pair"]["frac"])
+for k in ("metric_graph","cfg3"):
+    for kk,v in d.get(k,{}).items():
+        if isinstance(v,dict): print(k,kk,{a:v.get(a) for a in ("ms","tflops","evals_per_s","error","cuda_graph_replay","hits","misses") if v.get(a) is not None}, json.dumps(v.get("parity"))[:400])
+P
+tail -5 gpurun_out/bench7.err

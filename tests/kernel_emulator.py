@@ -52,6 +52,7 @@ template <typename T, int N> static inline void ptk_stv(T* p, const PVec<T, N>& 
   emu_check_align(p, sizeof(T) * N); std::memcpy(p, &v, sizeof(v));
 }
 template <typename T, int N> static inline PVec<T, N> ptk_ldv_pin(const T* p) { return ptk_ldv<T, N>(p); }
+static inline void ptk_prefetch_l2(const void*) {}
 """
 
 

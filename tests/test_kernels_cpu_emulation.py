@@ -432,7 +432,7 @@ def test_nonzero_count_scan_fill_kernels(tmp_path, n, density, misalign):
         np.testing.assert_array_equal(out[:expect.size], expect)
 
 
-# ---- error-free leading pieces of the fp32-accurate GEMM (row_scale_exp_kernel / split_aligned_kernel, ptk_gemm_tc.cu) ------
+# ---- error-free leading pieces of the fp32-accurate GEMM (row_absmax_kernel / split_aligned_kernel, ptk_gemm_tc.cu) ------
 BF16_SHIM = r"""
 #include <cmath>
 struct __nv_bfloat16 { unsigned short u; };
@@ -447,10 +447,23 @@ static inline float __bfloat162float(__nv_bfloat16 h) { unsigned int b = (unsign
 """
 
 
+ATOMIC_SHIM = r"""
+static inline unsigned int atomicMax(unsigned int* p, unsigned int v) {
+  unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
+"""
+
+
+@pytest.mark.parametrize("lead_bits", [7, 5])
 @pytest.mark.parametrize("R,Cc,row_major", [(70, 130, True), (130, 70, False), (64, 64, True), (5, 9, False)])
-def test_aligned_three_piece_split_is_exact_and_on_the_row_grid(tmp_path, R, Cc, row_major):
-    """x = x1 + x2 + x3 to 2^-23 of the row's largest magnitude; x1 * 2^s is an integer of magnitude <= 128 with
-    s = 6 - ilogb(row max), so that the A1 x B1 products of a dot product are integers on one common unit."""
+def test_aligned_three_piece_split_is_exact_and_on_the_row_grid(tmp_path, R, Cc, row_major, lead_bits):
+    """x = x1 + x2 + x3 to 2^-(b+16) of the row's largest magnitude; x1 * 2^s is an integer of magnitude <= 2^b with
+    s = b - 1 - ilogb(row max), so that the A1 x B1 products of a dot product are integers on one common unit (b = 7 for
+    K <= 1024 ... 4 for K > 16384: 2^2b * K <= 2^24 keeps the whole accumulation exact)."""
     rng = np.random.default_rng(R * 1000 + Cc)
     x = (rng.standard_normal((R, Cc)) * np.exp(rng.uniform(-6, 6, (R, 1)))).astype(np.float32)
     x[1 % R, :] = 0.0                       # an all-zero row
@@ -458,24 +471,30 @@ def test_aligned_three_piece_split_is_exact_and_on_the_row_grid(tmp_path, R, Cc,
     src = np.ascontiguousarray(x if row_major else x.T)   # the kernel reads src[r * sr + c * sc]
     sr, sc = (Cc, 1) if row_major else (1, R)
     text = open(os.path.join(CSRC, "ptk_gemm_tc.cu")).read()
-    assert "row_scale_exp_kernel" in text
-    sexp = np.full(R, -99, dtype=np.int32)
-    k1 = EmulatedKernel(BF16_SHIM + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "row_scale_exp_kernel"),
-                        "row_scale_exp_kernel", tmp_path, threaded=True)
-    k1.launch(2, 256, [_ptr(src), c_longlong(sr), c_longlong(sc), c_longlong(R), c_longlong(Cc), _ptr(sexp)])
+    i0 = text.index("__device__ __forceinline__ int scale_exp_of")
+    helper = text[i0:text.index("\n}\n", i0) + 3]
+    maxbits = np.zeros(R, dtype=np.uint32)
+    k1 = EmulatedKernel(BF16_SHIM + ATOMIC_SHIM + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "row_absmax_kernel"),
+                        "row_absmax_kernel", tmp_path, threaded=True)
+    k1.launch(((Cc + 63) // 64, (R + 63) // 64), 256, [_ptr(src), c_longlong(sr), c_longlong(sc), c_longlong(R), c_longlong(Cc),
+                                                     _ptr(maxbits)])
     rowmax = np.abs(x).max(axis=1)
-    expect_s = np.where(rowmax > 0, 6 - np.floor(np.log2(np.where(rowmax > 0, rowmax, 1.0))).astype(np.int64), 0)
-    np.testing.assert_array_equal(sexp, expect_s)
+    np.testing.assert_array_equal(maxbits.view(np.float32), rowmax)
+    sexp = np.where(rowmax > 0, lead_bits - 1 - np.floor(np.log2(np.where(rowmax > 0, rowmax, 1.0))).astype(np.int64),
+                    0).astype(np.int32)
     ld, pr = (Cc + 7) // 8 * 8, (R + 255) // 256 * 256
     dst = np.zeros((3 * pr, ld), dtype=np.uint16)
-    k2 = EmulatedKernel(BF16_SHIM + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "split_aligned_kernel"),
+    k2 = EmulatedKernel(BF16_SHIM + ATOMIC_SHIM + helper + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "split_aligned_kernel"),
                         "split_aligned_kernel", tmp_path, threaded=True)
     k2.launch(((Cc + 63) // 64, (R + 63) // 64), 256, [_ptr(src), c_longlong(sr), c_longlong(sc), _ptr(dst), c_longlong(ld),
-                                                     c_longlong(R), c_longlong(Cc), c_longlong(pr), _ptr(sexp)])
+                                                     c_longlong(R), c_longlong(Cc), c_longlong(pr), _ptr(maxbits), c_int(lead_bits)])
     pieces = [(dst[k * pr:k * pr + R, :Cc].astype(np.uint32) << 16).view(np.float32).astype(np.float64) for k in range(3)]
     lead_units = pieces[0] * np.exp2(sexp.astype(np.float64))[:, None]
-    assert np.all(lead_units == np.rint(lead_units)) and np.abs(lead_units).max() <= 128
+    assert np.all(lead_units == np.rint(lead_units)) and np.abs(lead_units).max() <= 2 ** lead_bits
     err = np.abs(pieces[0] + pieces[1] + pieces[2] - x.astype(np.float64))
-    assert np.all(err <= np.maximum(rowmax[:, None].astype(np.float64) * 2.0 ** -23, 1e-45))
-    # every product of two leading pieces is an integer on the unit 2^-(s_i + s_j): 1024 of them stay below 2^24
-    assert 128 * 128 * 1024 <= 2 ** 24
+    assert np.all(err <= np.maximum(rowmax[:, None].astype(np.float64) * 2.0 ** -(lead_bits + 16), 1e-45))
+    # every product of two leading pieces is an integer (<= 2^14 for the shipped width 7) on the unit 2^-(s_i + s_j)
+    from pytensor_b200.runtime import lib as L
+
+    assert L.load_library().ptk_gemm_lead_bits(4096) == 7 and L._TraceLib().ptk_gemm_lead_bits(4096) == 7
+    assert (2 ** 7) ** 2 * 1024 <= 2 ** 24

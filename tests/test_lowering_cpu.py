@@ -278,3 +278,18 @@ def test_opfromgraph_inner_graph_never_destroys_its_inputs():
     f2 = pytensor.function([x], OpFromGraph([xi], [xi.T])(y), mode="CUDA")
     inner2 = [m.op for n in f2.maker.fgraph.toposort() if isinstance(n.op, OpFromGraph) for m in n.op.fgraph.toposort()]
     assert any(isinstance(o, DeepCopyOp) for o in inner2)
+
+
+def test_random_variables_lower_to_the_device_sampler_and_keep_the_generator_protocol():
+    pytensor.config.floatX = "float32"
+    rng = pytensor.shared(np.random.default_rng(3), name="rng")
+    mu = pt.fvector("mu")
+    nr, x = pt.random.normal(mu, 2.0, size=(4, 3), rng=rng).owner.outputs
+    f = pytensor.function([mu], [x, pt.random.gamma(2.0, scale=1.0, size=(5,), rng=rng)], updates={rng: nr}, mode="CUDA")
+    assert _steps(f).count("RandomVariableNode") == 2
+    st0 = rng.get_value(borrow=True).bit_generator.state["state"]["state"]
+    trace_function(f, [np.zeros(3, dtype="float32")])
+    # multivariate / unsupported samplers are compile-time errors, like every other unsupported op
+    with pytest.raises(NotImplementedError, match="no device sampler"):
+        pytensor.function([], pt.random.multivariate_normal(np.zeros(2), np.eye(2), rng=rng), mode="CUDA")
+    del st0
