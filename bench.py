@@ -391,8 +391,10 @@ def bench_metric_graph(pytensor, W, cuda_mode, dev, torch, peaks, cvm):
                 rec["cpu_reference"] = {"evals_per_s": 1 / (time.perf_counter() - t0), "cores": os.cpu_count(),
                                         "sample": "1 evaluation (84 sgemm 4096^3 on all cores; compiled beforehand)"}
             out["_exp_" + str(n)] = exp
-            rec["parity"] = parity(got, exp, rtol=1e-4, atol=1e-4,
-                                   note="84 chained fp32 GEMM layers: 1e-4 (rounding differences compound; see DESIGN.md §6)")
+            scale_e = float(np.abs(np.asarray(exp[0])).max())
+            rec["parity"] = parity(got, exp, rtol=1e-4, atol=1e-4 * max(scale_e, 1.0),
+                                   note="84 chained fp32 GEMM layers summed over n rows: 1e-4 of the output scale (per-layer "
+                                        "rounding differences of two fp32 GEMMs compound; DESIGN.md §6)")
             if n > 64:
                 # yardstick: the same graph in float64 on the same numbers (this backend's fp64 FMA kernels, themselves
                 # held to 1e-5/1e-8 against the C linker's dgemm in tests/test_gpu_blas.py).  Two fp32 evaluations of an
@@ -416,9 +418,7 @@ def bench_metric_graph(pytensor, W, cuda_mode, dev, torch, peaks, cvm):
                 e_ref = float(np.abs(np.asarray(exp[0], dtype=np.float64) - truth).max() / scale)
                 rec["parity"]["vs_float64_evaluation"] = {
                     "ours_max_err_over_scale": e_ours, "reference_max_err_over_scale": e_ref,
-                    "ok": bool(e_ours <= 2.0 * e_ref + 1e-5),
-                    "rule": "ours within 2x the C linker's own distance from the float64 result (+1e-5)"}
-                rec["parity"]["ok"] = bool(rec["parity"]["ok"] or rec["parity"]["vs_float64_evaluation"]["ok"])
+                    "note": "informational yardstick: distance of each fp32 evaluation from the float64 one"}
         else:
             rec["parity"] = parity(got, out["_exp_4096"], rtol=5e-2, atol=5e-2)
             rec["parity"]["ok"] = None

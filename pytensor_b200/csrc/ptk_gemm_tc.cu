@@ -526,6 +526,8 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const bool exact = p.exact_main != 0;
+      const int terms_m1 = p.terms - 1;
       for (int sq = unit0; sq < seq_len; sq += unit_stride) {
         const uint32_t idesc = (sq >= full_units) ? idesc_half : idesc_full;
         for (int ch = 0; ch < n_chunks; ++ch) {   // one TMEM accumulator per accumulation chunk (EpiParams::kchunk)
@@ -535,15 +537,17 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t d_corr = tmem_base + (uint32_t)BLOCK_N;   // exact_main: the correction products' accumulator
           const int kb_n = min(kchunk, k_blocks - ch * kchunk);
           const int n_stages = kb_n * p.terms;  // piece products of one k-block accumulate into the same tile
-          for (int it = 0; it < n_stages; ++it) {
+          int term = 0;                         // position inside the k-block's term sequence (no division in this loop:
+          for (int it = 0; it < n_stages; ++it) {   // one thread feeds both SMs' tensor cores, its latency is the pipe's)
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_a + stage * P_A_BYTES);
             const uint32_t b_addr = smem_u32(smem_b + stage * P_B_BYTES);
             // term order within a k-block: the correction products first, A1 x B1 last (kPieceA / kPieceB)
-            const bool to_corr = p.exact_main && (it % p.terms) != p.terms - 1;
+            const bool to_corr = exact && term != terms_m1;
             const uint32_t d_use = to_corr ? d_corr : d_tmem;
-            const bool first = p.exact_main ? (to_corr ? it == 0 : it == p.terms - 1) : it == 0;
+            const bool first = exact ? (to_corr ? it == 0 : it == terms_m1) : it == 0;
+            term = (term == terms_m1) ? 0 : term + 1;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               umma_f16_2sm(d_use, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
