@@ -75,7 +75,7 @@ def _k3_pipeline() -> str:
     warps more than the loads need the head start).  PTK_K3_PIPE overrides."""
     import os
 
-    return os.environ.get("PTK_K3_PIPE", "none")
+    return os.environ.get("PTK_K3_PIPE", "none")   # also: "tma" = gen_row_kernel_tma (bulk-copy staging through shared memory)
 
 
 def _k3_min_blocks() -> int:
@@ -83,7 +83,9 @@ def _k3_min_blocks() -> int:
     the two-trip software pipeline of a 2-input Composite with a couple of spilled words; PTK_K3_MINB overrides (A/B)."""
     import os
 
-    return int(os.environ.get("PTK_K3_MINB", {"regs": "4", "l2": "6"}.get(_k3_pipeline(), "1")))
+    # "none": capped at 42 registers like the L2 variant — left alone the compiler hoists the trip's four loads and takes
+    # 64 registers (4 CTAs/SM): 40.1 us vs 39.1 us on cfg2
+    return int(os.environ.get("PTK_K3_MINB", {"regs": "4"}.get(_k3_pipeline(), "6")))
 
 
 def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: tuple, red_op: str, acc_dtype: str,
@@ -290,6 +292,193 @@ extern "C" __global__ void __launch_bounds__(256, {_k3_min_blocks()}) {name}({',
   }}
 }}
 """.replace("split_of_block()", "(int)blockIdx.y")
+
+
+# ---- K3 with TMA staging: a producer thread streams the rows through shared memory with bulk async copies ------------------
+_TMA_HELPERS = r"""
+// mbarrier + bulk-copy (TMA 1-D) wrappers used by the staged row kernel
+__device__ __forceinline__ unsigned ptk_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ptk_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ptk_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ptk_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void ptk_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ptk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ptk_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ptk_mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(ptk_smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy (bytes and both addresses multiples of 16) completing on `bar`
+__device__ __forceinline__ void ptk_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptk_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptk_smem_u32(bar)) : "memory");
+}
+"""
+
+TMA_STAGES = 4
+
+
+def _k3_tma_min_blocks() -> int:
+    import os
+
+    return int(os.environ.get("PTK_K3_MINB", "6"))   # 6 CTAs/SM: 42 registers, 6 x 34 KB of staging buffers
+
+
+def gen_row_kernel_tma(prog: ScalarProgram, name: str, col_modes: tuple, store_map: tuple, red_op: str, acc_dtype: str,
+                       out_dtype: str, identity, vw: int, tpr: int, inplace: dict | None = None) -> str:
+    """gen_row_kernel with the north star's "TMA staging into shared memory": thread 0 of the CTA issues one bulk
+    asynchronous copy (cp.async.bulk, completion counted on an mbarrier) per input row chunk, TMA_STAGES trips ahead of the
+    consumers; all 256 threads then read their 16-byte vector of every input from shared memory, release the stage
+    (one mbarrier arrival per warp) and run the scalar bodies.  No load instruction, no address arithmetic and no register
+    is spent on the prefetch, so occupancy stays that of the plain kernel while the memory system always has
+    TMA_STAGES - 1 trips in flight per CTA.  Same parameters / launch geometry as gen_row_kernel; requires every
+    vector-mode input to have 16-byte vectors (vw * itemsize == 16) — the launcher falls back otherwise."""
+    from .scalar import ITEMSIZE
+
+    n_in, n_map = len(prog.in_dtypes), len(prog.out_dtypes)
+    ACC, OUT = CTYPE[acc_dtype], CTYPE[out_dtype]
+    restrict = "" if inplace else " __restrict__"
+    params = [f"const {CTYPE[d]}*{restrict} pi{k}" for k, d in enumerate(prog.in_dtypes)]
+    stored = [k for k in range(n_map) if store_map[k]]
+    params += [f"{CTYPE[prog.out_dtypes[k]]}*{restrict} po{k}" for k in stored]
+    params += ["void* __restrict__ pred"]
+    params += [f"long long rsi{k}" for k in range(n_in)]
+    params += [f"long long rso{k}" for k in stored]
+    params += ["long long rows", "long long cols", "int nsplit"]
+    rpb = 256 // tpr
+    vec_in = [k for k in range(n_in) if col_modes[k] == 1]
+    for k in vec_in:
+        assert vw * ITEMSIZE[prog.in_dtypes[k]] == 16, "TMA staging moves 16-byte vectors"
+    smem_decl = "\n".join(f"  __shared__ __align__(128) {CTYPE[prog.in_dtypes[k]]} s_in{k}[STG][{rpb}][TPR * VW];" for k in vec_in)
+    issue_rows = "\n".join(
+        f"          ptk_bulk_g2s(&s_in{k}[p_stage][rr][0], pi{k} + rp * rsi{k} + (long long)cvb * VW, nbytes, &s_full[p_stage]);"
+        for k in vec_in)
+    base_in = "\n".join(f"      const {CTYPE[d]}* q{k} = pi{k} + r * rsi{k};" for k, d in enumerate(prog.in_dtypes))
+    base_out = "\n".join(f"      {CTYPE[prog.out_dtypes[k]]}* w{k} = po{k} + r * rso{k};" for k in stored)
+    row_scalars = "\n".join(f"      const {CTYPE[d]} s{k} = q{k}[0];" for k, d in enumerate(prog.in_dtypes) if col_modes[k] != 1)
+    ld_smem = "\n".join(f"        if (mine) va{k} = *reinterpret_cast<const PVec<{CTYPE[prog.in_dtypes[k]]}, VW>*>(&s_in{k}[c_stage][row_in_block][lane_in_row * VW]);"
+                        for k in vec_in)
+    vdecl = "\n".join(f"        PVec<{CTYPE[prog.in_dtypes[k]]}, VW> va{k};" for k in vec_in)
+    call_in = [f"va{k}.v[e]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
+    odecl = "\n".join(f"          PVec<{CTYPE[d]}, VW> oa{k};" for k, d in enumerate(prog.out_dtypes))
+    call_out = [f"oa{k}.v[e]" for k in range(n_map)]
+    st_ = "\n".join(f"          ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(w{k} + ca, oa{k});" for k in stored)
+    tail_in = [f"q{k}[c]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
+    tail_tmp = "\n".join(f"          {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
+    tail_st = "\n".join(f"          w{k}[c] = to{k};" for k in stored)
+    n_vec = len(vec_in)
+    return f"""{PRELUDE}
+{_VEC_HELPERS}
+{_RED_HELPERS}
+{_TMA_HELPERS}
+{emit_body(prog)}
+typedef {ACC} ACC;
+typedef {OUT} OUT;
+{_combine(red_op, acc_dtype)}
+#define VW {vw}
+#define TPR {tpr}
+#define STG {TMA_STAGES}
+
+extern "C" __global__ void __launch_bounds__(256, {_k3_tma_min_blocks()}) {name}({', '.join(params)}) {{
+{smem_decl}
+  __shared__ unsigned long long s_full[STG], s_empty[STG];
+  const int lane_in_row = threadIdx.x & (TPR - 1);
+  const int row_in_block = threadIdx.x / TPR;
+  const int ncv = (int)(cols / VW);
+  int cv_lo = 0, cv_hi = ncv;
+  if (nsplit > 1) {{
+    const int per_split = (ncv + nsplit - 1) / nsplit;
+    cv_lo = (int)blockIdx.y * per_split;
+    cv_hi = (cv_lo + per_split < ncv) ? (cv_lo + per_split) : ncv;
+  }}
+  const bool last_split = (int)blockIdx.y == nsplit - 1;
+  const int trips = (cv_hi > cv_lo) ? (cv_hi - cv_lo + TPR - 1) / TPR : 0;   // per row block (one division per CTA)
+  if (threadIdx.x == 0) {{
+    for (int s = 0; s < STG; ++s) {{ ptk_mbar_init(&s_full[s], 1); ptk_mbar_init(&s_empty[s], 8); }}
+    ptk_mbar_fence_init();
+  }}
+  __syncthreads();
+  // producer cursor (thread 0 only): next (row block, trip) to request and the ring slot it goes to
+  long long p_rb = (long long)blockIdx.x * {rpb};
+  int p_t = 0, p_stage = 0;
+  unsigned p_par = 1;          // parity to wait for on s_empty: a fresh barrier's previous phase counts as complete
+  auto issue = [&]() {{
+    if (trips == 0 || p_rb >= rows) return;
+    ptk_mbar_wait(&s_empty[p_stage], p_par);
+    const int cvb = cv_lo + p_t * TPR;
+    const int nvec = (cv_hi - cvb < TPR) ? (cv_hi - cvb) : TPR;
+    const unsigned nbytes = (unsigned)nvec * 16u;
+    int nrows = 0;
+    for (int rr = 0; rr < {rpb}; ++rr) nrows += (p_rb + rr < rows) ? 1 : 0;
+    ptk_mbar_expect_tx(&s_full[p_stage], nbytes * (unsigned)nrows * {n_vec}u);
+    for (int rr = 0; rr < {rpb}; ++rr) {{
+      const long long rp = p_rb + rr;
+      if (rp < rows) {{
+{issue_rows}
+      }}
+    }}
+    if (++p_stage == STG) {{ p_stage = 0; p_par ^= 1u; }}
+    if (++p_t == trips) {{ p_t = 0; p_rb += (long long)gridDim.x * {rpb}; }}
+  }};
+  if (threadIdx.x == 0) {{
+    for (int s = 0; s < STG - 1; ++s) issue();
+  }}
+  int c_stage = 0;
+  unsigned c_par = 0;
+  for (long long rb = (long long)blockIdx.x * {rpb}; rb < rows; rb += (long long)gridDim.x * {rpb}) {{
+    const long long r = rb + row_in_block;
+    const bool row_ok = r < rows;
+    ACC acc = (ACC){literal(acc_dtype, identity)};
+    {{
+      const long long rc = row_ok ? r : rb;     // (threads of a missing row idle through the trips: they still hit the barriers)
+{base_in.replace(" r * ", " rc * ")}
+{base_out.replace(" r * ", " rc * ")}
+{row_scalars}
+      for (int t = 0; t < trips; ++t) {{
+        if (threadIdx.x == 0) issue();           // keeps STG - 1 trips in flight
+        const int cv = cv_lo + t * TPR + lane_in_row;
+        const bool mine = row_ok && cv < cv_hi;
+        ptk_mbar_wait(&s_full[c_stage], c_par);
+{vdecl}
+{ld_smem}
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) ptk_mbar_arrive(&s_empty[c_stage]);   // this warp is done with the slot
+        if (++c_stage == STG) {{ c_stage = 0; c_par ^= 1u; }}
+        if (mine) {{
+          const int ca = cv * VW;
+{odecl}
+          #pragma unroll
+          for (int e = 0; e < VW; ++e) {{
+            ptk_body({', '.join(call_in + call_out)});
+            acc = ptk_red(acc, (ACC)oa0.v[e]);
+          }}
+{st_}
+        }}
+      }}
+      if (row_ok && last_split) {{
+        for (int c = ncv * VW + lane_in_row; c < (int)cols; c += TPR) {{
+{tail_tmp}
+          ptk_body({', '.join(tail_in + [f'to{k}' for k in range(n_map)])});
+          acc = ptk_red(acc, (ACC)to0);
+{tail_st}
+        }}
+      }}
+    }}
+{_block_reduce_code(tpr)}
+    if (lane_in_row == 0 && row_ok) {{
+      if (nsplit == 1) reinterpret_cast<OUT*>(pred)[r] = (OUT)acc;
+      else reinterpret_cast<ACC*>(pred)[r * nsplit + (int)blockIdx.y] = acc;
+    }}
+  }}
+}}
+"""
 
 
 def gen_finish_kernel(name: str, red_op: str, acc_dtype: str, out_dtype: str, identity) -> str:

@@ -186,6 +186,7 @@ struct EpiParams {
   // staged output pieces (Cbf, out_pieces == 3): leading piece aligned to the fixed exponent out_exp (operands known to lie
   // in [-1, 1]) so that it can feed an exact-main product; PTK_NO_EXP: ordinary bf16 split
   int out_exp;
+  float out_scale, out_inv;   // 2^out_exp and 2^-out_exp (exact powers of two: the alignment is two multiplies and a rint)
 };
 #define PTK_NO_EXP (-100000)
 // piece indices of the term sequence; a run of `terms` entries ending at index 5 is used
@@ -422,6 +423,10 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_m
                : "memory");
 }
 
+// kExact: compile-time copy of EpiParams::exact_main — the plain instantiation keeps the double-buffered accumulator
+// bookkeeping and the single-accumulator epilogue as constants (the bf16 mode's inner loops carry none of the
+// exact mode's selects).
+template <bool kExact>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_bh, EpiParams p) {
@@ -446,7 +451,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kchunk = (p.kchunk > 0 && p.kchunk < k_blocks) ? p.kchunk : max(k_blocks, 1);
   const int n_chunks = max(1, (k_blocks + kchunk - 1) / kchunk);
-  const int n_acc = p.exact_main ? 1 : ACC_STAGES;   // exact_main: both TMEM buffers belong to one accumulator stage
+  constexpr int n_acc = kExact ? 1 : ACC_STAGES;   // exact: both TMEM buffers belong to one accumulator stage
   const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
   // Wave-quantisation fix: the units of the last, partially filled round are split into two 256 x 128 HALF units when
   // that fills the idle CTA pairs (e.g. 4096^2: 256 units on 74 pairs = 3 full rounds + 34 -> 68 half units, 3.5 rounds
@@ -526,7 +531,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const bool exact = p.exact_main != 0;
+      constexpr bool exact = kExact;
       const int terms_m1 = p.terms - 1;
       for (int sq = unit0; sq < seq_len; sq += unit_stride) {
         const uint32_t idesc = (sq >= full_units) ? idesc_half : idesc_full;
@@ -590,7 +595,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
           tmem_ld_32x32b_x32(taddr, r);
-          if (p.exact_main) {
+          if constexpr (kExact) {
             uint32_t r2[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), r2);
             tmem_ld_wait();
@@ -651,7 +656,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (pc == 0 && p.out_exp != PTK_NO_EXP) {     // aligned leading piece (exact in bf16)
 #pragma unroll
                       for (int e = 0; e < 4; ++e) {
-                        const float lead = scalbnf(rintf(scalbnf(vv[e], p.out_exp)), -p.out_exp);
+                        const float lead = rintf(vv[e] * p.out_scale) * p.out_inv;
                         vv[e] -= lead;
                         reinterpret_cast<float*>(&v)[e] = lead;
                       }
@@ -689,7 +694,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                   if (cbf) {
                     for (int pc = 0; pc < p.out_pieces; ++pc) {
                       const __nv_bfloat16 b = (pc == 0 && p.out_exp != PTK_NO_EXP)
-                                                  ? __float2bfloat16_rn(scalbnf(rintf(scalbnf(x, p.out_exp)), -p.out_exp))
+                                                  ? __float2bfloat16_rn(rintf(x * p.out_scale) * p.out_inv)
                                                   : __float2bfloat16_rn(x);
                       cbf[((long long)pc * p.cbf_rows + row) * p.ldcbf + col] = b;
                       x -= __bfloat162float(b);
@@ -909,12 +914,14 @@ __global__ void __launch_bounds__(256) split_aligned_kernel(const float* __restr
   for (int i = 0; i < 8; ++i) {
     const long long r = r0 + ty + 8 * i, c = c0 + 2 * tx;
     if (r < R && c < Cc) {
-      const int sx = scale_exp_of(maxbits[r], lead_bits);
+      int sx = scale_exp_of(maxbits[r], lead_bits);
+      sx = sx > 126 ? 126 : (sx < -126 ? -126 : sx);   // 2^sx and 2^-sx must be normal floats (rows of denormal size lose bits)
+      const float up = __int_as_float((127 + sx) << 23), dn = __int_as_float((127 - sx) << 23);
       float v[2] = {tile[ty + 8 * i][2 * tx], (c + 1 < Cc) ? tile[ty + 8 * i][2 * tx + 1] : 0.0f};
       __nv_bfloat16 pc[3][2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float lead = scalbnf(rintf(scalbnf(v[e], sx)), -sx);   // |rint| <= 128: exact in bf16; x - lead exact in fp32
+        const float lead = rintf(v[e] * up) * dn;   // |rint| <= 128: exact in bf16; x - lead exact in fp32
         pc[0][e] = __float2bfloat16_rn(lead);
         float rem = v[e] - lead;
         if (!(fabsf(v[e]) < __int_as_float(0x7f800000))) rem = 0.0f;  // inf / NaN ride in the leading piece only
@@ -1037,12 +1044,13 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     g_split = (e && e[0] == '0') ? 0 : 1;
   }
   p.split_tail = g_split;
-  p.terms = 1; p.a_rows = 0; p.b_rows = 0; p.kchunk = 0; p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP;
+  p.terms = 1; p.a_rows = 0; p.b_rows = 0; p.kchunk = 0; p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP; p.out_scale = 1.0f; p.out_inv = 1.0f;
   static bool attr_set = false;
   if (!attr_set) {
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
@@ -1062,7 +1070,7 @@ ptk_status gemm_tc_ex(int64_t M, int64_t N, int64_t K, float alpha, const float*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cluster == 3) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
+    if (cluster == 3) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel<false>, ta, tb, tbh, p));
     else PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<2>, ta, tb, p));
   } else {
     const int grid = std::max(1, std::min(m_tiles * n_tiles, sms));
@@ -1142,15 +1150,21 @@ ptk_status gemm_tc_staged(int64_t M, int64_t N, int64_t K, float alpha, const vo
   p.ldcbf = ldc_stage;
   p.out_pieces = C_stage ? out_pieces : 1;
   p.cbf_rows = c_rows;
-  p.exact_main = 0; p.out_exp = PTK_NO_EXP;
+  p.exact_main = 0; p.out_exp = PTK_NO_EXP; p.out_scale = 1.0f; p.out_inv = 1.0f;
   p.split_tail = 1;
   p.terms = terms; p.a_rows = terms == 1 ? 0 : (int)a_rows; p.b_rows = terms == 1 ? 0 : (int)b_rows;
   p.exact_main = (terms != 1 && exact_main) ? 1 : 0;
   p.out_exp = (C_stage && out_pieces == 3) ? out_exp : PTK_NO_EXP;
+  if (p.out_exp != PTK_NO_EXP) {
+    if (p.out_exp < -100 || p.out_exp > 100) return fail(PTK_ERR_ARG, "gemm_tc_staged: out_exp out of range");
+    p.out_scale = ldexpf(1.0f, p.out_exp);
+    p.out_inv = ldexpf(1.0f, -p.out_exp);
+  }
   p.kchunk = terms == 1 ? 0 : split_kchunk(K, p.exact_main);
   static bool attr_set = false;
   if (!attr_set) {
-    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
@@ -1169,7 +1183,8 @@ ptk_status gemm_tc_staged(int64_t M, int64_t N, int64_t K, float alpha, const vo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
+  if (p.exact_main) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel<true>, ta, tb, tbh, p));
+  else PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel<false>, ta, tb, tbh, p));
   PTK_LAUNCH_CHECK("gemm_tc_staged");
   return PTK_OK;
 }
@@ -1207,14 +1222,15 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Cbf = nullptr;
   p.ldcbf = 0;
-  p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP;
+  p.out_pieces = 1; p.cbf_rows = 0; p.exact_main = 0; p.out_exp = PTK_NO_EXP; p.out_scale = 1.0f; p.out_inv = 1.0f;
   p.split_tail = 1;
   p.terms = terms; p.a_rows = (int)Mp; p.b_rows = (int)Np;
   p.exact_main = exact;
   p.kchunk = split_kchunk(K, exact);
   static bool attr_set = false;
   if (!attr_set) {
-    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
+    PTK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
@@ -1233,7 +1249,8 @@ ptk_status gemm_tc_split(int64_t M, int64_t N, int64_t K, float alpha, const flo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel, ta, tb, tbh, p));
+  if (p.exact_main) PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel<true>, ta, tb, tbh, p));
+  else PTK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_pair_kernel<false>, ta, tb, tbh, p));
   PTK_LAUNCH_CHECK("gemm_bf16x3_tc");
   return PTK_OK;
 }

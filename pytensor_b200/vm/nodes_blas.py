@@ -218,27 +218,31 @@ def gemm_staged(A: Staged, B: Staged, terms, alpha, beta, C, bias=None, act=0, o
 # same object at the same torch version as in the previous calls, device-resident shared variables between updates) is
 # staged ONCE and the staged copy is reused by every later call / graph capture; PTK_STAGE_CACHE=0 turns this off.
 STAGE_CACHE_ON = _os.environ.get("PTK_STAGE_CACHE", "1") != "0"
-STAGE_CACHE_BYTES = int(_os.environ.get("PTK_STAGE_CACHE_MB", "8192")) << 20
+STAGE_CACHE_BYTES = int(_os.environ.get("PTK_STAGE_CACHE_MB", "32768")) << 20
 _stage_cache: dict = {}   # (key, pieces, shape, strides) -> Staged   (insertion order = LRU order)
 _stage_cache_stats = {"hits": 0, "misses": 0, "bytes": 0}
 
 
+def forget_weights(kind, serial) -> None:
+    """Drop every resident staged copy whose content key starts with (kind, serial): the VM calls this when the tensor
+    behind a key is replaced or changes version, and when an Executor (with its captured graphs) dies."""
+    for ck in [c for c in _stage_cache if c[0][0] == kind and c[0][1] == serial]:
+        _stage_cache_stats["bytes"] -= _stage_cache.pop(ck).buf.numel()
+
+
 def staged_weight(key, t: torch.Tensor, pieces: int) -> Staged | None:
-    """The resident staged copy of B (as B^T) for content identity `key`, staging it on first sight; None = not cacheable."""
+    """The resident staged copy of B (as B^T) for content identity `key`, staging it on first sight; None = not cacheable.
+    Keys are ("const", executor serial, slot) or ("in", tracking serial, torch version): process-unique numbers handed out
+    by the VM (never id(): ids recycle), so a hit can only be the content it was staged from."""
     if key is None or not STAGE_CACHE_ON or _lib.TRACE_ONLY:
         return None
     ck = (key, pieces, tuple(t.shape), tuple(t.stride()))
-    ent = _stage_cache.get(ck)
-    if ent is not None:
-        st, owner = ent
-        # keys of caller-owned tensors contain id(tensor): only valid while THAT object is alive — a new tensor can be
-        # handed the id of a dead one, so a hit must also be a hit on the object itself
-        if owner is None or owner() is t:
-            _stage_cache[ck] = _stage_cache.pop(ck)  # most recently used last
-            _stage_cache_stats["hits"] += 1
-            st.in_graph = st.in_graph or dev.alloc_state.capturing
-            return st
-        _stage_cache_stats["bytes"] -= _stage_cache.pop(ck)[0].buf.numel()
+    st = _stage_cache.get(ck)
+    if st is not None:
+        _stage_cache[ck] = _stage_cache.pop(ck)  # most recently used last
+        _stage_cache_stats["hits"] += 1
+        st.in_graph = st.in_graph or dev.alloc_state.capturing
+        return st
     _stage_cache_stats["misses"] += 1
     with dev.unmanaged():          # persistent: outlives the call, never part of a capture arena
         if dev.alloc_state.capturing:
@@ -250,14 +254,13 @@ def staged_weight(key, t: torch.Tensor, pieces: int) -> Staged | None:
         else:
             st = stage_operand(t, pieces, transposed=True)
     st.in_graph = dev.alloc_state.capturing
-    import weakref
-
-    _stage_cache[ck] = (st, weakref.ref(t) if key[0] == "in" else None)
+    _stage_cache[ck] = st
     _stage_cache_stats["bytes"] += st.buf.numel()
-    # entries whose tensor died can never hit again; beyond the budget the oldest go, except buffers a captured graph reads
-    for old in [k for k, (v, w) in _stage_cache.items() if k != ck and not v.in_graph
-                and ((w is not None and w() is None) or _stage_cache_stats["bytes"] > STAGE_CACHE_BYTES)]:
-        _stage_cache_stats["bytes"] -= _stage_cache.pop(old)[0].buf.numel()
+    if _stage_cache_stats["bytes"] > STAGE_CACHE_BYTES:   # oldest first; buffers a live captured graph reads are kept
+        for old in [k for k, v in _stage_cache.items() if k != ck and not v.in_graph]:
+            _stage_cache_stats["bytes"] -= _stage_cache.pop(old).buf.numel()
+            if _stage_cache_stats["bytes"] <= STAGE_CACHE_BYTES:
+                break
     return st
 
 

@@ -589,12 +589,16 @@ class ElemwiseReduceNode(Node):
             return self._unfused_given(vals, ins, outs)
         store = tuple((k != 0 or self.store_reduced_input) for k in range(ew.n_out))  # in self.order numbering
         in_modes = tuple(col_modes[: len(ins)])
-        key = (in_modes, vw, tpr, store)
+        # TMA staging (cp.async.bulk through shared memory) needs 16-byte vectors on every streamed input
+        tma = (cg_red._k3_pipeline() == "tma" and tpr >= 64
+               and all(vw * ITEMSIZE[dt] == 16 for dt, m in zip(ew.prog.in_dtypes, in_modes) if m == 1))
+        key = (in_modes, vw, tpr, store, tma)
         fn = self._kernels.get(key)
         if fn is None:
+            gen = cg_red.gen_row_kernel_tma if tma else cg_red.gen_row_kernel
             fn, _ = jit.get_function_gen(
-                lambda kn: cg_red.gen_row_kernel(self.prog, kn, in_modes, store, red.red_op, red.acc_dtype,
-                                                 red.out_dtype, red.identity, vw, tpr, inplace=ew.inplace),
+                lambda kn: gen(self.prog, kn, in_modes, store, red.red_op, red.acc_dtype,
+                               red.out_dtype, red.identity, vw, tpr, inplace=ew.inplace),
                 "ptk_ew_red_row")
             self._kernels[key] = fn
         rout = dev.empty(oshape[: nd - n_red], red.out_dtype)

@@ -319,19 +319,38 @@ class Executor:
             tr = self._w_track.get(k)
             if not hasattr(x, "is_cuda") or not x.is_cuda:
                 if tr is not None:
-                    self._w_track.pop(k)
+                    self._forget(self._w_track.pop(k)[4])
                 continue
             v = x._version
             if tr is None or tr[0] is not x:
-                self._w_track[k] = [x, v, 0, tr[3] if tr is not None and tr[0] is x else False]
+                # another object: a new process-unique serial (an id() could be the recycled id of a dead tensor, and the
+                # key is part of the graph signature), and everything staged for the previous object is dropped
+                if tr is not None:
+                    self._forget(tr[4])
+                self._w_track[k] = [x, v, 0, False, next(_executor_uid)]
                 continue
             if tr[1] != v:
                 tr[1], tr[2], tr[3] = v, 0, True
+                self._forget(tr[4])
                 continue
             tr[2] += 1
             if tr[2] >= 2 and not tr[3]:
-                keys[k] = ("in", id(x), v)
+                keys[k] = ("in", tr[4], v)
         return tuple(sorted(keys.items())) if keys else ()
+
+    @staticmethod
+    def _forget(serial, kind="in"):
+        from . import nodes_blas
+
+        nodes_blas.forget_weights(kind, serial)
+
+    def __del__(self):
+        try:   # staged copies only this executor's keys (and captured graphs) can reach
+            for tr in self._w_track.values():
+                self._forget(tr[4])
+            self._forget(self._uid, "const")
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def _wrap_inputs(self, inputs):
         vals = self.vals

@@ -55,7 +55,10 @@ def export_launches(path, name):
 go = os.path.join(REPO, "gpurun_out")
 for fn in sorted(os.listdir(go)):
     p = os.path.join(go, fn)
+    stem = fn.rsplit(".", 1)[0]
+    if stem.startswith(tag + "_"):      # files already named per round (r2_prof_*): no second prefix
+        stem = stem[len(tag) + 1:]
     if fn.endswith(".ncu-rep"):
-        export_rep(p, fn[: -len(".ncu-rep")])
-    elif fn.startswith("launches") and fn.endswith(".csv"):
-        export_launches(p, fn[: -len(".csv")])
+        export_rep(p, stem)
+    elif "launches" in fn and fn.endswith(".csv"):
+        export_launches(p, stem)

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# Round-2 closing single-GPU pass: full GPU suite, smoke, the default bench command (both arms).
+set -u
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+( time timeout 1500 python -m pytest tests -q -m gpu --timeout 300 --maxfail=40 ) > gpurun_out/pytest_gpu_final.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu_final.log; tail -6 gpurun_out/pytest_gpu_final.log
+( timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+( time timeout 1500 python bench.py ) > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench exit $?"
+tail -4 gpurun_out/bench_final.err
+( time timeout 600 python bench.py --impl reference --steps 5 --warmup 1 ) > gpurun_out/bench_final_reference.json 2>> gpurun_out/bench_final.err

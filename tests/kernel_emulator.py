@@ -56,6 +56,39 @@ static inline void ptk_prefetch_l2(const void*) {}
 """
 
 
+# Host stand-ins for the mbarrier / bulk-copy wrappers of the TMA-staged row kernel (codegen/careduce.py _TMA_HELPERS): one
+# 64-bit word per barrier — bit 63 phase, bits 40..55 arrival count, bits 24..39 pending arrivals, bits 0..23 pending bytes.
+EMU_TMA = r"""
+static inline bool emu_bar_update(unsigned long long* bar, long long d_pending, long long d_tx) {
+  unsigned long long old = __atomic_load_n(bar, __ATOMIC_SEQ_CST), neu;
+  do {
+    unsigned long long phase = old >> 63, count = (old >> 40) & 0xffffull;
+    long long pending = (long long)((old >> 24) & 0xffffull) + d_pending, tx = (long long)(old & 0xffffffull) + d_tx;
+    if (pending < 0 || tx < 0 || tx > 0xffffff) { std::fprintf(stderr, "mbarrier protocol violated\n"); std::abort(); }
+    if (pending == 0 && tx == 0) { phase ^= 1ull; pending = (long long)count; }
+    neu = (phase << 63) | (count << 40) | ((unsigned long long)pending << 24) | (unsigned long long)tx;
+  } while (!__atomic_compare_exchange_n(bar, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return true;
+}
+static inline void ptk_mbar_init(unsigned long long* bar, unsigned count) {
+  __atomic_store_n(bar, ((unsigned long long)count << 40) | ((unsigned long long)count << 24), __ATOMIC_SEQ_CST);
+}
+static inline void ptk_mbar_fence_init() {}
+static inline void ptk_mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu_bar_update(bar, -1, (long long)bytes); }
+static inline void ptk_mbar_arrive(unsigned long long* bar) { emu_bar_update(bar, -1, 0); }
+static inline void ptk_mbar_wait(unsigned long long* bar, unsigned parity) {
+  while ((unsigned)(__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 63) == parity) std::this_thread::yield();
+}
+static inline void ptk_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15u) {
+    std::fprintf(stderr, "bulk copy needs 16-byte aligned addresses and size\n"); std::abort();
+  }
+  std::memcpy(dst, src, bytes);
+  emu_bar_update(bar, 0, -(long long)bytes);
+}
+"""
+
+
 # Threaded variant for kernels with warp shuffles, __syncthreads and __shared__ memory (the row reductions): every
 # simulated thread of a block is a real OS thread, a shuffle is "publish my value, warp barrier, read the partner's value,
 # warp barrier", __syncthreads is a block barrier, `__shared__` becomes a function-local static (blocks run one at a time).
@@ -154,7 +187,10 @@ class EmulatedKernel:
         `dynamic_smem`: name of the kernel's `extern __shared__` array (gets a fixed 100 KiB static buffer)."""
         from pytensor_b200.codegen.elemwise import _VEC_HELPERS
 
-        body = source.replace(PRELUDE, "").replace(_VEC_HELPERS, ALIGN_CHECKED_VEC)
+        from pytensor_b200.codegen.careduce import _TMA_HELPERS
+
+        body = source.replace(PRELUDE, "").replace(_VEC_HELPERS, ALIGN_CHECKED_VEC).replace(_TMA_HELPERS, EMU_TMA)
+        body = body.replace("__shared__ __align__(128)", "alignas(128) static")
         if dynamic_smem:
             body = re.sub(r"extern __shared__[^\n;]*\b" + re.escape(dynamic_smem) + r"\[\];",
                           f"alignas(16) static unsigned char {dynamic_smem}[100 * 1024];", body)

@@ -190,10 +190,13 @@ from pytensor_b200.codegen import careduce as cg_red  # noqa: E402
 @pytest.mark.parametrize("rows,cols,tpr,vw,store", [(9, 64, 32, 4, True), (3, 1024, 256, 4, True), (10, 70, 32, 1, True),
                                                      (5, 260, 32, 4, False), (2, 2052, 256, 4, True), (5, 2060, 128, 4, True),
                                                      (7, 1024, 64, 4, False)])
-def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store):
+@pytest.mark.parametrize("tma", [False, True])
+def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store, tma):
     """The bench's dominant kernel shape (gen_row_kernel): map over (rows, cols), store the map result (or not), reduce each
     row with fp64 accumulation — warp-shuffle tree, cross-warp combine through shared memory for TPR = 256, scalar tail for
     cols % VW, rows that do not fill the last block."""
+    if tma and vw != 4:
+        pytest.skip("the TMA-staged variant moves 16-byte vectors")
     rng = np.random.default_rng(6)
     dt = "float32"
     prog = ScalarProgram(in_dtypes=[dt, dt, dt], out_dtypes=[dt])
@@ -201,8 +204,9 @@ def test_fused_map_row_reduce_kernel_k3(tmp_path, rows, cols, tpr, vw, store):
                   ScalarInst("Tanh", [("t", 1)], [dt], dt)]
     prog.outputs = [("t", 2)]
     in_modes = (1, 0, 1)                                      # input 1: one value per row
-    src = cg_red.gen_row_kernel(prog, "k_row", in_modes, (store,), "add", "float64", "float32", 0, vw, tpr)
-    k = EmulatedKernel(src, "k_row", tmp_path, threaded=True)
+    gen = cg_red.gen_row_kernel_tma if tma else cg_red.gen_row_kernel
+    src = gen(prog, "k_row", in_modes, (store,), "add", "float64", "float32", 0, vw, tpr)
+    k = EmulatedKernel(src, "k_row", tmp_path, threaded=True, warp_shim=tma)   # (a real __syncwarp before the slot release)
     a, c = _aligned((rows, cols), dt, rng), _aligned((rows, cols), dt, rng)
     b = _aligned((rows,), dt, rng)
     e = _aligned((rows, cols), dt)
