@@ -65,7 +65,7 @@ def _ncu_traffic(kernel_prefix, pattern="*prof_ew*_ncu_summary.csv"):
             kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             vals = [float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
-                    for r in rows[2:] if r[kn].startswith(kernel_prefix)]
+                    for r in rows[2:] if r[kn].startswith(kernel_prefix) and not r[kn].endswith("_fin")]
             if vals:
                 return sum(vals) / len(vals)
         except Exception:  # noqa: BLE001

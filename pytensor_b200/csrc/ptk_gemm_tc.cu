@@ -609,7 +609,35 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // a shared-memory tile turns that into 128 contiguous bytes of one row per quarter warp, so every global
           // load / store instruction of the warp covers 4 full 128-byte lines (the read-modify-write of the accumulation
           // chunks and the bf16 / three-piece operand copies move whole sectors instead of 16-byte shards of 32 lines).
-          if (vec_ok && col0 + 32 <= p.N) {
+          if (vec_ok && col0 + 32 <= p.N && beta == 0.0f && (cbf == nullptr || p.out_pieces == 1)) {
+            // Store-only epilogue (nothing to read back, at most a bf16 copy): each lane keeps its ROW of the block and
+            // writes it as eight independent 16-byte groups — no shared-memory round trip, no warp barriers, eight-way
+            // instruction-level parallelism through the tanh chains.  The strided 16-byte stores are fire-and-forget; with
+            // a bias + tanh + bf16-copy epilogue this path keeps up with the next tile's MMAs where the row-contiguous one
+            // below (which pays off as soon as old values must be LOADED) does not (cfg3: 0.43 vs 0.47 ms).
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 v;
+                float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float x = p.alpha * __uint_as_float(r[j + e]);
+                  if (bias) x += bias[col0 + j + e];
+                  if (act == 1) x = tanhf(x);
+                  vv[e] = x;
+                }
+                *reinterpret_cast<float4*>(crow + col0 + j) = v;
+                if (cbf) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(vv[0], vv[1]), hi = __floats2bfloat162_rn(vv[2], vv[3]);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(cbf + row * p.ldcbf + col0 + j) = pk;
+                }
+              }
+            }
+          } else if (vec_ok && col0 + 32 <= p.N) {
             float* tile = epi_tiles + (warp - 4) * (32 * EPI_PITCH);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
