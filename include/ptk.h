@@ -220,6 +220,13 @@ int          ptk_gemm_exact_main_default(void);
 /* Width b of the aligned leading piece for a contraction of length K (|leading integer| <= 2^b; 7 today for every K);
  * out_exp of a chained tanh epilogue feeding a product of contraction length K' is ptk_gemm_lead_bits(K') - 1. */
 int          ptk_gemm_lead_bits(int64_t K);
+/* A chain of L <= 96 small dense layers in one launch: h <- act_l(h @ W_l + bias_l), every K_l, N_l <= 128, N_l % 4 == 0,
+ * K_l == N_(l-1), W_l contiguous row-major fp32 [K_l, N_l] (16-byte aligned), bias_l [N_l] or NULL, act_l 0 | 1 (tanh).
+ * x [M, K_0] (row stride sx0, unit column stride) -> y [M, N_(L-1)] (row stride sy0).  Replaces L sgemm_ calls plus L
+ * Composite{tanh(x + b)} loops of the C linker (tensor/blas/c_code/codegen.py:463-540) when the matrices are so small that
+ * a launch per layer costs more than the layer: the BASELINE metric graph at n = 64. */
+ptk_status   ptk_mlp_chain(const void* x, int64_t sx0, void* y, int64_t sy0, int64_t M, int L, const void* const* W,
+                           const void* const* bias, const int* K, const int* N, const int* act, void* stream);
 /* y[M] = alpha * A[M,N] @ x[N] + beta * y   (beta == 0 never reads y). */
 ptk_status   ptk_gemv(int dtype, int64_t M, int64_t N, double alpha, const void* A, int64_t sa0, int64_t sa1,
                       const void* x, int64_t sx, double beta, void* y, int64_t sy, void* stream);

@@ -598,6 +598,101 @@ ptk_status launch_gemv(int64_t M, int64_t N, double alpha, const void* A, int64_
   return PTK_OK;
 }
 
+// ---- a whole chain of small dense layers in ONE launch ----------------------------------------------------------------------
+// h <- act_l(h @ W_l + b_l), l = 0..L-1, with every layer at most 128 wide (the "256-node Elemwise+Gemm+Scan" metric graph of
+// BASELINE.json at n = 64: 84 such layers).  Node by node that is one launch per layer at ~3 us of launch + drain each, for
+// ~0.5 MFLOP of work; here a CTA owns 16 rows for ALL layers: the activations live in shared memory (two buffers), the weights
+// of layer l+1 stream into shared memory with cp.async while layer l is computed, and nothing but the final activations
+// goes back to HBM.  Thread (r, c) = (tid / 16, tid % 16) accumulates 4 consecutive columns [4c + 64j, +4) of row r:
+// per k one broadcast LDS of h and one LDS.128 of W per 4 FMAs.  fp32 FMA, k ascending (the SIMT GEMM's arithmetic).
+constexpr int MC_MAXW = 128;   // widest layer
+constexpr int MC_ROWS = 16;    // rows of the batch per CTA
+constexpr int MC_MAXL = 96;    // layers per launch
+struct MlpLayer {
+  const float* W;      // [K, N] row-major, contiguous, 16-byte aligned, N % 4 == 0
+  const float* bias;   // [N] or null
+  int K, N, act, pad_;
+};
+struct MlpChain {
+  int L, pad_;
+  MlpLayer layer[MC_MAXL];
+};
+
+__device__ __forceinline__ void mc_cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mc_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict__ x, long long sx0, float* __restrict__ y,
+                                                        long long sy0, long long M, const __grid_constant__ MlpChain c) {
+  extern __shared__ float mc_smem[];
+  float* hbuf[2] = {mc_smem, mc_smem + MC_ROWS * MC_MAXW};
+  float* wbuf[2] = {mc_smem + 2 * MC_ROWS * MC_MAXW, mc_smem + 2 * MC_ROWS * MC_MAXW + MC_MAXW * MC_MAXW};
+  const int tid = threadIdx.x, r = tid >> 4, c0 = tid & 15;
+  const long long row0 = (long long)blockIdx.x * MC_ROWS;
+  // layer 0's weights start streaming; meanwhile the input rows are copied in (zeros for rows past M)
+  {
+    const MlpLayer& l0 = c.layer[0];
+    const int n4 = (l0.K * l0.N) >> 2;
+    for (int i = tid; i < n4; i += 256) mc_cp_async16(wbuf[0] + 4 * i, l0.W + 4 * i);
+    for (int i = tid; i < MC_ROWS * l0.K; i += 256) {
+      const int rr = i / l0.K, kk = i - rr * l0.K;
+      hbuf[0][rr * MC_MAXW + kk] = (row0 + rr < M) ? x[(row0 + rr) * sx0 + kk] : 0.0f;
+    }
+  }
+  for (int l = 0; l < c.L; ++l) {
+    const MlpLayer& ly = c.layer[l];
+    mc_cp_async_wait_all();          // this thread's part of W_l has landed ...
+    __syncthreads();                 // ... and everybody's, together with the activations the previous layer wrote
+    if (l + 1 < c.L) {               // W_{l+1} goes into the buffer layer l-1 used (all its readers passed the barrier above)
+      const MlpLayer& nx = c.layer[l + 1];
+      const int n4 = (nx.K * nx.N) >> 2;
+      float* dst = wbuf[(l + 1) & 1];
+      for (int i = tid; i < n4; i += 256) mc_cp_async16(dst + 4 * i, nx.W + 4 * i);
+    }
+    const float* h = hbuf[l & 1] + r * MC_MAXW;
+    const float* W = wbuf[l & 1];
+    const int K = ly.K, N = ly.N;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int ca = 4 * c0, cb = 64 + 4 * c0;
+    const bool use_a = ca < N, use_b = cb < N;
+    for (int k = 0; k < K; ++k) {
+      const float hv = h[k];
+      if (use_a) {
+        const float4 w = *reinterpret_cast<const float4*>(W + k * N + ca);
+        acc[0][0] = fmaf(hv, w.x, acc[0][0]); acc[0][1] = fmaf(hv, w.y, acc[0][1]);
+        acc[0][2] = fmaf(hv, w.z, acc[0][2]); acc[0][3] = fmaf(hv, w.w, acc[0][3]);
+      }
+      if (use_b) {
+        const float4 w = *reinterpret_cast<const float4*>(W + k * N + cb);
+        acc[1][0] = fmaf(hv, w.x, acc[1][0]); acc[1][1] = fmaf(hv, w.y, acc[1][1]);
+        acc[1][2] = fmaf(hv, w.z, acc[1][2]); acc[1][3] = fmaf(hv, w.w, acc[1][3]);
+      }
+    }
+    const bool last = l + 1 == c.L;
+    float* hn = hbuf[(l + 1) & 1] + r * MC_MAXW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int cc = j ? cb : ca;
+      if (cc < N) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = acc[j][e];
+          if (ly.bias) v += ly.bias[cc + e];
+          if (ly.act == 1) v = tanhf(v);
+          if (last) {
+            if (row0 + r < M) y[(row0 + r) * sy0 + cc + e] = v;
+          } else {
+            hn[cc + e] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) ger_kernel(int64_t M, int64_t N, T alpha, const T* __restrict__ x, int64_t sx,
                                                   const T* __restrict__ y, int64_t sy, T* __restrict__ A, int64_t sa0,
@@ -633,6 +728,37 @@ ptk_status ptk_gemm_bias_act(int dtype, int64_t M, int64_t N, int64_t K, const v
   if (dtype == PTK_F32) return launch_gemm<float>(M, N, K, 1.0, A, sa0, sa1, B, sb0, sb1, 0.0, C, sc0, sc1, bias, act, st);
   if (dtype == PTK_F64) return launch_gemm<double>(M, N, K, 1.0, A, sa0, sa1, B, sb0, sb1, 0.0, C, sc0, sc1, bias, act, st);
   return fail(PTK_ERR_UNSUPPORTED, "ptk_gemm: dtype must be float32 or float64");
+}
+
+ptk_status ptk_mlp_chain(const void* x, int64_t sx0, void* y, int64_t sy0, int64_t M, int L, const void* const* W,
+                         const void* const* bias, const int* K, const int* N, const int* act, void* stream) {
+  PTK_REQUIRE_INIT();
+  if (L < 1 || L > MC_MAXL) return fail(PTK_ERR_ARG, "ptk_mlp_chain: 1..96 layers");
+  if (M <= 0) return PTK_OK;
+  MlpChain c;
+  c.L = L;
+  c.pad_ = 0;
+  for (int l = 0; l < L; ++l) {
+    if (K[l] < 1 || N[l] < 4 || K[l] > MC_MAXW || N[l] > MC_MAXW || (N[l] & 3) || (l > 0 && K[l] != N[l - 1]))
+      return fail(PTK_ERR_ARG, "ptk_mlp_chain: layer widths must be <= 128, N a multiple of 4, K_l == N_(l-1)");
+    if (((uintptr_t)W[l] & 15) != 0) return fail(PTK_ERR_ARG, "ptk_mlp_chain: weights must be 16-byte aligned");
+    c.layer[l].W = (const float*)W[l];
+    c.layer[l].bias = bias ? (const float*)bias[l] : nullptr;
+    c.layer[l].K = K[l];
+    c.layer[l].N = N[l];
+    c.layer[l].act = act ? act[l] : 0;
+    c.layer[l].pad_ = 0;
+  }
+  const int smem = (2 * MC_ROWS * MC_MAXW + 2 * MC_MAXW * MC_MAXW) * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTK_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((M + MC_ROWS - 1) / MC_ROWS);
+  mlp_chain_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)x, sx0, (float*)y, sy0, M, c);
+  PTK_LAUNCH_CHECK("mlp_chain");
+  return PTK_OK;
 }
 
 ptk_status ptk_gemm(int dtype, int64_t M, int64_t N, int64_t K, double alpha, const void* A, int64_t sa0,

@@ -2,7 +2,7 @@
 
 from __future__ import annotations
 
-from pytensor_b200.vm.nodes_blas import Dot22Node, GemmBiasActNode
+from pytensor_b200.vm.nodes_blas import Dot22Node, GemmBiasActNode, MlpChainNode
 from pytensor_b200.vm.nodes_elemwise import CAReduceNode, ElemwiseNode, ElemwiseReduceNode
 from pytensor_b200.vm.vm import Step
 
@@ -132,3 +132,56 @@ def fuse_elemwise_reduce(steps, output_slots, opts):
                 continue
         new_steps.append(st)
     return new_steps
+
+
+def fuse_small_mlp_chains(steps, output_slots, opts, min_layers=4):
+    """Runs of >= `min_layers` dense layers, each product read only by the next one as its A operand ==> one MlpChainNode
+    step at the position of the run's LAST layer (every weight / bias slot is available there).  Whether the chain
+    executes as one launch is decided per call from the actual shapes (MlpChainNode)."""
+    dense = (Dot22Node, GemmBiasActNode)
+    readers, producer = {}, {}
+    for i, st in enumerate(steps):
+        for s in st.ins:
+            readers.setdefault(s, []).append(i)
+        for o in st.outs:
+            producer[o] = i
+    outset = set(output_slots)
+
+    def is_layer(st):
+        return type(st.impl) in dense and not getattr(st.impl, "scalar", False) and st.impl.dtype == "float32"
+
+    nxt = {}
+    for i, st in enumerate(steps):
+        if not is_layer(st):
+            continue
+        o = st.outs[0]
+        rd = readers.get(o, [])
+        if o in outset or len(rd) != 1:
+            continue
+        j = rd[0]
+        if j > i and is_layer(steps[j]) and steps[j].ins[0] == o and o not in steps[j].ins[1:]:
+            nxt[i] = j
+    heads = set(nxt) - set(nxt.values())
+    repl, drop = {}, set()
+    for hd in sorted(heads):
+        chain = [hd]
+        while chain[-1] in nxt:
+            chain.append(nxt[chain[-1]])
+        if len(chain) < min_layers:
+            continue
+        ins = [steps[chain[0]].ins[0]]
+        layers = []
+        for i in chain:
+            st = steps[i]
+            has_bias = type(st.impl) is GemmBiasActNode and len(st.ins) > 2
+            ins += [st.ins[1]] + ([st.ins[2]] if has_bias else [])
+            layers.append((st.impl, has_bias))
+        last = chain[-1]
+        # every other input must exist before the first layer's A operand does NOT matter: the fused step sits at `last`,
+        # after every constituent step, hence after everything any of them read
+        node = MlpChainNode(layers, name=f"MlpChain[{len(chain)} layers]")
+        repl[last] = Step(node, ins, list(steps[last].outs), origin=steps[last].origin)
+        drop.update(chain[:-1])
+    if not repl:
+        return steps
+    return [repl.get(i, st) for i, st in enumerate(steps) if i not in drop]

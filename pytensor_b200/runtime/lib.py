@@ -99,6 +99,8 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_void_p]),
     "ptk_gemm_exact_main_default": (c_int, []),
     "ptk_gemm_lead_bits": (c_int, [c_int64]),
+    "ptk_mlp_chain": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_void_p),
+                              POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "ptk_gemv": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_double,
                          c_void_p, c_int64, c_void_p]),
     "ptk_ger": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

@@ -447,3 +447,82 @@ class BatchedDotNode(Node):
                 for i in range(nb):
                     gemm(self.dtype, 1.0, A[i], B[i], 0.0, out[i], self.precision)
         return [Val(d=out)]
+
+
+class MlpChainNode(Node):
+    """A run of >= 4 dense layers h <- act(h @ W_l + b_l) in which every product feeds only the next one (found by
+    link/cuda/fusion_passes.py::fuse_small_mlp_chains).  When every layer is at most 128 wide — the BASELINE metric graph at
+    n = 64: 84 layers of 64x64 — the whole chain is ONE launch (`ptk_mlp_chain`: activations stay in shared memory, weights
+    stream in behind the arithmetic) instead of one launch per layer at ~3 us each; otherwise the constituent nodes run one
+    after the other exactly as they would have in the program (tensor cores, resident weights, chained operands).
+    Inputs: [A0, W_0, (b_0), W_1, (b_1), ...]; `layers` = [(node, has_bias), ...]."""
+
+    MAX_W = 128
+
+    def __init__(self, layers, name="MlpChain"):
+        self.layers = list(layers)
+        self.name = name
+        self.fused_calls = self.unfused_calls = 0
+        pos, wpos = 1, []
+        for _, has_bias in self.layers:
+            wpos.append(pos)
+            pos += 2 if has_bias else 1
+        self.weight_in_positions = wpos   # (Program.weight_inputs: the B operands this node reads directly)
+
+    def _small(self, vals):
+        if vals[0].ndim != 2 or vals[0].dtype != "float32" or vals[0].shape[0] == 0 or not 1 <= vals[0].shape[1] <= self.MAX_W:
+            return None
+        pos = 1
+        for node, has_bias in self.layers:   # shapes first (metadata only): nothing is uploaded for a chain that stays unfused
+            w = vals[pos]
+            if node.dtype != "float32" or w.ndim != 2 or w.dtype != "float32" or not 4 <= w.shape[1] <= self.MAX_W or w.shape[1] % 4:
+                return None
+            pos += 2 if has_bias else 1
+        A = vals[0].dev()
+        if A.shape[1] > 1 and A.stride(1) != 1:
+            return None
+        width, pos, spec = A.shape[1], 1, []
+        if not 1 <= width <= self.MAX_W:
+            return None
+        for node, has_bias in self.layers:
+            W = vals[pos].dev()
+            b = vals[pos + 1].dev() if has_bias else None
+            if (W.dim() != 2 or W.shape[0] != width or not 4 <= W.shape[1] <= self.MAX_W or W.shape[1] % 4 or not W.is_contiguous()
+                    or dev.ptr(W) % 16 or W.dtype != torch.float32):
+                return None
+            if has_bias and (b is None or b.numel() != W.shape[1] or not b.is_contiguous() or b.dtype != torch.float32):
+                return None
+            spec.append((W, b, int(getattr(node, "act", 0))))
+            width = W.shape[1]
+            pos += 2 if has_bias else 1
+        return A, spec
+
+    def run(self, vals):
+        small = self._small(vals) if _os.environ.get("PTK_MLP_CHAIN", "1") != "0" else None
+        if small is None:
+            self.unfused_calls += 1
+            h, pos = vals[0], 1
+            for node, has_bias in self.layers:
+                n = 2 if has_bias else 1
+                h = node.run([h, *vals[pos:pos + n]])[0]   # the previous activation dies with this rebinding
+                pos += n
+            return [h]
+        self.fused_calls += 1
+        A, spec = small
+        import ctypes
+
+        L = _lib.lib()
+        cur, M = A, A.shape[0]
+        for s0 in range(0, len(spec), 96):                  # (ptk_mlp_chain takes up to 96 layers per launch)
+            seg = spec[s0:s0 + 96]
+            n = len(seg)
+            out = dev.empty((M, seg[-1][0].shape[1]), "float32")
+            Wp = (ctypes.c_void_p * n)(*[dev.ptr(w) for w, _, _ in seg])
+            Bp = (ctypes.c_void_p * n)(*[(dev.ptr(b) if b is not None else None) for _, b, _ in seg])
+            Ks = (ctypes.c_int * n)(*[w.shape[0] for w, _, _ in seg])
+            Ns = (ctypes.c_int * n)(*[w.shape[1] for w, _, _ in seg])
+            acts = (ctypes.c_int * n)(*[a for _, _, a in seg])
+            _lib.check(L.ptk_mlp_chain(dev.ptr(cur), cur.stride(0), dev.ptr(out), out.stride(0), M, n, Wp, Bp, Ks, Ns, acts,
+                                       dev.stream_ptr()), "ptk_mlp_chain")
+            cur = out
+        return [Val(d=cur)]

@@ -142,6 +142,8 @@ class Program:
             b_pos = {"Dot22Node": 1, "GemmBiasActNode": 1, "GemmNode": 3}
             slots = {st.ins[b_pos[type(st.impl).__name__]] for st in self.steps
                      if type(st.impl).__name__ in b_pos and len(st.ins) > b_pos[type(st.impl).__name__]}
+            for st in self.steps:   # fused nodes that still read weight matrices directly (MlpChainNode)
+                slots.update(st.ins[p] for p in getattr(st.impl, "weight_in_positions", ()) if p < len(st.ins))
             self._weight_inputs = ({k: s for k, s in enumerate(self.inputs) if s in slots},
                                    {s for s in self.constants if s in slots})
         return self._weight_inputs

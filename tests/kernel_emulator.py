@@ -193,7 +193,7 @@ class EmulatedKernel:
         body = body.replace("__shared__ __align__(128)", "alignas(128) static")
         if dynamic_smem:
             body = re.sub(r"extern __shared__[^\n;]*\b" + re.escape(dynamic_smem) + r"\[\];",
-                          f"alignas(16) static unsigned char {dynamic_smem}[100 * 1024];", body)
+                          f"alignas(16) static unsigned char {dynamic_smem}[160 * 1024];", body)
             body = (WARP_SHIM if warp_shim else STATIC_SHIM) + body
         elif warp_shim:
             body = WARP_SHIM + body

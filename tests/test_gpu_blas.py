@@ -123,3 +123,49 @@ def test_gemv_beta_zero_ignores_nan_y(gpu):
     assert np.all(np.isfinite(got[0]))
     for _ in range(3):  # repeated calls reuse NaN-poisoned allocator blocks; result must stay finite
         assert np.all(np.isfinite(f(Av, xv)[0]))
+
+
+def _chain_graph(widths, acts, bias=True):
+    x = pt.fmatrix("x")
+    Ws = [pt.fmatrix(f"W{i}") for i in range(len(widths) - 1)]
+    bs = [pt.fvector(f"b{i}") for i in range(len(widths) - 1)]
+    h = x
+    for W, b, a in zip(Ws, bs, acts):
+        h = pt.dot(h, W) + b if bias else pt.dot(h, W)
+        if a:
+            h = pt.tanh(h)
+    return x, Ws, bs, h
+
+
+@pytest.mark.parametrize("M,widths,acts,bias", [
+    (64, [64] * 9, [1] * 8, True),                         # the metric graph's layer shape
+    (37, [20, 128, 4, 68, 128, 12], [1, 1, 1, 1, 1], True),  # ragged widths, rows not a multiple of 16
+    (130, [32, 32, 32, 32, 32], [1, 1, 1, 1], False),       # tanh(A @ B) layers without bias
+])
+def test_small_mlp_chain_is_one_launch_and_matches_the_c_linker(gpu, M, widths, acts, bias):
+    """>= 4 dense layers of at most 128 columns run as ONE kernel (MlpChainNode / ptk_mlp_chain); same 1e-5 bar as the
+    layer-by-layer path."""
+    pytensor.config.floatX = "float32"
+    rng = np.random.default_rng(71)
+    x, Ws, bs, h = _chain_graph(widths, acts, bias)
+    ins = [x, *Ws, *(bs if bias else [])]
+    vals = [rng.standard_normal((M, widths[0])).astype("float32")]
+    vals += [(rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype("float32") for i in range(len(widths) - 1)]
+    if bias:
+        vals += [(rng.standard_normal(widths[i + 1]) * 0.1).astype("float32") for i in range(len(widths) - 1)]
+    f, _ = compare_cuda_and_cvm(ins, [h, h.sum(axis=0)], vals, rtol=1e-5, atol=1e-5)
+    chain = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "MlpChainNode"]
+    assert len(chain) == 1 and chain[0].fused_calls >= 1 and chain[0].unfused_calls == 0
+
+
+def test_mlp_chain_with_a_wide_layer_runs_layer_by_layer(gpu):
+    pytensor.config.floatX = "float32"
+    rng = np.random.default_rng(72)
+    widths = [64, 300, 64, 64, 64]
+    x, Ws, bs, h = _chain_graph(widths, [1, 1, 1, 1])
+    vals = [rng.standard_normal((40, 64)).astype("float32")]
+    vals += [(rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype("float32") for i in range(4)]
+    vals += [(rng.standard_normal(widths[i + 1]) * 0.1).astype("float32") for i in range(4)]
+    f, _ = compare_cuda_and_cvm([x, *Ws, *bs], [h], vals, rtol=1e-5, atol=1e-5)
+    chain = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "MlpChainNode"]
+    assert len(chain) == 1 and chain[0].fused_calls == 0 and chain[0].unfused_calls >= 1

@@ -502,3 +502,52 @@ def test_aligned_three_piece_split_is_exact_and_on_the_row_grid(tmp_path, R, Cc,
 
     assert L.load_library().ptk_gemm_lead_bits(4096) == 7 and L._TraceLib().ptk_gemm_lead_bits(4096) == 7
     assert (2 ** 7) ** 2 * 1024 <= 2 ** 24
+
+
+# ---- a chain of small dense layers in one launch (mlp_chain_kernel, csrc/ptk_blas.cu) -----------------------------------------
+@pytest.mark.parametrize("M,widths,acts,with_bias", [
+    (37, [64, 64, 64, 64, 64], [1, 1, 1, 1], True),          # the metric graph's layer shape, rows not a multiple of 16
+    (16, [20, 128, 4, 68, 128], [1, 0, 1, 0], True),         # ragged widths, both column groups, no activation on some layers
+    (5, [128, 128], [1], False),                             # a single widest layer without bias
+    (50, [8, 12, 8, 12, 8, 12, 8], [0, 0, 1, 1, 0, 1], True),
+])
+def test_small_mlp_chain_kernel(tmp_path, M, widths, acts, with_bias):
+    """h <- act(h @ W_l + b_l) for all layers inside one CTA per 16 rows: activations ping-pong between two shared-memory
+    buffers, the next layer's weights stream in while the current layer is computed; fp32 FMA, k ascending."""
+    rng = np.random.default_rng(len(widths) * 100 + M)
+    text = open(os.path.join(CSRC, "ptk_blas.cu")).read()
+    i0 = text.index("constexpr int MC_MAXW")
+    i1 = text.index("__device__ __forceinline__ void mc_cp_async16")
+    defs = text[i0:i1]
+    shim = ("#define __grid_constant__\nstruct alignas(16) float4 { float x, y, z, w; };\n" + defs +
+            "static inline void mc_cp_async16(float* d, const float* s) { std::memcpy(d, s, 16); }\n"
+            "static inline void mc_cp_async_wait_all() {}\nusing std::fmaf;\n")
+    src = shim + extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), "mlp_chain_kernel").replace(
+        "extern __shared__ float mc_smem[];", "alignas(16) static float mc_smem[2 * 16 * 128 + 2 * 128 * 128];")
+    k = EmulatedKernel(src, "mlp_chain_kernel", tmp_path, threaded=True)
+
+    class MlpLayer(ctypes.Structure):
+        _fields_ = [("W", c_void_p), ("bias", c_void_p), ("K", c_int), ("N", c_int), ("act", c_int), ("pad_", c_int)]
+
+    class MlpChain(ctypes.Structure):
+        _fields_ = [("L", c_int), ("pad_", c_int), ("layer", MlpLayer * 96)]
+
+    L = len(widths) - 1
+    x = _aligned((M, widths[0]), "float32", rng)
+    Ws = [_aligned((widths[l], widths[l + 1]), "float32") for l in range(L)]
+    bs = [_aligned((widths[l + 1],), "float32", rng) for l in range(L)]
+    ch = MlpChain()
+    ch.L = L
+    ref = x.astype(np.float64)
+    for l in range(L):
+        Ws[l][...] = (rng.standard_normal(Ws[l].shape) / np.sqrt(widths[l])).astype("float32")
+        ch.layer[l].W = Ws[l].ctypes.data
+        ch.layer[l].bias = bs[l].ctypes.data if with_bias else None
+        ch.layer[l].K, ch.layer[l].N, ch.layer[l].act = widths[l], widths[l + 1], acts[l]
+        ref = ref @ Ws[l].astype(np.float64) + (bs[l].astype(np.float64) if with_bias else 0.0)
+        if acts[l]:
+            ref = np.tanh(ref)
+    y = _aligned((M, widths[-1]), "float32")
+    y[...] = -7.0
+    k.launch((M + 15) // 16, 256, [_ptr(x), c_longlong(widths[0]), _ptr(y), c_longlong(widths[-1]), c_longlong(M), ch])
+    np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-6)
