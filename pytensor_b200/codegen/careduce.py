@@ -124,26 +124,16 @@ def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: 
         return "\n".join(out)
 
     row_scalars = "\n".join(f"      const {CTYPE[d]} s{k} = q{k}[0];" for k, d in enumerate(prog.in_dtypes) if col_modes[k] != 1)
-    # (A float32 map output is promoted element by element: adding the VW lanes of a vector in fp32 first would save
-    # conversions but breaks the reference's "fp32 sums accumulate in float64" contract on cancelling sums — measured 2e-6
-    # on a 200000-term row, tests/test_gpu_careduce.py::test_fp32_sum_accumulates_in_fp64.)
-    presum = False
+    # (A float32 map output is promoted to the accumulator type element by element: adding the VW lanes of a vector in fp32
+    # first would save conversions but breaks the reference's "fp32 sums accumulate in float64" contract on cancelling sums —
+    # measured 2e-6 on a 200000-term row, tests/test_gpu_careduce.py::test_fp32_sum_accumulates_in_fp64.)
 
     def compute(tag, cexpr):
         call_in = [f"v{tag}{k}.v[e]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
         decl = "\n".join(f"          PVec<{CTYPE[d]}, VW> o{tag}{k};" for k, d in enumerate(prog.out_dtypes))
         call_out = [f"o{tag}{k}.v[e]" for k in range(n_map)]
         st_ = "\n".join(f"          ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(w{k} + {cexpr}, o{tag}{k});" for k in stored)
-        if presum:
-            terms = [f"o{tag}0.v[{e}]" for e in range(vw)]
-            while len(terms) > 1:
-                terms = [f"({terms[q]} + {terms[q + 1]})" for q in range(0, len(terms), 2)]
-            red = f"          acc = ptk_red(acc, (ACC){terms[0]});"
-            body = f"""          #pragma unroll
-          for (int e = 0; e < VW; ++e) ptk_body({', '.join(call_in + call_out)});
-{red}"""
-        else:
-            body = f"""          #pragma unroll
+        body = f"""          #pragma unroll
           for (int e = 0; e < VW; ++e) {{
             ptk_body({', '.join(call_in + call_out)});
             acc = ptk_red(acc, (ACC)o{tag}0.v[e]);

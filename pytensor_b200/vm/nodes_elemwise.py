@@ -6,6 +6,7 @@ that only has torch + libptk.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_int, c_longlong, c_uint, c_void_p
 
 import numpy as np
@@ -579,10 +580,8 @@ class ElemwiseReduceNode(Node):
         # threads per row: more elements per thread amortise the per-row reduction (shuffles, shared memory, barriers)
         # — 128 when that still leaves at least 4 row blocks per SM, the full CTA for long rows of short matrices
         tpr = 32 if cols < 1024 else (128 if (cols < 16384 and rows >= sms * 8) else 256)
-        import os as _os
-
-        if _os.environ.get("PTK_K3_TPR"):   # developer A/B switch
-            tpr = int(_os.environ["PTK_K3_TPR"])
+        if os.environ.get("PTK_K3_TPR"):   # developer A/B switch
+            tpr = int(os.environ["PTK_K3_TPR"])
         rows_per_block = 256 // tpr
         row_blocks = (rows + rows_per_block - 1) // rows_per_block
         if row_blocks < sms:  # too few rows to fill the GPU with one CTA-row mapping: keep the two-kernel path
