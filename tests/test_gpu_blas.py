@@ -32,7 +32,7 @@ def test_dot22(gpu, dtype, shapes):
     y = pt.tensor("y", dtype=dtype, shape=(None, None))
     xv = rng.standard_normal(shapes[0]).astype(dtype)
     yv = rng.standard_normal(shapes[1]).astype(dtype)
-    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "float32" else {}
+    tol = dict(rtol=1e-5, atol_scale=1e-5) if dtype == "float32" else {}   # 1e-5 of the output scale
     compare_cuda_and_cvm([x, y], [pt.dot(x, y), pt.dot(x, y) * 0.6], [xv, yv], **tol)
 
 
@@ -52,8 +52,8 @@ def test_gemm_transposed_operands(gpu):
     y = pt.fmatrix("y")
     xv = rng.standard_normal((65, 129)).astype("float32")
     yv = rng.standard_normal((65, 77)).astype("float32")
-    compare_cuda_and_cvm([x, y], [pt.dot(x.T, y), pt.dot(y.T, x), pt.dot(x.T[::2], y[:, ::3])], [xv, yv], rtol=1e-4,
-                         atol=1e-4)
+    compare_cuda_and_cvm([x, y], [pt.dot(x.T, y), pt.dot(y.T, x), pt.dot(x.T[::2], y[:, ::3])], [xv, yv], rtol=1e-5,
+                         atol_scale=1e-5)
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
@@ -65,7 +65,7 @@ def test_gemv_variants(gpu, dtype):
     Av = rng.standard_normal((70, 1300)).astype(dtype)
     xv = rng.standard_normal(1300).astype(dtype)
     yv = rng.standard_normal(70).astype(dtype)
-    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "float32" else {}
+    tol = dict(rtol=1e-5, atol_scale=1e-5) if dtype == "float32" else {}
     compare_cuda_and_cvm([A, x, y], [pt.dot(A, x), y + 0.5 * pt.dot(A, x), pt.dot(A.T, y), pt.dot(x, A.T),
                                      pt.dot(x, x)], [Av, xv, yv], **tol)
 
@@ -99,7 +99,7 @@ def test_skinny_gemm_shapes(gpu, dtype):
     bv = rng.standard_normal((1500, 8)).astype(dtype)
     Xv = rng.standard_normal((1030, 8)).astype(dtype)
     Rv = rng.standard_normal((1500, 1030)).astype(dtype)
-    tol = dict(rtol=2e-4, atol=2e-4) if dtype == "float32" else dict(rtol=1e-9, atol=1e-9)
+    tol = dict(rtol=1e-5, atol_scale=1e-5) if dtype == "float32" else dict(rtol=1e-9, atol=1e-9)
     compare_cuda_and_cvm([beta, X, R], [pt.dot(beta, X.T), pt.dot(R, X), 0.5 * R + 2.0 * pt.dot(beta, X.T)], [bv, Xv, Rv], **tol)
 
 

@@ -70,7 +70,7 @@ def test_mlp_chain_bf16_vs_cvm(gpu):
     assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
     # and the native-precision linker meets the 1e-5 class bar on the same graph
     f32 = pytensor.function(ins, outs, mode="CUDA")
-    np.testing.assert_allclose(f32(*a)[0], ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f32(*a)[0], ref, rtol=1e-5, atol=1e-5)   # outputs of tanh: scale 1
 
 
 # ---- fp32-accurate tensor-core GEMM (bf16x3 operand split, ptk_gemm_tc_split): the DEFAULT mode="CUDA" path for large fp32 ----
