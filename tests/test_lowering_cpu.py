@@ -293,3 +293,31 @@ def test_random_variables_lower_to_the_device_sampler_and_keep_the_generator_pro
     with pytest.raises(NotImplementedError, match="no device sampler"):
         pytensor.function([], pt.random.multivariate_normal(np.zeros(2), np.eye(2), rng=rng), mode="CUDA")
     del st0
+
+
+def test_runs_of_dense_layers_become_one_chain_node_only_when_nothing_else_reads_them():
+    pytensor.config.floatX = "float32"
+    # the metric graph: 84 layers -> ONE MlpChainNode reading x, 84 weights and 84 bias rows
+    ins, outs, mk, _ = W.metric_graph(n=16, layers=84, scan_steps=4)
+    f = pytensor.function(ins, outs, mode="CUDA")
+    chain = [st for st in f.vm.executor.program.steps if type(st.impl).__name__ == "MlpChainNode"]
+    assert len(chain) == 1 and len(chain[0].impl.layers) == 84
+    assert len(chain[0].ins) == 1 + sum(2 if has_bias else 1 for _, has_bias in chain[0].impl.layers)
+    assert "GemmBiasActNode" not in _steps(f) and "Dot22Node" not in _steps(f)
+    # its weight inputs stay visible to the resident-weights bookkeeping
+    w_in, _ = f.vm.executor.program.weight_inputs()
+    assert len(w_in) == 84
+    # three layers (cfg3) are left alone; so is a run whose intermediate is also an output
+    ins, outs, mk, _ = W.cfg3_mlp(64)
+    assert "MlpChainNode" not in _steps(pytensor.function(ins, outs, mode="CUDA"))
+    x = pt.fmatrix("x")
+    Ws = [pt.fmatrix(f"W{i}") for i in range(6)]
+    hs = [x]
+    for Wi in Ws:
+        hs.append(pt.tanh(pt.dot(hs[-1], Wi)))
+    f = pytensor.function([x, *Ws], [hs[-1], hs[3]], mode="CUDA")       # layer 3's result escapes: no run of >= 4 remains
+    assert "MlpChainNode" not in _steps(f)
+    f = pytensor.function([x, *Ws], [hs[-1], hs[1]], mode="CUDA")       # layers 2..6 still form a run of five
+    chain = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "MlpChainNode"]
+    assert len(chain) == 1 and len(chain[0].layers) == 5
+    trace_function(f, [np.zeros((8, 16), dtype="float32")] + [np.zeros((16, 16), dtype="float32")] * 6)
