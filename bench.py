@@ -367,7 +367,11 @@ def bench_metric_graph(pytensor, W, cuda_mode, dev, torch, peaks, cvm):
     """The graph BASELINE.json's `metric` names: 84 x tanh(h@W+b), a 16-step Scan, a Sum — 265 compiled nodes; n=64
     (overhead-bound) and n=4096 (throughput-bound), the reference C linker timed beside both."""
     out = {}
-    for n, kw, steps, label in ((64, {}, 50, "n64"), (4096, {}, 2, "n4096"), (4096, {"gemm_precision": "bf16"}, 3, "n4096_bf16")):
+    cases = ((64, {}, 50, "n64"), (4096, {}, 2, "n4096"), (4096, {"gemm_precision": "bf16"}, 3, "n4096_bf16"))
+    only = [c for c in os.environ.get("PTK_BENCH_METRIC_CASES", "").split(",") if c]   # developer runs: a subset of the cases
+    for n, kw, steps, label in cases:
+        if only and label not in only:
+            continue
         ins, outs, make_args, meta = W.metric_graph(n=n)
         host = make_args()
         f = pytensor.function(ins, outs, mode=cuda_mode(device_outputs=True, borrow_outputs=True, **kw), trust_input=True)
@@ -434,7 +438,7 @@ def bench_metric_graph(pytensor, W, cuda_mode, dev, torch, peaks, cvm):
                     "ours_max_err_over_scale": e_ours, "reference_max_err_over_scale": e_ref,
                     "note": "informational yardstick: distance of each fp32 evaluation from the float64 one (same row slice)"}
         else:
-            rec["parity"] = parity(got, out["_exp_4096"], rtol=5e-2, atol=5e-2)
+            rec["parity"] = parity(got, out["_exp_4096"], rtol=5e-2, atol=5e-2) if "_exp_4096" in out else {}
             rec["parity"]["ok"] = None
             rec["parity"]["note"] = ("informational, no parity claim: bf16 operands through 84 chained layers and a sum over "
                                      "the rows (the opt-in CUDA_BF16 mode; the default mode above carries the parity bar)")
