@@ -551,3 +551,120 @@ def test_small_mlp_chain_kernel(tmp_path, M, widths, acts, with_bias):
     y[...] = -7.0
     k.launch((M + 15) // 16, 256, [_ptr(x), c_longlong(widths[0]), _ptr(y), c_longlong(widths[-1]), c_longlong(M), ch])
     np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-6)
+
+
+# ---- counter-based random draws (random_kernel, ptk_random.cu) -------------------------------------------------------------
+RNG_SHIM = r"""
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline double sinpi(double x) { return std::sin(M_PI * x); }
+static inline double cospi(double x) { return std::cos(M_PI * x); }
+using std::sqrt; using std::log; using std::exp; using std::pow; using std::fabs; using std::floor; using std::copysign;
+"""
+
+RNG_KAT = r"""
+extern "C" void emu_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  Philox p; p.k0 = key[0]; p.k1 = key[1];
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  p.block(c);
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+"""
+
+
+def _random_kernel(tmp_path, out_type="double"):
+    text = open(os.path.join(CSRC, "ptk_random.cu")).read()
+    body = text[text.index("struct Philox"):text.index("}  // namespace")]
+    return EmulatedKernel(RNG_SHIM + body + RNG_KAT, "random_kernel", tmp_path, template_args=out_type, type_subst={"OUT": out_type})
+
+
+def _draw(k, dist, n, key, seed, params=(), dtype=np.float64, grid=3):
+    out = np.full(n, -12345, dtype=dtype)
+    ps, keep = [], []   # `keep`: the parameter arrays must outlive the launch
+    for p in list(params) + [None] * (3 - len(params)):
+        if p is None:
+            ps += [c_void_p(None), c_longlong(0)]
+        else:
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            ps += [_ptr(p), c_longlong(0 if p.size == 1 else 1)]
+            keep.append(p)
+    k.launch(grid, 256, [c_int(dist), _ptr(out), c_longlong(n), ctypes.c_uint64(key), ctypes.c_uint64(seed), *ps])
+    return out
+
+
+def test_philox_block_matches_the_published_known_answers(tmp_path):
+    """Philox4x32-10 (Salmon et al., SC'11) known-answer vectors of the Random123 distribution: zero, all-ones and the
+    digits-of-pi counter/key."""
+    k = _random_kernel(tmp_path)
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c, kk, out = np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32), np.zeros(4, dtype=np.uint32)
+        k.lib.emu_philox(_ptr(c), _ptr(kk), _ptr(out))
+        assert tuple(int(v) for v in out) == want
+
+
+def test_random_kernel_streams_are_per_element_and_keyed(tmp_path):
+    """An element's draw depends on (key, seed, element index) only — not on the launch geometry — and changes with either
+    key word; uniforms lie strictly inside (0, 1)."""
+    k = _random_kernel(tmp_path)
+    a = _draw(k, 0, 5000, 0x1234567890abcdef, 42, grid=1)
+    b = _draw(k, 0, 5000, 0x1234567890abcdef, 42, grid=7)
+    np.testing.assert_array_equal(a, b)
+    assert np.all((a > 0) & (a < 1)) and len(np.unique(a)) == a.size
+    assert not np.array_equal(a, _draw(k, 0, 5000, 0x1234567890abcdee, 42))
+    assert not np.array_equal(a, _draw(k, 0, 5000, 0x1234567890abcdef, 43))
+    # a prefix of a longer fill is the shorter fill (streams are indexed, not consumed)
+    np.testing.assert_array_equal(_draw(k, 1, 100, 7, 9), _draw(k, 1, 5000, 7, 9)[:100])
+
+
+@pytest.mark.parametrize("dist,params,ref", [
+    (0, (-2.0, 3.0), ("uniform", dict(loc=-2.0, scale=5.0))),
+    (1, (1.5, 0.5), ("norm", dict(loc=1.5, scale=0.5))),
+    (2, (0.0, 2.0), ("halfnorm", dict(loc=0.0, scale=2.0))),
+    (3, (0.2, 0.4), ("lognorm", dict(s=0.4, scale=float(np.exp(0.2))))),
+    (4, (2.5,), ("expon", dict(scale=2.5))),
+    (5, (1.0, 0.7), ("laplace", dict(loc=1.0, scale=0.7))),
+    (6, (-1.0, 0.6), ("logistic", dict(loc=-1.0, scale=0.6))),
+    (7, (0.5, 1.5), ("gumbel_r", dict(loc=0.5, scale=1.5))),
+    (8, (0.3, 2.0), ("cauchy", dict(loc=0.3, scale=2.0))),
+    (15, (0.0, 1.5), ("halfcauchy", dict(loc=0.0, scale=1.5))),
+    (10, (0.4, 2.0), ("gamma", dict(a=0.4, scale=2.0))),
+    (10, (7.5, 0.5), ("gamma", dict(a=7.5, scale=0.5))),
+    (16, (3.0, 2.0), ("invgamma", dict(a=3.0, scale=2.0))),
+    (11, (0.7, 2.2), ("beta", dict(a=0.7, b=2.2))),
+    (13, (1.7,), ("weibull_min", dict(c=1.7))),
+    (14, (2.5, 1.5), ("pareto", dict(b=2.5, scale=1.5))),
+    (17, (4.0, 0.5, 2.0), ("t", dict(df=4.0, loc=0.5, scale=2.0))),
+])
+def test_random_kernel_distributions(tmp_path, dist, params, ref):
+    """Kolmogorov-Smirnov of 20000 emulated draws against scipy's CDF of the distribution the reference's RandomVariable
+    of that name samples (pytensor/tensor/random/basic.py)."""
+    import scipy.stats as st
+
+    k = _random_kernel(tmp_path)
+    x = _draw(k, dist, 20000, 0xfeedfacecafebeef, 1234 + dist, [np.array([p]) for p in params])
+    name, kw = ref
+    stat, p = st.kstest(x, getattr(st, name)(**kw).cdf)
+    assert p > 1e-3, (name, stat, p)
+
+
+def test_random_kernel_discrete_and_broadcast_parameters(tmp_path):
+    k = _random_kernel(tmp_path)
+    n = 20000
+    # Bernoulli with a per-element probability vector; integers in [low, high)
+    pvec = np.linspace(0.05, 0.95, n)
+    b = _draw(k, 9, n, 11, 22, [pvec])
+    assert set(np.unique(b)) <= {0.0, 1.0}
+    halves = b[: n // 2].mean(), b[n // 2:].mean()
+    assert abs(halves[0] - pvec[: n // 2].mean()) < 0.02 and abs(halves[1] - pvec[n // 2:].mean()) < 0.02
+    (tmp_path / "i64").mkdir()
+    ki = _random_kernel(tmp_path / "i64", "int64_t")
+    r = _draw(ki, 12, n, 5, 6, [np.array([-3.0]), np.array([4.0])], dtype=np.int64)
+    vals, counts = np.unique(r, return_counts=True)
+    assert vals.tolist() == list(range(-3, 4))
+    assert np.all(np.abs(counts / n - 1 / 7) < 0.015)
+    # per-element location vector with a scalar scale: the stride-0 / stride-1 parameter walk
+    loc = np.arange(n, dtype=np.float64)
+    x = _draw(k, 1, n, 3, 4, [loc, np.array([0.01])])
+    assert np.max(np.abs(x - loc)) < 0.1 and np.std(x - loc) == pytest.approx(0.01, rel=0.05)
