@@ -668,3 +668,300 @@ def test_random_kernel_discrete_and_broadcast_parameters(tmp_path):
     loc = np.arange(n, dtype=np.float64)
     x = _draw(k, 1, n, 3, 4, [loc, np.array([0.01])])
     assert np.max(np.abs(x - loc)) < 0.1 and np.std(x - loc) == pytest.approx(0.01, rel=0.05)
+
+
+# ---- native-precision BLAS family: gemm_simt_kernel / gemv_row|col_kernel / ger_kernel (ptk_blas.cu) ---------------------
+def _blas_text():
+    return open(os.path.join(CSRC, "ptk_blas.cu")).read()
+
+
+@pytest.mark.parametrize("dtype,a_kfast,b_nfast,M,N,K,beta,with_bias,act", [
+    ("float32", True, True, 70, 130, 37, 0.0, True, 1),       # row-major A and B, ragged tiles in all three dims, bias + tanh
+    ("float32", False, True, 64, 64, 16, 0.6, False, 0),      # A transposed view (M fast), exact tiles, beta * C
+    ("float64", True, False, 33, 47, 29, -1.0, False, 0),     # B transposed view (K fast)
+    ("float64", False, False, 5, 200, 3, 1.0, True, 0),       # both transposed, K smaller than one k-tile
+])
+def test_fma_gemm_kernel_strides_edges_and_epilogue(tmp_path, dtype, a_kfast, b_nfast, M, N, K, beta, with_bias, act):
+    """C = act(alpha*A@B + beta*C + bias) over arbitrary element strides; beta == 0 never reads C (NaN-poisoned here, the
+    AllocEmpty contract of pytensor/tensor/blas/gemm.py:194-198)."""
+    rng = np.random.default_rng(31)
+    cT, ct = ("float", c_float) if dtype == "float32" else ("double", c_double)
+    text = _blas_text()
+    src = text[text.index("constexpr int BM = 64"):text.index("// ---- skinny shapes")]
+    k = EmulatedKernel(src, "gemm_simt_kernel", tmp_path, threaded=True,
+                       template_args=f"{cT}, {str(a_kfast).lower()}, {str(b_nfast).lower()}", type_subst={"T": cT})
+    A = rng.standard_normal((M, K)).astype(dtype) if a_kfast else rng.standard_normal((K, M)).astype(dtype).T
+    B = rng.standard_normal((K, N)).astype(dtype) if b_nfast else rng.standard_normal((N, K)).astype(dtype).T
+    # C: every second column of a wider buffer (a non-unit column stride)
+    Cbuf = rng.standard_normal((M, 2 * N)).astype(dtype)
+    if beta == 0.0:
+        Cbuf[:] = np.nan
+    C = Cbuf[:, ::2]
+    bias = rng.standard_normal(N).astype(dtype)
+    expect = 0.7 * (A.astype(np.float64) @ B.astype(np.float64))
+    if beta != 0.0:
+        expect = expect + beta * C.astype(np.float64)
+    if with_bias:
+        expect = expect + bias
+    if act:
+        expect = np.tanh(expect)
+    isz = A.itemsize
+    args = [c_longlong(M), c_longlong(N), c_longlong(K), ct(0.7), c_void_p(A.ctypes.data), c_longlong(A.strides[0] // isz),
+            c_longlong(A.strides[1] // isz), c_void_p(B.ctypes.data), c_longlong(B.strides[0] // isz),
+            c_longlong(B.strides[1] // isz), ct(beta), c_void_p(C.ctypes.data), c_longlong(C.strides[0] // isz),
+            c_longlong(C.strides[1] // isz), _ptr(bias) if with_bias else c_void_p(None), c_int(act)]
+    untouched = Cbuf[:, 1::2].copy()
+    k.launch(((N + 63) // 64, (M + 63) // 64), 256, args)
+    tol = 2e-5 if dtype == "float32" else 1e-12
+    np.testing.assert_allclose(C, expect, rtol=tol, atol=tol)
+    np.testing.assert_array_equal(Cbuf[:, 1::2], untouched)   # the columns between the strided ones are not written
+
+
+@pytest.mark.parametrize("dtype,M,N,nchunks,beta", [("float32", 70, 1300, 1, 0.5), ("float64", 9, 5000, 3, 1.0), ("float32", 33, 17, 1, 0.0)])
+def test_gemv_row_kernel(tmp_path, dtype, M, N, nchunks, beta):
+    """y = alpha*A@x + beta*y, one warp per (row, column chunk): strided x and y, split rows accumulate atomically into the
+    pre-scaled y, beta == 0 never reads y (pytensor/tensor/blas/gemv.py:79-86)."""
+    rng = np.random.default_rng(32)
+    cT, ct = ("float", c_float) if dtype == "float32" else ("double", c_double)
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), "gemv_row_kernel")
+    k = EmulatedKernel(src, "gemv_row_kernel", tmp_path, threaded=True, template_args=cT, type_subst={"T": cT}, warp_shim=True)
+    A = rng.standard_normal((M, N)).astype(dtype)
+    xb = rng.standard_normal(3 * N).astype(dtype)
+    yb = rng.standard_normal(2 * M).astype(dtype)
+    x, y = xb[::3], yb[::2]
+    y0 = y.astype(np.float64).copy()
+    if beta == 0.0:
+        y[:] = np.nan
+    if nchunks > 1:
+        y *= np.asarray(beta, dtype=dtype)   # what scale_vec_kernel does before a split launch
+    expect = 1.25 * (A.astype(np.float64) @ x.astype(np.float64)) + (beta * y0 if beta != 0.0 else 0.0)
+    chunk = (N + nchunks - 1) // nchunks
+    args = [c_longlong(M), c_longlong(N), ct(1.25), _ptr(A), c_longlong(N), c_longlong(1), c_void_p(x.ctypes.data), c_longlong(3),
+            ct(beta), c_void_p(y.ctypes.data), c_longlong(2), c_longlong(chunk), c_longlong(nchunks)]
+    k.launch(2, 256, args)
+    tol = 3e-5 if dtype == "float32" else 1e-11
+    np.testing.assert_allclose(y, expect, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype,M,N,nchunks", [("float64", 70, 1300, 4), ("float32", 31, 9, 1), ("float32", 100, 300, 2)])
+def test_gemv_col_kernel(tmp_path, dtype, M, N, nchunks):
+    """The column-fast variant (A.T views: sa0 == 1): lanes own consecutive rows, 8 column groups reduced through shared memory,
+    column chunks accumulate atomically into the pre-scaled y."""
+    rng = np.random.default_rng(33)
+    cT, ct = ("float", c_float) if dtype == "float32" else ("double", c_double)
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), "gemv_col_kernel")
+    k = EmulatedKernel(src, "gemv_col_kernel", tmp_path, threaded=True, template_args=cT, type_subst={"T": cT}, warp_shim=True)
+    At = rng.standard_normal((N, M)).astype(dtype)   # A = At.T: element (m, n) at m*1 + n*M
+    x = rng.standard_normal(N).astype(dtype)
+    y = rng.standard_normal(M).astype(dtype)
+    expect = 0.5 * (At.T.astype(np.float64) @ x.astype(np.float64)) + y.astype(np.float64)
+    chunk = (N + nchunks - 1) // nchunks
+    args = [c_longlong(M), c_longlong(N), ct(0.5), _ptr(At), c_longlong(1), c_longlong(M), _ptr(x), c_longlong(1), _ptr(y),
+            c_longlong(1), c_longlong(chunk)]
+    k.launch(((M + 31) // 32, nchunks), 256, args)
+    tol = 3e-5 if dtype == "float32" else 1e-11
+    np.testing.assert_allclose(y, expect, rtol=tol, atol=tol)
+
+
+def test_ger_kernel_strided_update(tmp_path):
+    """A += alpha * outer(x, y) in place over a column-strided A and strided vectors (pytensor/tensor/blas/ger.py:8)."""
+    rng = np.random.default_rng(34)
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), "ger_kernel")
+    k = EmulatedKernel(src, "ger_kernel", tmp_path, template_args="double", type_subst={"T": "double"})
+    M, N = 40, 50
+    Abuf = rng.standard_normal((M, 2 * N))
+    A = Abuf[:, ::2]
+    xb, yb = rng.standard_normal(2 * M), rng.standard_normal(3 * N)
+    expect = A + 0.3 * np.outer(xb[::2], yb[::3])
+    other = Abuf[:, 1::2].copy()
+    args = [c_longlong(M), c_longlong(N), c_double(0.3), c_void_p(xb.ctypes.data), c_longlong(2), c_void_p(yb.ctypes.data),
+            c_longlong(3), c_void_p(A.ctypes.data), c_longlong(2 * N), c_longlong(2)]
+    k.launch(3, 256, args)
+    np.testing.assert_allclose(A, expect, rtol=1e-14, atol=1e-14)
+    np.testing.assert_array_equal(Abuf[:, 1::2], other)
+
+
+# ---- gather / scatter kernels (ptk_index.cu) ---------------------------------------------------------------------------------
+INDEX_SHIM = r"""
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void emu_atomic_add(int* p, int v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void emu_atomic_add(long* p, long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void emu_atomic_add(float* p, float v) { atomicAdd(p, v); }    // (the float / double atomicAdd of the warp shim)
+static inline void emu_atomic_add(double* p, double v) { atomicAdd(p, v); }
+"""
+
+
+def _index_kernel(tmp_path, name, targs, subst, smem=None, fix=None):
+    src = extract_static_kernel(os.path.join(CSRC, "ptk_index.cu"), name)
+    for a, b in (fix or {}).items():
+        assert a in src
+        src = src.replace(a, b)
+    return EmulatedKernel(INDEX_SHIM + src, name, tmp_path, threaded=True, template_args=targs, type_subst=subst,
+                          dynamic_smem=smem, warp_shim=True)
+
+
+@pytest.mark.parametrize("outer,n_src,n_idx,inner", [(3, 11, 7, 5), (1, 40, 300, 1), (4, 6, 9, 2)])
+def test_take_kernel_negative_and_out_of_range_indices(tmp_path, outer, n_src, n_idx, inner):
+    """out[o, j, i] = src[o, idx[j], i] with NumPy's negative-index wrap; an index outside [-n, n) raises the error word and
+    leaves that output element alone (the host turns the word into IndexError, like tensor/subtensor.py:2164)."""
+    rng = np.random.default_rng(41)
+    k = _index_kernel(tmp_path, "take_kernel", "uint32_t", {"T": "uint32_t"})
+    src = rng.integers(0, 1 << 31, size=(outer, n_src, inner), dtype=np.uint32)
+    idx = rng.integers(-n_src, n_src, size=n_idx).astype(np.int64)
+    out = np.full((outer, n_idx, inner), 77, dtype=np.uint32)
+    err = np.zeros(1, dtype=np.int32)
+    args = [_ptr(out), _ptr(src), _ptr(idx), c_longlong(outer), c_longlong(n_src), c_longlong(n_idx), c_longlong(inner), _ptr(err)]
+    k.launch(2, 256, args)
+    np.testing.assert_array_equal(out, src[:, idx, :])
+    assert err[0] == 0
+    idx[n_idx // 2] = n_src          # one past the end
+    out[:] = 77
+    k.launch(2, 256, args)
+    assert err[0] == 1
+    good = np.ones(n_idx, dtype=bool)
+    good[n_idx // 2] = False
+    np.testing.assert_array_equal(out[:, good, :], src[:, idx[good], :])
+    assert np.all(out[:, n_idx // 2, :] == 77)
+
+
+@pytest.mark.parametrize("kernel,outer,n_src,n_idx,misalign", [
+    ("take_lastaxis_kernel", 37, 500, 256, 0),      # vector path: 4 rows in flight + the row remainder
+    ("take_lastaxis_kernel", 9, 64, 70, 0),         # n_idx not a multiple of 4: scalar stores, ragged last thread
+    ("take_lastaxis_kernel", 20, 100, 128, 1),      # output base not 16-byte aligned
+    ("take_lastaxis_smem_kernel", 70, 50, 256, 0),  # staged source rows, last row block short (70 = 4*16 + 6)
+    ("take_lastaxis_smem_kernel", 64, 33, 130, 0),  # scalar tail
+])
+def test_take_along_the_last_axis_kernels(tmp_path, kernel, outer, n_src, n_idx, misalign):
+    rng = np.random.default_rng(42)
+    smem = kernel.endswith("smem_kernel")
+    k = _index_kernel(tmp_path, kernel, "uint32_t, 16" if smem else "uint32_t", {"T": "uint32_t"}, smem="take_smem" if smem else None)
+    src = rng.integers(0, 1 << 31, size=(outer, n_src), dtype=np.uint32)
+    idx = rng.integers(-n_src, n_src, size=n_idx).astype(np.int64)
+    buf = _aligned((outer * n_idx + 8,), "uint32")
+    out = buf[misalign:misalign + outer * n_idx].reshape(outer, n_idx)
+    out[:] = 5
+    err = np.zeros(1, dtype=np.int32)
+    args = [c_void_p(out.ctypes.data), _ptr(src), _ptr(idx), c_longlong(outer), c_longlong(n_src), c_longlong(n_idx), _ptr(err)]
+    grid = (1, (outer + 15) // 16) if smem else ((n_idx + 1023) // 1024, 3)
+    k.launch(grid, 256, args)
+    np.testing.assert_array_equal(out, src[:, idx])
+    assert err[0] == 0
+    idx[3] = -n_src - 1
+    out[:] = 5
+    k.launch(grid, 256, args)
+    assert err[0] == 1
+    keep = np.arange(n_idx) != 3
+    np.testing.assert_array_equal(out[:, keep], src[:, idx[keep]])
+    assert np.all(out[:, 3] == 5)
+
+
+@pytest.mark.parametrize("ctype,dtype,op", [("float", np.float32, 1), ("double", np.float64, 1), ("int64_t", np.int64, 1),
+                                            ("int32_t", np.int32, 0)])
+def test_put_kernel_set_and_accumulate(tmp_path, ctype, dtype, op):
+    """x[:, idx, :] = y (unique indices) / np.add.at(x, (:, idx, :), y) with repeated and negative indices — the atomics
+    path of AdvancedIncSubtensor (tensor/subtensor.py:2275)."""
+    rng = np.random.default_rng(43)
+    k = _index_kernel(tmp_path, "put_kernel", f"{ctype}, {op}", {"T": ctype},
+                      fix={"atomic_add_t<T>(p, y[t])": "emu_atomic_add(p, y[t])"})
+    outer, n_dst, n_idx, inner = 3, 13, 40 if op else 9, 4
+    x = (rng.standard_normal((outer, n_dst, inner)) * 8).astype(dtype)
+    y = (rng.standard_normal((outer, n_idx, inner)) * 8).astype(dtype)
+    idx = (rng.integers(-n_dst, n_dst, size=n_idx) if op else rng.permutation(n_dst)[:n_idx] - n_dst * (np.arange(n_idx) % 2)).astype(np.int64)
+    want = x.copy()
+    if op:
+        np.add.at(want, (slice(None), idx, slice(None)), y)
+    else:
+        want[:, idx, :] = y
+    err = np.zeros(1, dtype=np.int32)
+    k.launch(2, 256, [_ptr(x), _ptr(y), _ptr(idx), c_longlong(outer), c_longlong(n_dst), c_longlong(n_idx), c_longlong(inner), _ptr(err)])
+    if np.issubdtype(dtype, np.floating):
+        np.testing.assert_allclose(x, want, rtol=1e-5 if dtype == np.float32 else 1e-13, atol=1e-4 if dtype == np.float32 else 1e-12)
+    else:
+        np.testing.assert_array_equal(x, want)
+    assert err[0] == 0
+
+
+@pytest.mark.parametrize("dtype,ctype,outer,n_dst,n_idx", [(np.float32, "float", 21, 64, 1024), (np.float64, "double", 5, 7, 300),
+                                                          (np.float32, "float", 3, 130, 33)])
+def test_put_rows_segmented_scatter_add(tmp_path, dtype, ctype, outer, n_dst, n_idx):
+    """x[:, idx] += y with ONE index vector shared by all rows (the group index of a hierarchical model): histogram + exclusive
+    scan, stable permutation, one warp per row adding each bin's contributions in ascending source order — the order of
+    np.add.at, so the result is deterministic and, in fp64, bit-identical to NumPy's."""
+    rng = np.random.default_rng(44)
+    idx = rng.integers(-n_dst, n_dst, size=n_idx).astype(np.int64)
+    idx[rng.integers(0, n_idx, size=3)] = n_dst - 1
+    offsets = np.full(n_dst + 1, -1, dtype=np.int32)
+    perm = np.full(n_idx, -1, dtype=np.int32)
+    err = np.zeros(1, dtype=np.int32)
+    (tmp_path / "a").mkdir(), (tmp_path / "b").mkdir(), (tmp_path / "c").mkdir()
+    k1 = _index_kernel(tmp_path / "a", "put_rows_offsets_kernel", "", None, fix={"extern __shared__ int cnt[];": "static int cnt[16384];"})
+    k1.launch(1, 1024, [_ptr(idx), c_longlong(n_idx), c_longlong(n_dst), _ptr(offsets), _ptr(err)])
+    norm = np.where(idx < 0, idx + n_dst, idx)
+    counts = np.bincount(norm, minlength=n_dst)
+    assert offsets.tolist() == np.concatenate([[0], np.cumsum(counts)]).tolist() and err[0] == 0
+    k2 = _index_kernel(tmp_path / "b", "put_rows_perm_kernel", "", None, fix={"extern __shared__ int sidx[];": "static int sidx[16384];"})
+    k2.launch((n_dst + 255) // 256, 256, [_ptr(idx), c_longlong(n_idx), c_longlong(n_dst), _ptr(offsets), _ptr(perm)])
+    assert perm.tolist() == np.argsort(norm, kind="stable").tolist()
+    k3 = _index_kernel(tmp_path / "c", "put_rows_kernel", ctype, {"T": ctype}, smem="put_smem")
+    x = rng.standard_normal((outer, n_dst)).astype(dtype)
+    y = rng.standard_normal((outer, n_idx)).astype(dtype)
+    want = x.copy()
+    np.add.at(want, (slice(None), idx), y)
+    wpb = 4
+    k3.launch(2, 256, [_ptr(x), _ptr(y), _ptr(offsets), _ptr(perm), c_longlong(outer), c_longlong(n_dst), c_longlong(n_idx), c_int(wpb)])
+    if dtype == np.float64:
+        np.testing.assert_array_equal(x, want)
+    else:
+        np.testing.assert_allclose(x, want, rtol=1e-5, atol=1e-5)
+
+
+class _Dims(ctypes.Structure):
+    _fields_ = [("ndim", c_int), ("shape", c_longlong * 8), ("a", c_longlong * 8), ("b", c_longlong * 8)]
+
+
+COLLAPSE_EXPORT = r"""
+extern "C" long long emu_collapse(Dims* d, const int64_t* shape, const int64_t* sa, const int64_t* sb, int ndim) {
+  return collapse(*d, shape, sa, sb, ndim);
+}
+"""
+
+
+@pytest.mark.parametrize("kernel,ctype,dtype", [("copy_strided_kernel", "uint32_t", np.float32), ("copy_strided_kernel", "uint64_t", np.float64),
+                                                ("inc_strided_kernel", "float", np.float32), ("inc_strided_kernel", "int16_t", np.int16)])
+def test_strided_copy_and_increment_with_collapsed_dims(tmp_path, kernel, ctype, dtype):
+    """dst[...] = src[...] / dst[...] += src[...] over up-to-8-d element strides: the host-side dimension collapse (size-1 dims
+    dropped, neighbours contiguous in BOTH operands merged) and the kernel's mixed-radix walk, on a transposed + reversed +
+    broadcast source and a sliced destination (DeepCopyOp / Alloc / IncSubtensor: compile/ops.py:121, tensor/basic.py:1545,
+    tensor/subtensor.py:1441)."""
+    rng = np.random.default_rng(45)
+    text = open(os.path.join(CSRC, "ptk_index.cu")).read()
+    src_txt = text[text.index("constexpr int kMaxDims"):text.index("// Contiguous destination and source both 16-byte aligned")]
+    if kernel == "inc_strided_kernel":
+        src_txt += extract_static_kernel(os.path.join(CSRC, "ptk_index.cu"), kernel)
+    k = EmulatedKernel(src_txt + COLLAPSE_EXPORT, kernel, tmp_path, template_args=ctype, type_subst={"T": ctype})
+    mk = (lambda shape: (rng.standard_normal(shape) * 50).astype(dtype))
+    dbuf = mk((6, 5, 4, 10))
+    sbuf = mk((7, 1, 4, 6))
+    dst = dbuf[1:6, :, :, 2:9:2]                       # (5, 5, 4, 4): sliced rows, strided last axis
+    src = np.broadcast_to(sbuf.transpose(3, 1, 2, 0)[::-1][:5, :, :, 1:5], (5, 5, 4, 4))   # reversed, broadcast, transposed
+    want = src.copy() if kernel == "copy_strided_kernel" else (dst + src).astype(dtype)
+    isz = dbuf.itemsize
+    shape = (c_longlong * 4)(*dst.shape)
+    sa = (c_longlong * 4)(*[s // isz for s in dst.strides])
+    sb = (c_longlong * 4)(*[s // isz for s in src.strides])
+    d = _Dims()
+    k.lib.emu_collapse.restype = c_longlong
+    total = k.lib.emu_collapse(ctypes.byref(d), shape, sa, sb, 4)
+    assert total == dst.size and 1 <= d.ndim <= 4
+    before = dbuf.copy()
+    k.launch(3, 256, [c_void_p(dst.ctypes.data), c_void_p(src.ctypes.data), d, c_longlong(total)])
+    np.testing.assert_array_equal(dst, want)
+    mask = np.ones(dbuf.shape, dtype=bool)
+    mask[1:6, :, :, 2:9:2] = False
+    np.testing.assert_array_equal(dbuf[mask], before[mask])      # nothing outside the destination window is touched
+    # fully contiguous operands collapse to ONE dimension (the 128-bit streaming copy's precondition)
+    c_shape = (c_longlong * 3)(4, 1, 6)
+    c_st = (c_longlong * 3)(6, 6, 1)
+    assert k.lib.emu_collapse(ctypes.byref(d), c_shape, c_st, c_st, 3) == 24 and d.ndim == 1 and d.shape[0] == 24 and d.a[0] == 1
