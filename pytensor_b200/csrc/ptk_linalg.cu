@@ -9,6 +9,8 @@
 // All matrices are addressed through element strides (rs, cs): "upper" is the lower algorithm on the transposed view.
 #include <math_constants.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include "ptk_common.h"
 
 namespace {
@@ -310,10 +312,15 @@ ptk_status trsm_blocked(int dtype, const T* A, T* B, int64_t n, int64_t nrhs, in
   return PTK_OK;
 }
 
+// Status word of one blocked factorisation / solve.  Calls on different streams (parallel branches of a captured graph) must
+// not share a word, so every call takes the next one of a small ring; a captured node keeps the word it was captured with.
 int* scratch_flag() {
+  constexpr unsigned kWords = 1024;
   static int* p = nullptr;
-  if (!p) cudaMalloc(&p, 64);
-  return p;
+  static std::atomic<unsigned> next{0};
+  static std::once_flag once;
+  std::call_once(once, [] { if (cudaMalloc(&p, kWords * sizeof(int)) != cudaSuccess) p = nullptr; });
+  return p ? p + (next.fetch_add(1) % kWords) : nullptr;
 }
 
 }  // namespace

@@ -965,3 +965,136 @@ def test_strided_copy_and_increment_with_collapsed_dims(tmp_path, kernel, ctype,
     c_shape = (c_longlong * 3)(4, 1, 6)
     c_st = (c_longlong * 3)(6, 6, 1)
     assert k.lib.emu_collapse(ctypes.byref(d), c_shape, c_st, c_st, 3) == 24 and d.ndim == 1 and d.shape[0] == 24 and d.a[0] == 1
+
+
+# ---- Cholesky / triangular solve kernels (ptk_linalg.cu) -------------------------------------------------------------------
+LINALG_SHIM = r"""
+#define CUDART_NAN_F NAN
+#define CUDART_NAN ((double)NAN)
+using std::sqrt;
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, (int)((threadIdx.x & ~31u) + src)); }
+"""
+
+
+def _linalg_kernel(tmp_path, name, ctype, smem=None):
+    text = open(os.path.join(CSRC, "ptk_linalg.cu")).read()
+    head = text[text.index("constexpr int NB = 64;"):text.index("// ---- small path")]
+    src = LINALG_SHIM + head + extract_static_kernel(os.path.join(CSRC, "ptk_linalg.cu"), name)
+    return EmulatedKernel(src, name, tmp_path, threaded=True, template_args=ctype, type_subst={"T": ctype}, dynamic_smem=smem)
+
+
+def _spd(rng, n, dtype):
+    a = rng.standard_normal((n, n))
+    return (a @ a.T + n * np.eye(n)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype,ctype,n,lower,threads", [("float64", "double", 37, True, 64), ("float32", "float", 96, True, 256),
+                                                        ("float64", "double", 20, False, 64), ("float64", "double", 1, True, 64)])
+def test_small_cholesky_kernel(tmp_path, dtype, ctype, n, lower, threads):
+    """One CTA per matrix of a batch, left-looking, lanes along the dot-product index; upper = the lower algorithm on the
+    transposed view; the other triangle is zeroed; a matrix that is not positive definite comes back all-NaN while its batch
+    neighbours are factored (pytensor/tensor/linalg/decomposition/cholesky.py:52-83)."""
+    rng = np.random.default_rng(51)
+    k = _linalg_kernel(tmp_path, "potrf_small_kernel", ctype, smem="smem_raw")
+    batch = 3
+    A = np.stack([_spd(rng, n, dtype) for _ in range(batch)])
+    A0 = A.copy()
+    if n > 1:
+        A[1, n // 2, n // 2] = -1.0     # breaks positive definiteness of the middle matrix only
+    rs, cs = (n, 1) if lower else (1, n)
+    k.launch(batch, threads, [_ptr(A), c_longlong(n), c_longlong(rs), c_longlong(cs), c_longlong(n * n)])
+    tol = 2e-4 if dtype == "float32" else 1e-11
+    for b in range(batch):
+        if b == 1 and n > 1:
+            assert np.all(np.isnan(A[b]))
+            continue
+        L = np.linalg.cholesky(A0[b].astype(np.float64))
+        np.testing.assert_allclose(A[b], L if lower else L.T, rtol=tol, atol=tol * np.abs(L).max())
+
+
+@pytest.mark.parametrize("dtype,ctype,n", [("float64", "double", 150), ("float32", "float", 130)])
+def test_blocked_cholesky_kernels_compose(tmp_path, dtype, ctype, n):
+    """The right-looking blocked algorithm of ptk_potrf (n > 128) step by step: diagonal-block kernel, warp-per-row panel solve,
+    trailing update (NumPy stands in for ptk_gemm here), final clean-up; 64-wide panels with a short last one."""
+    rng = np.random.default_rng(52)
+    (tmp_path / "d").mkdir(), (tmp_path / "p").mkdir(), (tmp_path / "c").mkdir()
+    kd = _linalg_kernel(tmp_path / "d", "potrf_diag_kernel", ctype)
+    kp = _linalg_kernel(tmp_path / "p", "potrf_panel_kernel", ctype)
+    kc = _linalg_kernel(tmp_path / "c", "potrf_clean_kernel", ctype)
+    A = _spd(rng, n, dtype)
+    want = np.linalg.cholesky(A.astype(np.float64))
+    flag = np.zeros(1, dtype=np.int32)
+    isz = A.itemsize
+    at = lambda r, c: c_void_p(A.ctypes.data + (r * n + c) * isz)  # noqa: E731
+    for k0 in range(0, n, 64):
+        kb = min(64, n - k0)
+        kd.launch(1, 64, [at(k0, k0), c_longlong(n), c_longlong(1), c_int(kb), _ptr(flag)])
+        m = n - k0 - kb
+        if m > 0:
+            kp.launch(2, 256, [at(k0, k0), at(k0 + kb, k0), c_longlong(n), c_longlong(1), c_int(kb), c_longlong(m)])
+            A21 = A[k0 + kb:, k0:k0 + kb]
+            A[k0 + kb:, k0 + kb:] -= A21 @ A21.T
+    kc.launch(3, 256, [_ptr(A), c_longlong(n), c_longlong(n), c_longlong(1), _ptr(flag)])
+    assert flag[0] == 0
+    tol = 3e-4 if dtype == "float32" else 1e-10
+    np.testing.assert_allclose(A, want, rtol=tol, atol=tol * np.abs(want).max())
+    # a non-positive pivot inside a diagonal block raises the flag; the clean-up kernel then NaN-fills the whole matrix
+    B = _spd(rng, 40, dtype)
+    B[17, 17] = -5.0
+    kd.launch(1, 64, [_ptr(B), c_longlong(40), c_longlong(1), c_int(40), _ptr(flag)])
+    assert flag[0] == 1
+    kc.launch(1, 256, [_ptr(B), c_longlong(40), c_longlong(40), c_longlong(1), _ptr(flag)])
+    assert np.all(np.isnan(B))
+
+
+@pytest.mark.parametrize("dtype,ctype,n,nrhs,lower,trans,unit", [("float64", "double", 45, 70, 1, 0, 0), ("float32", "float", 33, 5, 0, 0, 0),
+                                                                 ("float64", "double", 20, 33, 1, 1, 0), ("float64", "double", 16, 8, 0, 1, 1)])
+def test_small_triangular_solve_kernel(tmp_path, dtype, ctype, n, nrhs, lower, trans, unit):
+    """op(A) X = B by substitution, one CTA per 32 right-hand sides, `trans` folded into the strides; unit_diag never reads the
+    diagonal; an exactly-zero diagonal element NaN-fills the solution (pytensor/tensor/linalg/solvers/triangular.py:41-71)."""
+    import scipy.linalg as sl
+
+    rng = np.random.default_rng(53)
+    k = _linalg_kernel(tmp_path, "trsm_small_kernel", ctype)
+    batch = 2
+    tri = np.tril if lower else np.triu
+    A = np.stack([tri(rng.standard_normal((n, n))) + 4 * np.eye(n) for _ in range(batch)]).astype(dtype)
+    if unit:
+        for b in range(batch):
+            A[b][np.diag_indices(n)] = np.nan    # must not be read
+    B = rng.standard_normal((batch, n, nrhs)).astype(dtype)
+    B0 = B.copy()
+    ars, acs = (1, n) if trans else (n, 1)
+    fwd = 1 if (bool(lower) != bool(trans)) else 0
+    args = [_ptr(A), _ptr(B), c_longlong(n), c_longlong(nrhs), c_longlong(ars), c_longlong(acs), c_int(fwd), c_int(unit)]
+    k.launch(((nrhs + 31) // 32, batch), 256, args)
+    tol = 2e-4 if dtype == "float32" else 1e-10
+    for b in range(batch):
+        Ab = A[b].astype(np.float64)
+        if unit:
+            Ab[np.diag_indices(n)] = 1.0
+        want = sl.solve_triangular(Ab, B0[b].astype(np.float64), lower=bool(lower), trans=trans, unit_diagonal=bool(unit))
+        np.testing.assert_allclose(B[b], want, rtol=tol, atol=tol * np.abs(want).max())
+    if not unit:
+        A[0, n // 3, n // 3] = 0.0
+        B[:] = B0
+        k.launch(((nrhs + 31) // 32, batch), 256, args)
+        assert np.all(np.isnan(B[0])) and np.all(np.isfinite(B[1]))
+
+
+@pytest.mark.parametrize("fwd,unit", [(1, 0), (0, 0), (1, 1)])
+def test_blocked_triangular_solve_diagonal_block_kernel(tmp_path, fwd, unit):
+    rng = np.random.default_rng(54)
+    import scipy.linalg as sl
+
+    k = _linalg_kernel(tmp_path, "trsm_diag_kernel", "double")
+    kb, nrhs, n = 50, 200, 70      # a kb x kb diagonal block inside an n x n matrix (row stride n)
+    A = (np.tril(rng.standard_normal((n, n))) if fwd else np.triu(rng.standard_normal((n, n)))) + 5 * np.eye(n)
+    B = rng.standard_normal((kb, nrhs))
+    B0 = B.copy()
+    off = 10
+    A11 = A[off:off + kb, off:off + kb]
+    k.launch((nrhs + 127) // 128, 128, [c_void_p(A.ctypes.data + (off * n + off) * 8), c_longlong(n), c_longlong(1), _ptr(B),
+                                         c_longlong(nrhs), c_int(kb), c_int(fwd), c_int(unit)])
+    want = sl.solve_triangular(A11, B0, lower=bool(fwd), unit_diagonal=bool(unit))
+    np.testing.assert_allclose(B, want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
