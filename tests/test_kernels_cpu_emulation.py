@@ -1098,3 +1098,127 @@ def test_blocked_triangular_solve_diagonal_block_kernel(tmp_path, fwd, unit):
                                          c_longlong(nrhs), c_int(kb), c_int(fwd), c_int(unit)])
     want = sl.solve_triangular(A11, B0, lower=bool(fwd), unit_diagonal=bool(unit))
     np.testing.assert_allclose(B, want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
+
+
+# ---- ARange / Argmax / CumOp / index linearisation (ptk_misc.cu) --------------------------------------------------------------
+MISC_SHIM = r"""
+#include <type_traits>
+static inline float __fmul_rn(float a, float b) { volatile float p = a * b; return p; }     // volatile: no FMA contraction
+static inline float __fadd_rn(float a, float b) { volatile float s = a + b; return s; }
+static inline double __dmul_rn(double a, double b) { volatile double p = a * b; return p; }
+static inline double __dadd_rn(double a, double b) { volatile double s = a + b; return s; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, (int)((threadIdx.x & ~31u) + src)); }
+"""
+
+
+def _misc_kernel(tmp_path, name, targs, subst, head=""):
+    src = MISC_SHIM + head + extract_static_kernel(os.path.join(CSRC, "ptk_misc.cu"), name)
+    return EmulatedKernel(src, name, tmp_path, threaded=True, template_args=targs, type_subst=subst)
+
+
+def test_arange_kernels_round_like_numpy(tmp_path):
+    """out[i] = first + i*delta in the OUTPUT type with two roundings (no FMA), like NumPy's <type>_fill; integers wrap."""
+    (tmp_path / "f").mkdir(), (tmp_path / "d").mkdir(), (tmp_path / "i").mkdir()
+    n = 3000
+    kf = _misc_kernel(tmp_path / "f", "arange_float_kernel", "float", {"T": "float"})
+    out = np.zeros(n, dtype=np.float32)
+    kf.launch(3, 256, [_ptr(out), c_longlong(n), c_float(0.1), c_float(0.3)])
+    i = np.arange(n, dtype=np.float32)
+    np.testing.assert_array_equal(out, np.float32(0.1) + i * np.float32(0.3))
+    kd = _misc_kernel(tmp_path / "d", "arange_float_kernel", "double", {"T": "double"})
+    outd = np.zeros(n, dtype=np.float64)
+    kd.launch(3, 256, [_ptr(outd), c_longlong(n), c_double(-7.7), c_double(1e-3)])
+    np.testing.assert_array_equal(outd, -7.7 + np.arange(n, dtype=np.float64) * 1e-3)
+    ki = _misc_kernel(tmp_path / "i", "arange_int_kernel", "int8_t", {"T": "int8_t"})
+    outi = np.zeros(n, dtype=np.int8)
+    ki.launch(2, 256, [_ptr(outi), c_longlong(n), c_longlong(-5), c_longlong(3)])
+    np.testing.assert_array_equal(outi, (-5 + 3 * np.arange(n, dtype=np.int64)).astype(np.int8))
+
+
+def _argmax_head():
+    text = open(os.path.join(CSRC, "ptk_misc.cu")).read()
+    return text[text.index("template <typename T>\n__device__ __forceinline__ bool is_nan_v"):text.index("// inner == 1: one warp (small rows)")]
+
+
+@pytest.mark.parametrize("threads,rows,n", [(32, 70, 100), (256, 5, 3000), (256, 3, 7), (32, 4, 1)])
+def test_argmax_rows_kernel_first_maximum_and_nan(tmp_path, threads, rows, n):
+    """np.argmax along the last axis: the FIRST maximal element wins across lanes, warps and strides; the first NaN wins
+    over everything (pytensor/tensor/math.py Argmax.perform = np.argmax)."""
+    rng = np.random.default_rng(61)
+    k = _misc_kernel(tmp_path, "argmax_rows_kernel", f"float, {threads}", {"T": "float"}, head=_argmax_head())
+    x = rng.integers(0, 6, size=(rows, n)).astype(np.float32)     # few distinct values: many ties
+    if n > 5:
+        x[1, n // 2] = np.nan
+        x[1, n - 1] = np.nan
+        x[2, :] = 3.0
+    out = np.full(rows, -1, dtype=np.int64)
+    k.launch(2, threads, [_ptr(x), _ptr(out), c_longlong(rows), c_longlong(n)])
+    np.testing.assert_array_equal(out, np.argmax(x, axis=1))
+
+
+def test_argmax_cols_kernel(tmp_path):
+    rng = np.random.default_rng(62)
+    k = _misc_kernel(tmp_path, "argmax_cols_kernel", "int32_t", {"T": "int32_t"}, head=_argmax_head())
+    x = rng.integers(-4, 4, size=(3, 17, 40)).astype(np.int32)
+    out = np.full((3, 40), -1, dtype=np.int64)
+    k.launch(2, 256, [_ptr(x), _ptr(out), c_longlong(3), c_longlong(17), c_longlong(40)])
+    np.testing.assert_array_equal(out, np.argmax(x, axis=1))
+
+
+@pytest.mark.parametrize("ctype,dtype,op", [("int64_t", np.int64, 0), ("double", np.float64, 0), ("int32_t", np.int32, 1), ("float", np.float32, 1)])
+def test_cumulative_kernels(tmp_path, ctype, dtype, op):
+    """CumOp (pytensor/tensor/extra_ops.py: np.cumsum / np.cumprod): warp scan with a carried total along the last axis,
+    one sequential thread per line otherwise — integers bit-exact (wrapping products included), floats within rounding
+    (rows kernel) or bit-exact (columns kernel, same order as NumPy)."""
+    rng = np.random.default_rng(63)
+    (tmp_path / "r").mkdir(), (tmp_path / "c").mkdir()
+    head = ("template <typename T, int OP>\n__device__ __forceinline__ T cum_combine(T a, T b) {\n"
+            "  return OP == 0 ? (T)(a + b) : (T)(a * b);\n}\n")
+    assert head in open(os.path.join(CSRC, "ptk_misc.cu")).read()
+    kr = _misc_kernel(tmp_path / "r", "cum_rows_kernel", f"{ctype}, {op}", {"T": ctype}, head=head)
+    kc = _misc_kernel(tmp_path / "c", "cum_cols_kernel", f"{ctype}, {op}", {"T": ctype}, head=head)
+    f = np.cumsum if op == 0 else np.cumprod
+    if np.issubdtype(dtype, np.integer):
+        x = rng.integers(-3, 4, size=(9, 77)).astype(dtype)
+    else:
+        x = (1.0 + 0.1 * rng.standard_normal((9, 77))).astype(dtype)
+    out = np.zeros_like(x)
+    kr.launch(1, 256, [_ptr(x), _ptr(out), c_longlong(9), c_longlong(77)])
+    want = f(x, axis=1, dtype=dtype)
+    if np.issubdtype(dtype, np.integer):
+        np.testing.assert_array_equal(out, want)
+    else:
+        np.testing.assert_allclose(out, want, rtol=2e-5 if dtype == np.float32 else 1e-13)
+    x3 = x.reshape(3, 3, 77).transpose(0, 2, 1).copy()       # (outer 3, n 77, inner 3)
+    out3 = np.zeros_like(x3)
+    kc.launch(1, 256, [_ptr(x3), _ptr(out3), c_longlong(3), c_longlong(77), c_longlong(3)])
+    np.testing.assert_array_equal(out3, f(x3, axis=1, dtype=dtype))
+
+
+class _LinIdxArgs(ctypes.Structure):
+    _fields_ = [("idx", c_void_p * 8), ("dim", c_longlong * 8), ("stride", c_longlong * 8), ("k", c_int)]
+
+
+def test_linearize_index_kernel(tmp_path):
+    """Several integer index arrays on consecutive axes -> one linear index (np.ravel_multi_index with NumPy's per-axis
+    negative wrap); any out-of-range component raises the error word."""
+    rng = np.random.default_rng(64)
+    text = open(os.path.join(CSRC, "ptk_misc.cu")).read()
+    head = text[text.index("struct LinIdxArgs {"):text.index("__global__ void linearize_index_kernel")]
+    k = _misc_kernel(tmp_path, "linearize_index_kernel", "", None, head=head)
+    dims, n = (5, 7, 3), 500
+    idx = [rng.integers(-d, d, size=n).astype(np.int64) for d in dims]
+    a = _LinIdxArgs()
+    a.k = 3
+    for j, d in enumerate(dims):
+        a.idx[j] = idx[j].ctypes.data
+        a.dim[j] = d
+        a.stride[j] = int(np.prod(dims[j + 1:]))
+    out = np.zeros(n, dtype=np.int64)
+    err = np.zeros(1, dtype=np.int32)
+    k.launch(2, 256, [a, c_longlong(n), _ptr(out), _ptr(err)])
+    np.testing.assert_array_equal(out, np.ravel_multi_index([np.where(i < 0, i + d, i) for i, d in zip(idx, dims)], dims))
+    assert err[0] == 0
+    idx[1][123] = 7
+    k.launch(2, 256, [a, c_longlong(n), _ptr(out), _ptr(err)])
+    assert err[0] == 1
