@@ -1222,3 +1222,49 @@ def test_linearize_index_kernel(tmp_path):
     idx[1][123] = 7
     k.launch(2, 256, [a, c_longlong(n), _ptr(out), _ptr(err)])
     assert err[0] == 1
+
+
+BF16_PAIR_SHIM = r"""
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { __nv_bfloat162 r; r.x = __float2bfloat16_rn(a); r.y = __float2bfloat16_rn(b); return r; }
+"""
+
+
+def _bf16_round(x):
+    """float32 -> bf16 (round to nearest even) -> float64, NumPy restatement."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x7FFF + ((b >> 16) & 1)) >> 16
+    return (b.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("R,Cc,row_major", [(70, 130, True), (130, 70, False), (64, 63, True), (3, 9, False)])
+def test_plain_bf16_staging_kernels(tmp_path, R, Cc, row_major):
+    """ptk_stage_operand's plain variants: one bf16 matrix (bf16 mode), or the three-piece split x1 = bf16(x), x2 = bf16(x - x1),
+    x3 = bf16(x - x1 - x2) stacked with a pitch of piece_rows rows; either source stride may be the unit one (the B operand
+    is staged transposed); odd column counts end in a zero / untouched pad inside the 8-element row pitch."""
+    rng = np.random.default_rng(R + 7 * Cc)
+    x = (rng.standard_normal((R, Cc)) * np.exp(rng.uniform(-8, 8, (R, Cc)))).astype(np.float32)
+    src = np.ascontiguousarray(x if row_major else x.T)
+    sr, sc = (Cc, 1) if row_major else (1, R)
+    ld, pr = (Cc + 7) // 8 * 8, (R + 255) // 256 * 256
+    grid = ((Cc + 63) // 64, (R + 63) // 64)
+    (tmp_path / "c").mkdir(), (tmp_path / "s").mkdir()
+    shim = BF16_SHIM + BF16_PAIR_SHIM
+    kc = EmulatedKernel(shim + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "convert_bf16_kernel"),
+                        "convert_bf16_kernel", tmp_path / "c", threaded=True)
+    one = np.full((R, ld), 0xABCD, dtype=np.uint16)
+    kc.launch(grid, 256, [_ptr(src), c_longlong(sr), c_longlong(sc), _ptr(one), c_longlong(ld), c_longlong(R), c_longlong(Cc)])
+    got = (one[:, :Cc].astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    np.testing.assert_array_equal(got, _bf16_round(x))
+    ks = EmulatedKernel(shim + extract_static_kernel(os.path.join(CSRC, "ptk_gemm_tc.cu"), "split_bf16x3_kernel"),
+                        "split_bf16x3_kernel", tmp_path / "s", threaded=True)
+    dst = np.zeros((3 * pr, ld), dtype=np.uint16)
+    ks.launch(grid, 256, [_ptr(src), c_longlong(sr), c_longlong(sc), _ptr(dst), c_longlong(ld), c_longlong(R), c_longlong(Cc),
+                          c_longlong(pr)])
+    p = [(dst[k * pr:k * pr + R, :Cc].astype(np.uint32) << 16).view(np.float32).astype(np.float64) for k in range(3)]
+    x64 = x.astype(np.float64)
+    np.testing.assert_array_equal(p[0], _bf16_round(x))
+    r1 = (x64 - p[0]).astype(np.float32)          # exact in fp32
+    np.testing.assert_array_equal(p[1], _bf16_round(r1))
+    np.testing.assert_array_equal(p[2], _bf16_round((r1.astype(np.float64) - p[1]).astype(np.float32)))
+    assert np.all(np.abs(p[0] + p[1] + p[2] - x64) <= np.abs(x64) * 2.0 ** -22)
+    assert not dst[R:pr].any() and not dst[pr + R:2 * pr].any()     # rows between the pieces stay untouched
