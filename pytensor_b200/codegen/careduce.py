@@ -78,6 +78,16 @@ def _k3_pipeline() -> str:
     return os.environ.get("PTK_K3_PIPE", "none")   # also: "tma" = gen_row_kernel_tma (bulk-copy staging through shared memory)
 
 
+def _k3_running_pointers() -> bool:
+    """Column walk of the default row kernel: running pointers (one 64-bit add per operand and trip; a trip's second vector
+    is addressed at a compile-time distance from the first) instead of re-deriving every address from the 32-bit column
+    index — 425 -> 408 SASS instructions per 8-element trip of the cfg2 kernel at the same 40 registers.  PTK_K3_ADDR=idx
+    restores the index form."""
+    import os
+
+    return os.environ.get("PTK_K3_ADDR", "ptr") != "idx"
+
+
 def _k3_min_blocks() -> int:
     """CTAs per SM the row kernel is compiled for (register cap 65536 / (256 * n)): 4 leaves 64 registers — enough for
     the two-trip software pipeline of a 2-input Composite with a couple of spilled words; PTK_K3_MINB overrides (A/B)."""
@@ -209,6 +219,55 @@ def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: 
             pf_note = "; the NEXT trip's lines are requested from L2 first (prefetch.global.L2)"
         else:
             prefetch, pf_note = "", ""
+    use_ptr = pipe not in ("regs", "l2") and _k3_running_pointers()
+    if use_ptr:
+        def loads_p(tag, off):
+            return "\n".join(f"          const PVec<{CTYPE[prog.in_dtypes[k]]}, VW> v{tag}{k} = ptk_ldv<{CTYPE[prog.in_dtypes[k]]}, VW>(a{k}{off});"
+                             for k in vec_in)
+
+        def compute_p(tag, off):
+            return "\n".join(_compute_ptr(tag, off))
+
+        def _compute_ptr(tag, off):
+            call_in = [f"v{tag}{k}.v[e]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
+            call_out = [f"o{tag}{k}.v[e]" for k in range(n_map)]
+            for k, d in enumerate(prog.out_dtypes):
+                yield f"          PVec<{CTYPE[d]}, VW> o{tag}{k};"
+            yield "          #pragma unroll"
+            yield "          for (int e = 0; e < VW; ++e) {"
+            yield f"            ptk_body({', '.join(call_in + call_out)});"
+            yield f"            acc = ptk_red(acc, (ACC)o{tag}0.v[e]);"
+            yield "          }"
+            for k in stored:
+                yield f"          ptk_stv<{CTYPE[prog.out_dtypes[k]]}, VW>(u{k}{off}, o{tag}{k});"
+
+        ptr_decl = "\n".join([f"      const {CTYPE[prog.in_dtypes[k]]}* a{k} = q{k} + cv * VW;" for k in vec_in]
+                             + [f"      {CTYPE[prog.out_dtypes[k]]}* u{k} = w{k} + cv * VW;" for k in stored])
+
+        def advance_p(n):
+            return " ".join([f"a{k} += {n} * TPR * VW;" for k in vec_in] + [f"u{k} += {n} * TPR * VW;" for k in stored])
+
+        main_loop = f"""      int cv = cv_lo + lane_in_row;
+{ptr_decl}
+      // two vectors per trip, running pointers: the second vector sits at a compile-time distance from the first
+      for (; cv + TPR < cv_hi; cv += 2 * TPR) {{
+        {{
+{loads_p('a', '')}
+{loads_p('b', ' + TPR * VW')}
+{compute_p('a', '')}
+{compute_p('b', ' + TPR * VW')}
+        }}
+        {advance_p(2)}
+      }}
+      for (; cv < cv_hi; cv += TPR) {{
+        {{
+{loads_p('a', '')}
+{compute_p('a', '')}
+        }}
+        {advance_p(1)}
+      }}
+"""
+    elif pipe != "regs":
         main_loop = f"""      int cv = cv_lo + lane_in_row;
       // two vectors per trip{pf_note}
       for (; cv + TPR < cv_hi; cv += 2 * TPR) {{
@@ -226,6 +285,14 @@ def gen_row_kernel(prog: ScalarProgram, name: str, col_modes: tuple, store_map: 
     tail_in = [f"q{k}[c]" if col_modes[k] == 1 else f"s{k}" for k in range(n_in)]
     tail_tmp = "\n".join(f"          {CTYPE[d]} to{k};" for k, d in enumerate(prog.out_dtypes))
     tail_st = "\n".join(f"          w{k}[c] = to{k};" for k in stored)
+    single_loop = "" if use_ptr else f"""
+      for (; cv < cv_hi; cv += TPR) {{
+        const int ca = cv * VW;
+        {{
+{loads('a', 'ca')}
+{compute('a', 'ca')}
+        }}
+      }}"""
 
     return f"""{PRELUDE}
 {_VEC_HELPERS}
@@ -257,14 +324,7 @@ extern "C" __global__ void __launch_bounds__(256, {_k3_min_blocks()}) {name}({',
 {base_in}
 {base_out}
 {row_scalars}
-{main_loop}
-      for (; cv < cv_hi; cv += TPR) {{
-        const int ca = cv * VW;
-        {{
-{loads('a', 'ca')}
-{compute('a', 'ca')}
-        }}
-      }}
+{main_loop}{single_loop}
       if (last_split) {{
         for (int c = ncv * VW + lane_in_row; c < (int)cols; c += TPR) {{
 {tail_tmp}

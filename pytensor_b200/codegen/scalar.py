@@ -551,6 +551,67 @@ def emit_body(prog: ScalarProgram, fn_name: str = "ptk_body") -> str:
     return "\n".join(lines)
 
 
+def simplify(prog: ScalarProgram) -> ScalarProgram:
+    """Exact algebraic peepholes over a ScalarProgram (every IEEE operation of the simplified program returns what the
+    unsimplified one returns, for EVERY input: NaNs, infinities, denormals), applied once at lowering time:
+
+      Maximum(u, -u) -> Abs(u)     where -u is `Neg(u)`, or u = c * x and -u = (-c) * x with literal constants of the
+                                   operands' own floating-point type.  IEEE multiplication is sign-symmetric, so (-c) * x is
+                                   exactly -(c * x); max(y, -y) is |y|: NaN for a NaN (the reference's Maximum propagates
+                                   NaNs, scalar/basic.py ScalarMaximum.c_code) and +0 for y = +-0, which is also what
+                                   the device's max.NaN instruction returns for (-0, +0) in either order.
+
+    The instruction that computed -u stays in the program (its result may have other readers); the device compiler drops
+    it when it has none.  PTK_SCALAR_SIMPLIFY=0 disables."""
+    import os
+
+    if os.environ.get("PTK_SCALAR_SIMPLIFY", "1") == "0":
+        return prog
+    insts = prog.insts
+
+    def const_value(ref, dtype):
+        if ref[0] != "c":
+            return None
+        d, v = prog.consts[ref[1]]
+        return v if d == dtype and isinstance(v, float) else None
+
+    def mul_parts(ref, dtype):
+        """(constant value, other operand ref) of `c * x` / `x * c` computed in `dtype`, else None."""
+        if ref[0] != "t":
+            return None
+        i = insts[ref[1]]
+        if i.op != "Mul" or len(i.args) != 2 or i.out_dtype != dtype or list(i.in_dtypes) != [dtype, dtype]:
+            return None
+        for a, b in ((0, 1), (1, 0)):
+            c = const_value(i.args[a], dtype)
+            if c is not None and i.args[b][0] != "c":
+                return c, tuple(i.args[b])
+        return None
+
+    def is_neg_of(a, b, dtype):
+        """Is the value of ref a exactly -(value of ref b)?"""
+        if a[0] == "t":
+            i = insts[a[1]]
+            if i.op == "Neg" and i.out_dtype == dtype and list(i.in_dtypes) == [dtype] and tuple(i.args[0]) == tuple(b):
+                return True
+        pa, pb = mul_parts(a, dtype), mul_parts(b, dtype)
+        return pa is not None and pb is not None and pa[1] == pb[1] and pa[0] == -pb[0] and pa[0] == pa[0]
+
+    out = None
+    for k, i in enumerate(insts):
+        if i.op == "Maximum" and len(i.args) == 2 and i.out_dtype in ("float32", "float64") \
+                and list(i.in_dtypes) == [i.out_dtype, i.out_dtype]:
+            a, b = tuple(i.args[0]), tuple(i.args[1])
+            if is_neg_of(b, a, i.out_dtype) or is_neg_of(a, b, i.out_dtype):
+                if out is None:
+                    out = list(insts)
+                keep = a if a[0] == "t" or b[0] != "t" else b
+                out[k] = ScalarInst("Abs", [keep], [i.out_dtype], i.out_dtype)
+    if out is None:
+        return prog
+    return ScalarProgram(list(prog.in_dtypes), list(prog.out_dtypes), list(prog.consts), out, list(prog.outputs))
+
+
 def single_op_program(op: str, in_dtypes, out_dtype) -> ScalarProgram:
     return ScalarProgram(
         in_dtypes=list(in_dtypes), out_dtypes=[out_dtype],

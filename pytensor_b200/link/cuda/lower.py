@@ -33,7 +33,7 @@ from pytensor.tensor.subtensor import (
     Subtensor,
 )
 
-from pytensor_b200.codegen.scalar import ScalarInst, ScalarProgram, UnsupportedScalarOp, OPS
+from pytensor_b200.codegen.scalar import ScalarInst, ScalarProgram, UnsupportedScalarOp, OPS, simplify
 from pytensor_b200.vm import nodes_basic as nb
 from pytensor_b200.vm import nodes_blas as nblas
 from pytensor_b200.vm import nodes_linalg as nlin
@@ -88,7 +88,7 @@ def scalar_program(scalar_op, in_dtypes, out_dtypes) -> ScalarProgram:
 
     outs = emit(scalar_op, [("i", k) for k in range(len(in_dtypes))], list(in_dtypes), list(out_dtypes))
     prog.outputs = list(outs)
-    return prog
+    return simplify(prog)
 
 
 _RED_NAMES = {"Add": "add", "Mul": "mul", "Maximum": "maximum", "Minimum": "minimum", "AND": "and", "OR": "or",

@@ -36,7 +36,7 @@ template <typename T> static inline T ptk_fmod_py(T x, T y) { T r = std::fmod(x,
 """
 
 
-def _compile_body(prog, tmp_path, tag):
+def _compile_body(prog, tmp_path, tag, extra_flags=()):
     ins_decl = ", ".join(f"const {CTYPE[d]}* i{k}" for k, d in enumerate(prog.in_dtypes))
     outs_decl = ", ".join(f"{CTYPE[d]}* o{k}" for k, d in enumerate(prog.out_dtypes))
     call = ", ".join([f"i{k}[n]" for k in range(len(prog.in_dtypes))] + [f"o{k}[n]" for k in range(len(prog.out_dtypes))])
@@ -47,12 +47,12 @@ def _compile_body(prog, tmp_path, tag):
     # same floating-point environment as the reference's generated C (`-march=native`, GNU default FMA contraction,
     # pytensor/link/c/cmodule.py) — nvcc contracts mul+add into FMA as well; which pairs get fused may still differ,
     # hence the small absolute tolerance on cancelling expressions below
-    subprocess.run(["g++", "-O2", "-march=native", "-fno-math-errno", "-shared", "-fPIC", "-std=c++17", str(cpp), "-o", str(so)],
-                   check=True)
+    subprocess.run(["g++", "-O2", "-march=native", "-fno-math-errno", *extra_flags, "-shared", "-fPIC", "-std=c++17", str(cpp),
+                    "-o", str(so)], check=True)
     return ctypes.CDLL(str(so))
 
 
-def _emulate(inputs, outputs, values, tmp_path):
+def _emulate(inputs, outputs, values, tmp_path, extra_flags=()):
     """Run the lowered program on the host: every step must be a plain ElemwiseNode over same-shaped vectors."""
     f = pytensor.function(inputs, outputs, mode="CUDA")
     prog = f.vm.executor.program
@@ -63,7 +63,7 @@ def _emulate(inputs, outputs, values, tmp_path):
     for k, st in enumerate(prog.steps):
         assert type(st.impl).__name__ == "ElemwiseNode", f"step {k} is {type(st.impl).__name__}: keep the test graph elementwise"
         p = st.impl.prog
-        lib = _compile_body(p, tmp_path, k)
+        lib = _compile_body(p, tmp_path, k, extra_flags)
         ins = []
         for j, d in zip(st.ins, p.in_dtypes):
             a = np.ascontiguousarray(np.broadcast_to(slots[j], (N,)).astype(d, copy=False))
@@ -221,3 +221,49 @@ def test_host_evaluator_for_shape_arithmetic_matches_reference(dtype):
     got = [np.asarray(slots[s]) for s in prog.outputs]
     ref = pytensor.function([i, j], outs, mode="CVM")(iv, jv)
     _check(got, ref, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_max_of_a_value_and_its_negation_becomes_abs_bit_exactly(tmp_path, dtype, monkeypatch):
+    """The lowering-time peephole Maximum(u, -u) -> Abs(u) (codegen/scalar.py::simplify): same BITS as the unsimplified
+    program and as the reference C linker for NaNs, signed zeros, infinities, denormals and ordinary values, in both forms
+    the host's canonicaliser produces (`Neg(u)`, and c*x next to (-c)*x); maxima that only LOOK similar are left alone."""
+    from pytensor_b200.codegen import scalar as cs
+
+    pytensor.config.floatX = dtype
+    x, y = pt.vector("x", dtype=dtype), pt.vector("y", dtype=dtype)
+    c = np.asarray(0.9, dtype=dtype)
+    u = (x * y + np.asarray(0.5, dtype=dtype)) * c
+    w = pt.exp(x)
+    outs = [pt.maximum(u, -u) + pt.sqr(x) * np.asarray(0.1, dtype=dtype),     # c*t next to (-c)*t after canonicalisation
+            pt.maximum(-w, w),                                                  # Neg form, operands swapped
+            pt.maximum(x * c, y * (-c)),                                        # different operands: NOT an abs
+            pt.maximum(x * c, x * np.asarray(-0.8, dtype=dtype))]               # different magnitudes: NOT an abs
+    v = _floats(dtype, n=4000)
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, np.finfo(dtype).tiny / 4, -np.finfo(dtype).tiny / 4,
+                        np.finfo(dtype).max, -np.finfo(dtype).max], dtype=dtype)
+    xs = np.concatenate([np.repeat(special, len(special)), v])
+    ys = np.concatenate([np.tile(special, len(special)), v[::-1]])
+    got, ref = _emulate([x, y], outs, [xs, ys], tmp_path)
+    _check(got, ref, rtol=2e-6 if dtype == "float32" else 1e-13, atol=1e-30)
+    f = pytensor.function([x, y], outs, mode="CUDA")
+    ops = [i.op for st in f.vm.executor.program.steps for i in st.impl.prog.insts]
+    assert ops.count("Abs") == 2 and ops.count("Maximum") == 2, ops
+    # Against the unsimplified programs with FMA contraction off (contraction picks its pairs per expression tree and may
+    # move a last bit in EITHER program, like in any other expression): identical bits.
+    (tmp_path / "s").mkdir(), (tmp_path / "raw").mkdir()
+    got_s, _ = _emulate([x, y], outs, [xs, ys], tmp_path / "s", extra_flags=("-ffp-contract=off",))
+    monkeypatch.setenv("PTK_SCALAR_SIMPLIFY", "0")
+    got_raw, _ = _emulate([x, y], outs, [xs, ys], tmp_path / "raw", extra_flags=("-ffp-contract=off",))
+    f_raw = pytensor.function([x, y], outs, mode="CUDA")
+    assert [i.op for st in f_raw.vm.executor.program.steps for i in st.impl.prog.insts].count("Abs") == 0
+    uint = np.uint32 if dtype == "float32" else np.uint64
+    for g, g0, r in zip(got_s, got_raw, ref):
+        nan = np.isnan(g0)
+        np.testing.assert_array_equal(np.isnan(g), nan)
+        # (max(-0, +0): the reference's C expression — and this file's host stand-in — keeps its FIRST operand's zero, the
+        # device's max.NaN.f32 returns +0 like |y| does; zeros therefore compare by value, everything else by bits)
+        nz = ~nan & (g0 != 0)
+        np.testing.assert_array_equal(g[nz].view(uint), g0[nz].view(uint))
+        np.testing.assert_array_equal(g[~nan & ~nz], g0[~nan & ~nz])
+        np.testing.assert_array_equal(np.isnan(np.asarray(r)), nan)                      # the C linker agrees on the NaNs
