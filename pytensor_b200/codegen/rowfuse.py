@@ -37,6 +37,13 @@ MAX_SMEM = 160 * 1024
 GEMM_R_MAX_Q = 16    # "reduce" form: q accumulators in registers
 GEMM_P_MAX_P = 32    # "pointwise" form: p operand values in registers
 STAGE_MAX_BYTES = 4096
+CTA_INDEX_MAX_BYTES = 32 * 1024   # shared index vectors up to 8192 entries get a per-CTA int32 table
+
+
+def _cta_index_enabled() -> bool:
+    import os
+
+    return os.environ.get("PTK_ROWFUSE_CTA_INDEX", "1") != "0"
 
 
 class NotFusable(Exception):
@@ -372,8 +379,39 @@ def gen_region_kernel(plan: RegionPlan, dims: dict, ext: list, name: str, idx_ch
             if v.out >= 0:
                 self.body.append(f"q{v.out}[b * {dims[v.dom]}LL + j] = v{i};")
 
+    cta_idx = {}        # (index value, axis length) -> (name, byte offset inside the CTA index region, entries)
+    cta_idx_bytes = 0
+    cta_idx_code = []
+
     def index_expr(L, idx, n_src):
-        """Bounds-checked (negative wrap like NumPy) index expression; flags `err` and clamps on out-of-bounds."""
+        """Bounds-checked (negative wrap like NumPy) index expression; flags `err` and clamps on out-of-bounds.
+
+        An index vector SHARED by all batch rows (the group index of a hierarchical model) is wrapped and checked ONCE per
+        CTA into an int32 table in shared memory; the per-row loops then read one LDS instead of re-validating a 64-bit
+        global load for every (row, element) — in the cfg5 kernel that check was ~20 of 70 instructions per element, twice
+        (gather and scatter) inside divergence-guarded regions.  PTK_ROWFUSE_CTA_INDEX=0 keeps the per-use form."""
+        nonlocal cta_idx_bytes
+        v = vals[idx]
+        n_ent = dims[v.dom]
+        if (v.kind == "S1" and is_ext(idx) and v.const is None and L.dom == v.dom and _cta_index_enabled()
+                and n_src < 2 ** 31 and n_ent * 4 <= CTA_INDEX_MAX_BYTES):
+            key = (idx, n_src)
+            if key not in cta_idx and smem_bytes + cta_idx_bytes + n_ent * 4 + 16 <= MAX_SMEM:
+                nm = f"cix{len(cta_idx)}"
+                e = ext[v.ext]
+                cta_idx[key] = (nm, cta_idx_bytes, n_ent)
+                chk = f" if ((unsigned long long)t >= {n_src}ULL) {{ atomicExch(err, 1); t = 0; }}" if idx_check else ""
+                cta_idx_code.append(
+                    f"int* const {nm} = reinterpret_cast<int*>(ptk_smem + {smem_bytes + cta_idx_bytes});\n"
+                    f"  for (int jj = threadIdx.x; jj < {n_ent}; jj += {WARPS * 32}) {{\n"
+                    f"    long long t = (long long)__ldg({gptr(idx)} + (long long)jj * {e.strides[-1]}LL);\n"
+                    f"    if (t < 0) t += {n_src};{chk}\n"
+                    f"    {nm}[jj] = (int)t;\n  }}")
+                cta_idx_bytes += (n_ent * 4 + 15) // 16 * 16
+            if key in cta_idx:
+                nm = f"ix{len(L.body)}"
+                L.body.append(f"const int {nm} = {cta_idx[key][0]}[j];")
+                return nm
         raw = L.pt(idx)
         nm = f"ix{len(L.body)}"
         L.body.append(f"long long {nm} = (long long)({raw});")
@@ -565,6 +603,7 @@ extern "C" __global__ void __launch_bounds__({WARPS * 32}) {name}({', '.join(par
   unsigned char* const wsm = ptk_smem + {acc_bytes} + warp * {warp_bytes};
   {(nl + '  ').join(sm_decl)}
   for (int i = threadIdx.x; i < ACC_LEN; i += {WARPS * 32}) cta_acc[i] = 0.0;
+  {(nl + '  ').join(cta_idx_code)}
   __syncthreads();
   {(nl + '  ').join(s0_decl)}
   const long long nwarps = (long long)gridDim.x * {WARPS};
@@ -589,4 +628,4 @@ extern "C" __global__ void __launch_bounds__(256) {finish_name}({', '.join(fin_p
   }}
 }}
 """
-    return KernelSpec(src, name, finish_name, smem_bytes, acc_len, n_groups, out_order, csum_out, pdesc, n_loops)
+    return KernelSpec(src, name, finish_name, smem_bytes + cta_idx_bytes, acc_len, n_groups, out_order, csum_out, pdesc, n_loops)

@@ -128,6 +128,9 @@ def test_cfg5_region_kernel_on_the_host_matches_the_c_linker(tmp_path, B, n, J, 
     got, err, spec = run_region_on_host(rstep.impl, ext, tmp_path)
     assert err == 0
     assert spec.n_loops <= 6
+    # the shared group-index vector is wrapped and checked once per CTA (int32 table in shared memory), then read by both
+    # the gather and the scatter of every row
+    assert spec.source.count("cix0[j]") == 2 and "cix1" not in spec.source
     by_slot = dict(zip(rstep.outs, got))
     # map node outputs to function outputs through the trailing view steps
     after = {}
@@ -184,3 +187,26 @@ def test_gather_elemwise_reduce_region_with_row_outputs(tmp_path):
     by_slot = dict(zip(rstep.outs, got))
     for k, slot in enumerate(prog.outputs):
         np.testing.assert_allclose(np.asarray(by_slot[slot]).reshape(exp[k].shape), exp[k], rtol=2e-5, atol=1e-5)
+
+
+def test_per_cta_index_table_and_per_use_checks_agree(tmp_path, monkeypatch):
+    """PTK_ROWFUSE_CTA_INDEX=0 keeps the per-use 64-bit bounds checks: same results, negative indices wrapped in both."""
+    pytensor.config.floatX = "float32"
+    ins, outs, mk, meta = W.cfg5_logp_grad(B=40, n=70, J=9, K=4, dtype="float32", packed=False)
+    args = mk(seed=11)
+    args[6] = args[6].copy()
+    args[6][::3] -= 9     # NumPy-style negative group indices
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PTK_ROWFUSE_CTA_INDEX", flag)
+        f = pytensor.function(ins, outs, mode="CUDA")
+        prog = f.vm.executor.program
+        ridx, rstep = _region_of(f)
+        vals = _host_values_until(prog, ridx, [_aligned_copy(a) for a in args])
+        (tmp_path / flag).mkdir()
+        got, err, spec = run_region_on_host(rstep.impl, [np.asarray(vals[s].h) for s in rstep.ins], tmp_path / flag, grid=2)
+        assert err == 0 and ("cix0" in spec.source) == (flag == "1")
+        res.append(got)
+    for a, b in zip(*res):   # (the shared-memory float atomics add in thread-arrival order: equal up to that rounding)
+        a, b = np.asarray(a), np.asarray(b)
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5 * max(1.0, float(np.max(np.abs(b))) if b.size else 1.0))
