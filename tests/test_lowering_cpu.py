@@ -321,3 +321,35 @@ def test_runs_of_dense_layers_become_one_chain_node_only_when_nothing_else_reads
     chain = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == "MlpChainNode"]
     assert len(chain) == 1 and len(chain[0].layers) == 5
     trace_function(f, [np.zeros((8, 16), dtype="float32")] + [np.zeros((16, 16), dtype="float32")] * 6)
+
+
+def test_advanced_indexing_dispatch_between_the_fast_and_the_general_nodes():
+    """Integer index arrays on consecutive axes with everything else taken in full -> TakeNode / PutNode (one gather /
+    scatter kernel); boolean masks, index arrays separated by a slice, partial slices next to an index array and
+    `ignore_duplicates` increments -> the general AdvIndexNode / AdvIndexPutNode with the template NumPy's rules need
+    (pytensor/tensor/subtensor.py:1932-2236)."""
+    pytensor.config.floatX = "float32"
+    x = pt.ftensor3("x")
+    i, j = pt.lvector("i"), pt.lvector("j")
+    mb = pt.tensor("mb", dtype="bool", shape=(None, None))
+    y = pt.fmatrix("y")
+
+    def only(f, name):
+        nodes = [st.impl for st in f.vm.executor.program.steps if type(st.impl).__name__ == name]
+        assert len(nodes) == 1, _steps(f)
+        return nodes[0]
+
+    assert "TakeNode" in _steps(pytensor.function([x, i], x[:, i], mode="CUDA"))
+    assert "TakeNode" in _steps(pytensor.function([x, i, j], x[i, j], mode="CUDA"))
+    n = only(pytensor.function([x, i, j], x[i, :, j], mode="CUDA"), "AdvIndexNode")           # separated by a slice
+    assert [e[0] for e in n.template] == ["a", "s", "a"] and set(n.kinds.values()) == {("int", 1)}
+    n = only(pytensor.function([x, mb], x[mb], mode="CUDA"), "AdvIndexNode")                   # 2-d mask over axes 0, 1
+    assert n.template == [("a", 0)] and n.kinds == {0: ("bool", 2)}
+    n = only(pytensor.function([x, i], x[1:, i], mode="CUDA"), "AdvIndexNode")                 # partial slice + index array
+    assert n.template[0][0] == "s" and n.template[1] == ("a", n.template[1][1])
+    assert _steps(pytensor.function([x, i, y], pt.inc_subtensor(x[:, i, 0], y), mode="CUDA")) == ["PutNode"]
+    n = only(pytensor.function([x, mb, pt.fscalar("s")], pt.set_subtensor(x[mb], 0.5), mode="CUDA", on_unused_input="ignore"),
+             "AdvIndexPutNode")
+    assert n.set_instead_of_inc and n.kinds == {0: ("bool", 2)}
+    n = only(pytensor.function([x, i, y], pt.inc_subtensor(x[i, :, 0], y, ignore_duplicates=True), mode="CUDA"), "AdvIndexPutNode")
+    assert n.ignore_duplicates and not n.set_instead_of_inc
