@@ -17,7 +17,6 @@ The inner graph is itself a lowered CUDA Program executed once per step — no h
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 from ..runtime import device as dev
 from .nodes_elemwise import Node
