@@ -628,18 +628,20 @@ __device__ __forceinline__ void mc_cp_async_wait_all() {
 __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict__ x, long long sx0, float* __restrict__ y,
                                                         long long sy0, long long M, const __grid_constant__ MlpChain c) {
   extern __shared__ float mc_smem[];
-  float* hbuf[2] = {mc_smem, mc_smem + MC_ROWS * MC_MAXW};
-  float* wbuf[2] = {mc_smem + 2 * MC_ROWS * MC_MAXW, mc_smem + 2 * MC_ROWS * MC_MAXW + MC_MAXW * MC_MAXW};
+  // Buffer l & 1 of the activations / weights, as ARITHMETIC on the shared array: an indexed array of pointers would live in
+  // local memory and turn every access of the k-loop into a generic load behind 64-bit address arithmetic.
+  auto hbuf = [&](int i) -> float* { return mc_smem + i * (MC_ROWS * MC_MAXW); };
+  auto wbuf = [&](int i) -> float* { return mc_smem + 2 * MC_ROWS * MC_MAXW + i * (MC_MAXW * MC_MAXW); };
   const int tid = threadIdx.x, r = tid >> 4, c0 = tid & 15;
   const long long row0 = (long long)blockIdx.x * MC_ROWS;
   // layer 0's weights start streaming; meanwhile the input rows are copied in (zeros for rows past M)
   {
     const MlpLayer& l0 = c.layer[0];
     const int n4 = (l0.K * l0.N) >> 2;
-    for (int i = tid; i < n4; i += 256) mc_cp_async16(wbuf[0] + 4 * i, l0.W + 4 * i);
+    for (int i = tid; i < n4; i += 256) mc_cp_async16(wbuf(0) + 4 * i, l0.W + 4 * i);
     for (int i = tid; i < MC_ROWS * l0.K; i += 256) {
       const int rr = i / l0.K, kk = i - rr * l0.K;
-      hbuf[0][rr * MC_MAXW + kk] = (row0 + rr < M) ? x[(row0 + rr) * sx0 + kk] : 0.0f;
+      hbuf(0)[rr * MC_MAXW + kk] = (row0 + rr < M) ? x[(row0 + rr) * sx0 + kk] : 0.0f;
     }
   }
   for (int l = 0; l < c.L; ++l) {
@@ -649,15 +651,24 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict_
     if (l + 1 < c.L) {               // W_{l+1} goes into the buffer layer l-1 used (all its readers passed the barrier above)
       const MlpLayer& nx = c.layer[l + 1];
       const int n4 = (nx.K * nx.N) >> 2;
-      float* dst = wbuf[(l + 1) & 1];
+      float* dst = wbuf((l + 1) & 1);
       for (int i = tid; i < n4; i += 256) mc_cp_async16(dst + 4 * i, nx.W + 4 * i);
     }
-    const float* h = hbuf[l & 1] + r * MC_MAXW;
-    const float* W = wbuf[l & 1];
+    const float* h = hbuf(l & 1) + r * MC_MAXW;
+    const float* W = wbuf(l & 1);
     const int K = ly.K, N = ly.N;
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     const int ca = 4 * c0, cb = 64 + 4 * c0;
     const bool use_a = ca < N, use_b = cb < N;
+    // the bias values are requested BEFORE the product loop (their L2 latency hides behind it); read after it
+    float bv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (ly.bias != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (use_a) bv[0][e] = __ldg(ly.bias + ca + e);
+        if (use_b) bv[1][e] = __ldg(ly.bias + cb + e);
+      }
+    }
     for (int k = 0; k < K; ++k) {
       const float hv = h[k];
       if (use_a) {
@@ -672,15 +683,14 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const float* __restrict_
       }
     }
     const bool last = l + 1 == c.L;
-    float* hn = hbuf[(l + 1) & 1] + r * MC_MAXW;
+    float* hn = hbuf((l + 1) & 1) + r * MC_MAXW;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int cc = j ? cb : ca;
       if (cc < N) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float v = acc[j][e];
-          if (ly.bias) v += ly.bias[cc + e];
+          float v = acc[j][e] + bv[j][e];
           if (ly.act == 1) v = tanhf(v);
           if (last) {
             if (row0 + r < M) y[(row0 + r) * sy0 + cc + e] = v;

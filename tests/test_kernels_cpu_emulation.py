@@ -521,7 +521,8 @@ def test_small_mlp_chain_kernel(tmp_path, M, widths, acts, with_bias):
     defs = text[i0:i1]
     shim = ("#define __grid_constant__\nstruct alignas(16) float4 { float x, y, z, w; };\n" + defs +
             "static inline void mc_cp_async16(float* d, const float* s) { std::memcpy(d, s, 16); }\n"
-            "static inline void mc_cp_async_wait_all() {}\nusing std::fmaf;\n")
+            "static inline void mc_cp_async_wait_all() {}\nusing std::fmaf;\n"
+            "template <typename T> static inline T __ldg(const T* p) { return *p; }\n")
     src = shim + extract_static_kernel(os.path.join(CSRC, "ptk_blas.cu"), "mlp_chain_kernel").replace(
         "extern __shared__ float mc_smem[];", "alignas(16) static float mc_smem[2 * 16 * 128 + 2 * 128 * 128];")
     k = EmulatedKernel(src, "mlp_chain_kernel", tmp_path, threaded=True)
