@@ -185,9 +185,12 @@ extern "C" __global__ void __launch_bounds__(256) {name}({', '.join(params)}) {{
 #pragma unroll
     for (int k = {MAX_DIMS} - 1; k >= 0; --k) {{
       if (k < dims.ndim) {{
-        const long long q = rem / dims.shape[k];
-        const long long cidx = rem - q * dims.shape[k];
-        rem = q;
+        long long cidx = rem;                 // the outermost axis (k == 0) keeps what is left: no division
+        if (k > 0) {{
+          const long long q = rem / dims.shape[k];
+          cidx = rem - q * dims.shape[k];
+          rem = q;
+        }}
 {offs_acc}
       }}
     }}

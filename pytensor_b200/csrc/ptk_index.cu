@@ -52,11 +52,14 @@ __global__ void __launch_bounds__(256) copy_strided_kernel(T* __restrict__ dst, 
 #pragma unroll
     for (int k = kMaxDims - 1; k >= 0; --k) {
       if (k < d.ndim) {
-        int64_t q = r / d.shape[k];
-        int64_t c = r - q * d.shape[k];
+        int64_t c = r;                        // the outermost axis (k == 0) keeps what is left: no division
+        if (k > 0) {
+          const int64_t q = r / d.shape[k];
+          c = r - q * d.shape[k];
+          r = q;
+        }
         oa += c * d.a[k];
         ob += c * d.b[k];
-        r = q;
       }
     }
     dst[oa] = src[ob];
@@ -90,11 +93,14 @@ __global__ void __launch_bounds__(256) inc_strided_kernel(T* __restrict__ dst, c
 #pragma unroll
     for (int k = kMaxDims - 1; k >= 0; --k) {
       if (k < d.ndim) {
-        int64_t q = r / d.shape[k];
-        int64_t c = r - q * d.shape[k];
+        int64_t c = r;                        // the outermost axis (k == 0) keeps what is left: no division
+        if (k > 0) {
+          const int64_t q = r / d.shape[k];
+          c = r - q * d.shape[k];
+          r = q;
+        }
         oa += c * d.a[k];
         ob += c * d.b[k];
-        r = q;
       }
     }
     dst[oa] = dst[oa] + src[ob];
