@@ -53,13 +53,15 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def _ncu_traffic(kernel_prefix, pattern="*prof_ew*_ncu_summary.csv"):
+def _ncu_traffic(kernel_prefix, pattern=("*prof_k3_final*_ncu_summary.csv", "*prof_ew*_ncu_summary.csv")):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture summary of the same command (profiles/); None when no capture is committed."""
+    capture summary of the same command (profiles/; the newest round's capture first); None when no capture is committed."""
     import csv
     import glob
 
-    for path in sorted(glob.glob(os.path.join(REPO, "profiles", pattern)), reverse=True):
+    patterns = (pattern,) if isinstance(pattern, str) else tuple(pattern)
+    paths = [p for pat in patterns for p in sorted(glob.glob(os.path.join(REPO, "profiles", pat)), reverse=True)]
+    for path in paths:
         try:
             rows = list(csv.reader(open(path)))
             hdr, units = rows[0], rows[1]
