@@ -16,7 +16,7 @@ GOLD = os.path.join(HERE, "golden")
 import sys  # noqa: E402
 
 sys.path.insert(0, GOLD)
-from cases import CASES  # noqa: E402
+from cases import CASES, CPU_ONLY  # noqa: E402
 
 from oracle import numpy_port  # noqa: E402
 
@@ -31,6 +31,8 @@ def _load(name):
 def _tol(name, dtype):
     if "scan" in name or "mlp" in name or "elemwise" in name:
         return dict(rtol=2e-5, atol=2e-5)
+    if "special" in name:   # the reference's own C support code (AS 103 / AS 121 with truncated coefficients, Cephes incbet) vs SciPy
+        return dict(rtol=1e-7, atol=1e-9)
     return dict(rtol=1e-6, atol=1e-6) if np.dtype(dtype) == np.float32 else dict(rtol=1e-9, atol=1e-10)
 
 
@@ -56,5 +58,6 @@ def test_numpy_port_matches_reference_golden(name):
     res2 = numpy_port.evaluate_program(prog2, gin)
     for r, e in zip(res2, res):
         np.testing.assert_array_equal(r, e)
-    with open(os.path.join(GOLD, name + ".program.pkl"), "wb") as fh:
-        fh.write(blob)
+    if name not in CPU_ONLY:   # (CPU_ONLY cases pin the port oracle only; the GPU suite replays what has a pickle)
+        with open(os.path.join(GOLD, name + ".program.pkl"), "wb") as fh:
+            fh.write(blob)
