@@ -28,17 +28,34 @@ def compare_cuda_and_cvm(inputs, outputs, test_inputs, mode="CUDA", rtol=None, a
     if os.environ.get("PTK_DRY") == "1":  # developer dry run without a GPU: lowering + reference only
         from pytensor_b200.precompile import trace_function
 
-        f_ref(*[np.array(x, copy=True) for x in test_inputs])
+        exp = f_ref(*[np.array(x, copy=True) for x in test_inputs])
         trace_function(f_cuda, [np.array(x, copy=True) for x in test_inputs])  # launch logic + NVRTC, no device
+        # ... and the LOWERED program (after this backend's fusion passes and peepholes) interpreted by the NumPy port
+        # oracle against the C linker: checks the lowering itself, not the kernels
+        from oracle import numpy_port
+
+        prog = f_cuda.vm.executor.program
+        if len(prog.inputs) == len(test_inputs):
+            try:
+                got = numpy_port.evaluate_program(prog, [np.array(x, copy=True) for x in test_inputs])
+            except NotImplementedError:
+                got = None
+            if got is not None:
+                _assert_close(got, exp, rtol, atol, exact, atol_scale, port=True)
         return f_cuda, None
     got = f_cuda(*[np.array(x, copy=True) for x in test_inputs])
     exp = f_ref(*[np.array(x, copy=True) for x in test_inputs])
+    _assert_close(got, exp, rtol, atol, exact, atol_scale)
+    return f_cuda, got
+
+
+def _assert_close(got, exp, rtol, atol, exact, atol_scale, port=False):
     assert len(got) == len(exp)
     for g, e in zip(got, exp):
         g, e = np.asarray(g), np.asarray(e)
         assert g.dtype == e.dtype, (g.dtype, e.dtype)
         assert g.shape == e.shape, (g.shape, e.shape)
-        if exact or e.dtype.kind in "biu":
+        if (exact and not (port and e.dtype.kind == "f")) or e.dtype.kind in "biu":
             np.testing.assert_array_equal(g, e)
         else:
             t = tol_for(e.dtype)
@@ -46,4 +63,3 @@ def compare_cuda_and_cvm(inputs, outputs, test_inputs, mode="CUDA", rtol=None, a
             if atol_scale is not None and e.size:
                 a = atol_scale * float(np.max(np.abs(e[np.isfinite(e)]))) if np.isfinite(e).any() else a
             np.testing.assert_allclose(g, e, rtol=rtol if rtol is not None else t["rtol"], atol=a, equal_nan=True)
-    return f_cuda, got
