@@ -198,14 +198,19 @@ def fuse_row_regions(steps, output_slots, opts):
     new_steps = list(steps)
     removed = set()
     inserts = {}     # position (index of the region's last step) -> (fused Step, tainted outside steps to move behind it)
-    for comp in comps.values():
-        comp = sorted(comp)
+    # Regions are accepted in program order of their last step, and only while the steps they TOUCH (members + outside steps
+    # that move behind the fused node) are untouched by an accepted region: a region whose members another region has
+    # moved (it reads, through a view, what that region produces) would otherwise be emitted BEFORE its producer — and
+    # its constituent steps once more behind it.  The rejected region simply stays unfused.
+    for comp in sorted((sorted(c) for c in comps.values()), key=lambda c: c[-1]):
         built = _build_region(steps, comp, kinds, types, consts, set(output_slots), opts)
         if built is None:
             continue
         fused_step, moved = built
-        removed.update(comp)
-        removed.update(moved)
+        touch = set(comp) | set(moved)
+        if touch & removed:
+            continue
+        removed.update(touch)
         inserts[comp[-1]] = (fused_step, [steps[j] for j in moved])
     if not inserts:
         return steps

@@ -1,0 +1,122 @@
+"""Random small graphs for the lowering: compile with mode="CUDA" (no device needed: lowering + this backend's fusion
+passes and peepholes run at link time), interpret the LOWERED program with the NumPy port oracle and compare with the
+reference C linker.  Finds lowering / re-fusion bugs without a GPU (it found the region-ordering bug fixed in
+link/cuda/fusion_rows.py).  Test infrastructure:
+
+    python tests/lowering_fuzz.py 500 [first_seed]          # FUZZ_BIG=1: 60-90 rows/columns instead of 2-8
+"""
+
+import os
+import sys
+
+import numpy as np
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from helpers import pytensor  # noqa: E402
+
+import pytensor.tensor as pt  # noqa: E402
+from oracle import numpy_port  # noqa: E402
+from pytensor_b200.link.cuda.fusion import read_before_write  # noqa: E402
+
+
+def build(rng, dtype):
+    lo, hi = (2, 9) if os.environ.get("FUZZ_BIG") != "1" else (60, 90)
+    M, N, K = (int(rng.integers(lo, hi)) for _ in range(3))
+    a, b, w = pt.matrix("a", dtype=dtype), pt.matrix("b", dtype=dtype), pt.matrix("w", dtype=dtype)
+    v = pt.vector("v", dtype=dtype)
+    idx = pt.lvector("idx")
+    vals = [rng.standard_normal((M, N)).astype(dtype), rng.standard_normal((M, N)).astype(dtype),
+            rng.standard_normal(N).astype(dtype), (rng.standard_normal((N, K)) / 2).astype(dtype),
+            rng.integers(-N, N, size=int(rng.integers(1, 7))).astype("int64")]
+    c = lambda x: np.asarray(x, dtype=dtype)  # noqa: E731
+    pool = [a, b, a * c(0.5) + b, v]
+
+    def pick(nd=None):
+        cand = [p for p in pool if nd is None or p.ndim == nd]
+        return cand[int(rng.integers(len(cand)))]
+
+    for _ in range(int(rng.integers(3, 10))):
+        k = int(rng.integers(0, 16))
+        try:
+            if k == 0:
+                r = pick(2) + pick(2)
+            elif k == 1:
+                r = pt.tanh(pick() * c(0.7))
+            elif k == 2:
+                x = pick()
+                r = pt.maximum(x, -x) + pt.sqr(x) * c(0.1)
+            elif k == 3:
+                r = pt.exp(-pt.abs(pick()))
+            elif k == 4:
+                r = pick(2).sum(axis=int(rng.integers(0, 2)))
+            elif k == 5:
+                r = pick(2).max(axis=int(rng.integers(0, 2)))
+            elif k == 6:
+                r = pt.dot(pick(2), w)
+            elif k == 7:
+                r = pick(2).T
+            elif k == 8:
+                r = pick(2)[:, idx]
+            elif k == 9:
+                r = pick(2)[::2, 1:]
+            elif k == 10:
+                x = pick(2)
+                r = pt.inc_subtensor(x[:, idx], x[:, idx] * 2)
+            elif k == 11:
+                r = pt.set_subtensor(pick(2)[1:, ::2], c(0.25))
+            elif k == 12:
+                r = pick(2) * v
+            elif k == 13:
+                r = pt.tanh(pt.dot(pick(2), w) + pt.zeros((K,), dtype=dtype) + c(0.1))
+            elif k == 14:
+                r = pt.special.softmax(pick(2), axis=1)
+            else:
+                x = pick()
+                r = pt.switch(x > 0, x, pt.expm1(x))
+            pool.append(r)
+        except Exception:  # noqa: BLE001  (shape-incompatible combination: skip this op)
+            pass
+    outs = []
+    for _ in range(int(rng.integers(1, 4))):
+        o = pick()
+        outs.append(o if rng.random() < 0.5 else o.sum())
+    return [a, b, v, w, idx], outs, vals
+
+
+def check_seed(seed):
+    """"ok" | "skipped" (the random graph is ill-shaped for the reference itself); raises on a lowering mismatch."""
+    rng = np.random.default_rng(seed)
+    dtype = "float32" if seed % 2 else "float64"
+    pytensor.config.floatX = dtype
+    try:
+        ins, outs, vals = build(rng, dtype)
+        exp = pytensor.function(ins, outs, mode="CVM", on_unused_input="ignore")(*[np.array(x, copy=True) for x in vals])
+    except Exception:  # noqa: BLE001
+        return "skipped"
+    f = pytensor.function(ins, outs, mode="CUDA", on_unused_input="ignore")
+    prog = f.vm.executor.program
+    bad = read_before_write(prog.steps, set(prog.inputs) | set(prog.constants))
+    assert bad is None, f"seed {seed}: step {bad} reads a slot nobody wrote: {[type(s.impl).__name__ for s in prog.steps]}"
+    got = numpy_port.evaluate_program(prog, [np.array(x, copy=True) for x in vals])
+    tol = 2e-5 if dtype == "float32" else 1e-9
+    for g, e in zip(got, exp):
+        g, e = np.asarray(g), np.asarray(e)
+        assert g.shape == e.shape and g.dtype == e.dtype, (seed, g.shape, e.shape, g.dtype, e.dtype)
+        np.testing.assert_allclose(g, e, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(e))) if e.size else 1.0),
+                                   err_msg=f"seed {seed}: {[type(s.impl).__name__ for s in prog.steps]}")
+    return "ok"
+
+
+if __name__ == "__main__":
+    n, first = int(sys.argv[1]), int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    count = {"ok": 0, "skipped": 0, "FAILED": 0}
+    for s in range(first, first + n):
+        try:
+            count[check_seed(s)] += 1
+        except Exception as e:  # noqa: BLE001
+            count["FAILED"] += 1
+            print("SEED", s, type(e).__name__, str(e)[:400].replace("\n", " | "))
+    print(count)

@@ -210,3 +210,29 @@ def test_per_cta_index_table_and_per_use_checks_agree(tmp_path, monkeypatch):
     for a, b in zip(*res):   # (the shared-memory float atomics add in thread-arrival order: equal up to that rounding)
         a, b = np.asarray(a), np.asarray(b)
         np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5 * max(1.0, float(np.max(np.abs(b))) if b.size else 1.0))
+
+
+def test_a_region_that_reads_a_view_of_another_regions_output_stays_behind_it():
+    """Two regions where the second reads (through a transposing view) what the first produces: the pass used to emit the
+    reader's fused node before its producer, and the reader's steps once more behind it (found by a random-graph search
+    that interprets every lowered program with the NumPy port oracle).  Now the conflicting region stays unfused; the
+    program is well ordered and agrees with the C linker."""
+    from oracle import numpy_port
+    from pytensor_b200.link.cuda.fusion import read_before_write
+
+    pytensor.config.floatX = "float64"
+    b, idx = pt.dmatrix("b"), pt.lvector("idx")
+    h = pt.switch(b > 0, b, pt.expm1(b))
+    u = pt.inc_subtensor(h[:, idx], h[:, idx] * 2)            # region over the rows of h
+    ht = h.T
+    w = pt.inc_subtensor(ht[:, idx], ht[:, idx] * 2)          # region over the rows of h.T: reads a view of the first one's output
+    outs = [ht.sum(), w, u]
+    rng = np.random.default_rng(1158)
+    vals = [rng.standard_normal((6, 6)), np.array([1, -2, 0, 1])]
+    f = pytensor.function([b, idx], outs, mode="CUDA")
+    prog = f.vm.executor.program
+    assert read_before_write(prog.steps, set(prog.inputs) | set(prog.constants)) is None
+    exp = pytensor.function([b, idx], outs, mode="CVM")(*vals)
+    got = numpy_port.evaluate_program(prog, vals)
+    for g, e in zip(got, exp):
+        np.testing.assert_allclose(g, e, rtol=1e-12, atol=1e-12)
