@@ -39,7 +39,7 @@ def build(rng, dtype):
         return cand[int(rng.integers(len(cand)))]
 
     for _ in range(int(rng.integers(3, 10))):
-        k = int(rng.integers(0, 16))
+        k = int(rng.integers(0, 30))
         try:
             if k == 0:
                 r = pick(2) + pick(2)
@@ -73,9 +73,49 @@ def build(rng, dtype):
                 r = pt.tanh(pt.dot(pick(2), w) + pt.zeros((K,), dtype=dtype) + c(0.1))
             elif k == 14:
                 r = pt.special.softmax(pick(2), axis=1)
-            else:
+            elif k == 15:
                 x = pick()
                 r = pt.switch(x > 0, x, pt.expm1(x))
+            elif k == 16:
+                r = pt.dot(pick(2), v)                                   # Gemv
+            elif k == 17:
+                r = pick(2) + c(0.3) * pt.outer(pick(2).sum(axis=1), v)  # Ger
+            elif k == 18:
+                x = pick(2)
+                r = c(0.6) * x + c(-1.5) * pt.dot(pt.dot(x, w), w.T)     # Gemm alpha/beta forms
+            elif k == 19:
+                r = pt.concatenate([pick(2), pick(2)], axis=int(rng.integers(0, 2)))
+            elif k == 20:
+                x = pick(2)
+                r = x.reshape((-1,))[:: int(rng.integers(1, 4))]
+            elif k == 21:
+                r = pt.cumsum(pick(2), axis=int(rng.integers(0, 2)))
+            elif k == 22:
+                r = pt.cast(pt.argmax(pick(2), axis=int(rng.integers(0, 2))), dtype)
+            elif k == 23:
+                x = pick(2)
+                r = x[x.sum(axis=1) > 0]                                 # boolean mask over rows (data-dependent shape)
+            elif k == 24:
+                x = pick(2)
+                r = pt.set_subtensor(x[x > c(0.5)], c(0.5))              # 2-d mask set
+            elif k == 25:
+                x = pick(2)
+                t3 = pt.stack([x, x * c(2.0), -x])                       # (3, ., .)
+                r = t3[idx % 3, :, idx % 2] if False else t3[:, idx, :].sum(axis=0)
+            elif k == 26:
+                x = pick(2)
+                r = pt.special.logsumexp(x, axis=1) + pt.special.log_softmax(x, axis=0).sum(axis=1)
+            elif k == 27:
+                x = pick(2)
+                g = pt.dot(x.T, x) + c(float(x.type.shape[0] or 10.0)) * pt.eye(x.shape[1], dtype=dtype) * c(10.0)
+                L = pt.linalg.cholesky(g)
+                r = pt.linalg.solve_triangular(L, x.T, lower=True)
+            elif k == 28:
+                x = pick(2)
+                r = pt.clip(x, c(-0.5), c(0.8)) * pt.sigmoid(x) + pt.log1p(pt.exp(x))
+            else:
+                x = pick(2)
+                r = pt.arange(x.shape[1], dtype=dtype) * x
             pool.append(r)
         except Exception:  # noqa: BLE001  (shape-incompatible combination: skip this op)
             pass
