@@ -179,6 +179,21 @@ def lower_node(node, opts):
         bc = [tuple(i.type.broadcastable) for i in node.inputs]
         return ElemwiseNode(prog, nd, bc, dict(op.inplace_pattern), name=str(op))
 
+    if isinstance(op, ps.ScalarOp):
+        # A scalar op applied to 0-d SCALAR-typed values (the reference's shape / index arithmetic between
+        # ScalarFromTensor and TensorFromScalar, e.g. maximum(shape_i, shape_j) of a broadcast; C code from
+        # ScalarOp.c_code, scalar/basic.py:1411-3861): the same scalar program as a 0-d Elemwise.
+        in_dt = [i.type.dtype for i in node.inputs]
+        out_dt = [o.type.dtype for o in node.outputs]
+        try:
+            prog = scalar_program(op, in_dt, out_dt)
+            from pytensor_b200.codegen.scalar import emit_body
+
+            emit_body(prog)
+        except UnsupportedScalarOp as e:
+            raise UnsupportedOp(str(e)) from e
+        return ElemwiseNode(prog, 0, [() for _ in node.inputs], {}, name=str(op))
+
     if isinstance(op, CAReduce):
         sname = type(op.scalar_op).__name__
         if sname not in _RED_NAMES:

@@ -353,3 +353,24 @@ def test_advanced_indexing_dispatch_between_the_fast_and_the_general_nodes():
     assert n.set_instead_of_inc and n.kinds == {0: ("bool", 2)}
     n = only(pytensor.function([x, i, y], pt.inc_subtensor(x[i, :, 0], y, ignore_duplicates=True), mode="CUDA"), "AdvIndexPutNode")
     assert n.ignore_duplicates and not n.set_instead_of_inc
+
+
+def test_scalar_ops_applied_to_scalar_typed_values_lower_as_zero_d_elemwise():
+    """The reference's shape arithmetic sometimes survives as a ScalarOp applied to SCALAR-typed values between
+    ScalarFromTensor and TensorFromScalar (here `maximum(shape_i, shape_j)` sizing the Gemv output of a broadcast sum; found
+    by tests/lowering_fuzz.py): lowered as the same scalar program over 0-d values, evaluated on the host."""
+    import pytensor.scalar.basic as ps
+    from oracle import numpy_port
+
+    pytensor.config.floatX = "float64"
+    a, b, w, v = pt.dmatrix("a"), pt.dmatrix("b"), pt.dmatrix("w"), pt.dvector("v")
+    k = a * 0.5 + b
+    out = pt.dot(0.6 * k - 1.5 * pt.dot(pt.dot(k, w), w.T), v)
+    f_ref = pytensor.function([a, b, w, v], out, mode="CVM")
+    assert any(isinstance(n.op, ps.ScalarOp) for n in f_ref.maker.fgraph.toposort())   # the situation exists in this graph
+    f = pytensor.function([a, b, w, v], out, mode="CUDA")
+    rng = np.random.default_rng(5)
+    vals = [rng.standard_normal((6, 4)), rng.standard_normal((6, 4)), rng.standard_normal((4, 3)), rng.standard_normal(4)]
+    got = numpy_port.evaluate_program(f.vm.executor.program, vals)
+    np.testing.assert_allclose(got[0], f_ref(*vals), rtol=1e-12, atol=1e-12)
+    assert trace_function(f, vals) >= 1      # the host shape arithmetic really runs in trace-only mode
