@@ -26,11 +26,13 @@ def build(rng, dtype):
     lo, hi = (2, 9) if os.environ.get("FUZZ_BIG") != "1" else (60, 90)
     M, N, K = (int(rng.integers(lo, hi)) for _ in range(3))
     a, b, w = pt.matrix("a", dtype=dtype), pt.matrix("b", dtype=dtype), pt.matrix("w", dtype=dtype)
+    ws = pt.matrix("ws", dtype=dtype)       # (N, N)
     v = pt.vector("v", dtype=dtype)
     idx = pt.lvector("idx")
     vals = [rng.standard_normal((M, N)).astype(dtype), rng.standard_normal((M, N)).astype(dtype),
             rng.standard_normal(N).astype(dtype), (rng.standard_normal((N, K)) / 2).astype(dtype),
-            rng.integers(-N, N, size=int(rng.integers(1, 7))).astype("int64")]
+            rng.integers(-N, N, size=int(rng.integers(1, 7))).astype("int64"),
+            (rng.standard_normal((N, N)) / np.sqrt(N)).astype(dtype)]
     c = lambda x: np.asarray(x, dtype=dtype)  # noqa: E731
     pool = [a, b, a * c(0.5) + b, v]
 
@@ -39,7 +41,7 @@ def build(rng, dtype):
         return cand[int(rng.integers(len(cand)))]
 
     for _ in range(int(rng.integers(3, 10))):
-        k = int(rng.integers(0, 30))
+        k = int(rng.integers(0, 36))
         try:
             if k == 0:
                 r = pick(2) + pick(2)
@@ -113,9 +115,37 @@ def build(rng, dtype):
             elif k == 28:
                 x = pick(2)
                 r = pt.clip(x, c(-0.5), c(0.8)) * pt.sigmoid(x) + pt.log1p(pt.exp(x))
-            else:
+            elif k == 29:
                 x = pick(2)
                 r = pt.arange(x.shape[1], dtype=dtype) * x
+            elif k == 30:      # elementwise recurrence (persistent fused Scan), last state or the whole trace
+                x = pick(2)
+                hs = pytensor.scan(lambda h, q: pt.tanh(h * c(0.9) + q), outputs_info=[x], non_sequences=[x * c(0.1)],
+                                   n_steps=int(rng.integers(1, 6)), return_updates=False)
+                r = hs[-1] if rng.random() < 0.5 else hs.sum(axis=0)
+            elif k == 31:      # sequence + two taps (general Scan loop)
+                x = pick(2)
+                hs = pytensor.scan(lambda s_t, h1, h2: h1 * c(0.5) - h2 * c(0.25) + s_t,
+                                   sequences=[pt.stack([x, x * c(2.0), -x])],
+                                   outputs_info=[dict(initial=pt.stack([x, x]), taps=[-1, -2])], return_updates=False)
+                r = hs[-1]
+            elif k == 32:
+                x = pick(2)
+                r = pt.dot(x, w).max(axis=1, keepdims=True) - x[:, :1]
+            elif k == 33:      # a run of dense layers (bias/tanh epilogue fusion; >= 4 of them: one chain node)
+                h = pick(2)
+                for _ in range(int(rng.integers(1, 6))):
+                    h = pt.tanh(pt.dot(h, ws) + v) if rng.random() < 0.8 else pt.tanh(pt.dot(h, ws))
+                r = h
+            elif k == 34:      # matmul recurrence
+                x = pick(2)
+                hs = pytensor.scan(lambda h, W_, b_: pt.tanh(pt.dot(h, W_) + b_), outputs_info=[x], non_sequences=[ws, v],
+                                   n_steps=int(rng.integers(1, 5)), return_updates=False)
+                r = hs[-1] if rng.random() < 0.5 else hs
+            else:
+                x = pick(2)
+                t3 = pt.stack([x, x * c(0.5)])
+                r = pt.batched_dot(t3, pt.stack([ws, ws.T])).sum(axis=0)
             pool.append(r)
         except Exception:  # noqa: BLE001  (shape-incompatible combination: skip this op)
             pass
@@ -123,7 +153,13 @@ def build(rng, dtype):
     for _ in range(int(rng.integers(1, 4))):
         o = pick()
         outs.append(o if rng.random() < 0.5 else o.sum())
-    return [a, b, v, w, idx], outs, vals
+    if rng.random() < 0.35:      # the PyMC use: a scalar and its gradients
+        cost = sum((o.sum() if o.ndim else o) for o in outs)
+        try:
+            outs = [cost] + list(pytensor.grad(cost, [a, v], disconnected_inputs="ignore"))
+        except Exception:  # noqa: BLE001  (non-differentiable op in the random graph)
+            pass
+    return [a, b, v, w, idx, ws], outs, vals
 
 
 def check_seed(seed):
