@@ -92,10 +92,22 @@ def host_eval_program(prog: ScalarProgram, inputs):
             return np.asarray(v, dtype=d)
         return tmp[i]
 
+    def c_differs_from_numpy(a):
+        """NumPy promotes a signed/unsigned pair to a wider signed type (or float64); the C expressions the reference
+        generates — and the device kernels, which compile the same expressions — convert the signed operand to the unsigned
+        type when that is at least as wide (and at least `int`): int32(-1) * uint32(3) is 4294967293 there.  Such programs
+        are left to the device path (they never occur in shape arithmetic, which is all int64)."""
+        kinds = [x.dtype for x in a if x.dtype.kind in "iu"]
+        signed = [d.itemsize for d in kinds if d.kind == "i"]
+        unsigned = [d.itemsize for d in kinds if d.kind == "u"]
+        return any(u >= 4 and u >= s_ for u in unsigned for s_ in signed)
+
     tmp = []
     for inst in prog.insts:
         a = [np.asarray(ref(r)) for r in inst.args]
         op, od = inst.op, inst.out_dtype
+        if len(a) > 1 and c_differs_from_numpy(a if op != "Switch" else a[1:]):
+            return None
         if op == "Add":
             r = a[0]
             for x in a[1:]:

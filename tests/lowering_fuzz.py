@@ -162,13 +162,84 @@ def build(rng, dtype):
     return [a, b, v, w, idx, ws], outs, vals
 
 
+def build_dtypes(rng):
+    """Second family: integer / bool / mixed-precision arithmetic, comparisons, bitwise ops, casts and reductions with the
+    reference's accumulator and output dtype rules (tensor/elemwise.py:1352-1417)."""
+    M, N = int(rng.integers(1, 7)), int(rng.integers(1, 9))
+    dts = ["int8", "int16", "int32", "int64", "uint8", "bool", "float32", "float64"]
+    names = ["p", "q", "r"]
+    ins, vals = [], []
+    for nm in names:
+        dt = dts[int(rng.integers(len(dts)))]
+        ins.append(pt.matrix(nm, dtype=dt))
+        if dt == "bool":
+            vals.append(rng.random((M, N)) < 0.5)
+        elif dt.startswith("float"):
+            vals.append((rng.standard_normal((M, N)) * 3).astype(dt))
+        else:
+            lo = 0 if dt.startswith("u") else -6
+            vals.append(rng.integers(lo, 7, size=(M, N)).astype(dt))
+    pool = list(ins)
+
+    def pick():
+        return pool[int(rng.integers(len(pool)))]
+
+    def nonzero(x):
+        return pt.switch(pt.eq(x, 0), pt.ones_like(x), x)
+
+    for _ in range(int(rng.integers(2, 8))):
+        k = int(rng.integers(0, 16))
+        try:
+            x, y = pick(), pick()
+            if k == 0:
+                r = x + y
+            elif k == 1:
+                r = x * y
+            elif k == 2:
+                r = x - y
+            elif k == 3:
+                r = x // nonzero(y) if "bool" not in (x.dtype, y.dtype) else x + y
+            elif k == 4:
+                r = x % nonzero(y) if "bool" not in (x.dtype, y.dtype) else x * y
+            elif k == 5:
+                r = pt.switch(x > y, x, y)
+            elif k == 6:
+                r = pt.cast(x, dts[int(rng.integers(len(dts)))])
+            elif k == 7:
+                r = (x < y) | pt.eq(x, y)
+            elif k == 8:
+                r = pt.maximum(x, y) - pt.minimum(x, y)
+            elif k == 9:
+                r = x.sum(axis=int(rng.integers(0, 2)), keepdims=True) + y
+            elif k == 10:
+                r = x.max(axis=1, keepdims=True) * pt.ones_like(y)
+            elif k == 11:
+                r = pt.abs(x) + pt.sgn(y) if x.dtype != "bool" and y.dtype != "bool" else x & y if x.dtype == y.dtype == "bool" else x + y
+            elif k == 12:
+                r = x / nonzero(y)                                   # true division: ints go through float64
+            elif k == 13:
+                r = pt.all(x > -100, axis=0, keepdims=True) & (y > -100)
+            elif k == 14:
+                r = x.prod(axis=0, keepdims=True) if x.dtype not in ("bool",) else x.any(axis=0, keepdims=True)
+            else:
+                r = pt.clip(x, -2, 3) if x.dtype != "bool" else ~x
+            pool.append(r)
+        except Exception:  # noqa: BLE001
+            pass
+    outs = []
+    for _ in range(int(rng.integers(1, 4))):
+        o = pick()
+        outs.append(o if rng.random() < 0.6 else o.sum(axis=int(rng.integers(0, 2))))
+    return ins, outs, vals
+
+
 def check_seed(seed):
     """"ok" | "skipped" (the random graph is ill-shaped for the reference itself); raises on a lowering mismatch."""
     rng = np.random.default_rng(seed)
     dtype = "float32" if seed % 2 else "float64"
     pytensor.config.floatX = dtype
     try:
-        ins, outs, vals = build(rng, dtype)
+        ins, outs, vals = build_dtypes(rng) if seed % 5 == 4 else build(rng, dtype)
         exp = pytensor.function(ins, outs, mode="CVM", on_unused_input="ignore")(*[np.array(x, copy=True) for x in vals])
     except Exception:  # noqa: BLE001
         return "skipped"

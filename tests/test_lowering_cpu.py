@@ -374,3 +374,26 @@ def test_scalar_ops_applied_to_scalar_typed_values_lower_as_zero_d_elemwise():
     got = numpy_port.evaluate_program(f.vm.executor.program, vals)
     np.testing.assert_allclose(got[0], f_ref(*vals), rtol=1e-12, atol=1e-12)
     assert trace_function(f, vals) >= 1      # the host shape arithmetic really runs in trace-only mode
+
+
+def test_host_integer_evaluator_leaves_c_conversion_corner_cases_to_the_device():
+    """Small integer programs over host values are evaluated with NumPy (shape arithmetic).  Where C's usual arithmetic
+    conversions — which the reference's generated code and the device kernels follow — differ from NumPy's promotion (a
+    signed operand meeting an unsigned one of at least its width: int8(-3) * uint32(2) is 4294967290 in C, -6 in NumPy) the
+    evaluator declines and the node takes the device path.  (Found with the port-oracle fuzzer over mixed integer dtypes.)"""
+    from pytensor_b200.codegen.scalar import ScalarInst, ScalarProgram
+    from pytensor_b200.vm.nodes_elemwise import host_eval_program
+
+    def prog(op, in_dt, out_dt):
+        return ScalarProgram(list(in_dt), [out_dt], [], [ScalarInst(op, [("i", k) for k in range(len(in_dt))], list(in_dt), out_dt)],
+                             [("t", 0)])
+
+    a8, u32 = np.array([-3, 2], dtype="int8"), np.array([2, 5], dtype="uint32")
+    assert host_eval_program(prog("Mul", ["int8", "uint32"], "int64"), [a8, u32]) is None
+    assert host_eval_program(prog("LT", ["int32", "uint64"], "bool"), [a8.astype("int32"), u32.astype("uint64")]) is None
+    assert host_eval_program(prog("Switch", ["bool", "int32", "uint32"], "int64"), [a8 > 0, a8.astype("int32"), u32]) is None
+    # no corner case: signed with a NARROWER unsigned (C promotes both to the signed type), and all-int64 shape arithmetic
+    r = host_eval_program(prog("Mul", ["int64", "uint32"], "int64"), [a8.astype("int64"), u32])
+    np.testing.assert_array_equal(r[0], np.array([-6, 10], dtype="int64"))
+    r = host_eval_program(prog("Maximum", ["int64", "int64"], "int64"), [np.int64(7), np.int64(9)])
+    assert int(r[0]) == 9
