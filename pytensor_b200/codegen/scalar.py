@@ -157,12 +157,21 @@ def _mod(a, it, ot):
     return f"ptk_imod_py<{T}>(({T})({x}), ({T})({y}))"
 
 
+def _mixed_signedness(it) -> bool:
+    return any(is_uint(t) for t in it) and any(is_int(t) and not is_uint(t) for t in it)
+
+
 def _maximum(a, it, ot):
     x, y = a
     if ot == "float32" and all(t == "float32" for t in it):
         return f"ptk_max_nan_f32(({x}), ({y}))"  # one FMNMX.NAN: NaN-propagating like the reference's Maximum.c_code
     if is_float(ot):
         return f"((({y}) > ({x})) ? ({y}) : ((({x}) >= ({y})) ? ({x}) : {_nan(ot)}))"
+    if _mixed_signedness(it):
+        # the reference's expression VERBATIM in meaning (scalar/basic.py Maximum.c_code: one expression with a nan("")
+        # arm for every dtype): the comparison happens in the unsigned type, but the selected operand reaches the integer
+        # result through the double the nan arm forces — so a negative signed operand keeps its sign
+        return f"((({y}) > ({x})) ? (double)({y}) : ((({x}) >= ({y})) ? (double)({x}) : {_nan('float64')}))"
     return f"((({y}) > ({x})) ? ({y}) : ({x}))"
 
 
@@ -172,6 +181,8 @@ def _minimum(a, it, ot):
         return f"ptk_min_nan_f32(({x}), ({y}))"
     if is_float(ot):
         return f"((({y}) < ({x})) ? ({y}) : ((({x}) <= ({y})) ? ({x}) : {_nan(ot)}))"
+    if _mixed_signedness(it):   # (see _maximum)
+        return f"((({y}) < ({x})) ? (double)({y}) : ((({x}) <= ({y})) ? (double)({x}) : {_nan('float64')}))"
     return f"((({y}) < ({x})) ? ({y}) : ({x}))"
 
 
