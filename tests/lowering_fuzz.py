@@ -197,10 +197,12 @@ def build_dtypes(rng):
                 r = x * y
             elif k == 2:
                 r = x - y
-            elif k == 3:
-                r = x // nonzero(y) if "bool" not in (x.dtype, y.dtype) else x + y
+            elif k == 3:     # (integers only: floor division of FLOATS one ulp from an integer is where two correct
+                both_int = all(d.dtype.startswith(("int", "uint")) for d in (x, y))   # implementations may disagree)
+                r = x // nonzero(y) if both_int else x + y
             elif k == 4:
-                r = x % nonzero(y) if "bool" not in (x.dtype, y.dtype) else x * y
+                both_int = all(d.dtype.startswith(("int", "uint")) for d in (x, y))
+                r = x % nonzero(y) if both_int else x * y
             elif k == 5:
                 r = pt.switch(x > y, x, y)
             elif k == 6:
