@@ -140,6 +140,10 @@ def _truediv(a, it, ot):
 def _intdiv(a, it, ot):
     x, y = a
     if is_float(ot):
+        if not any(is_float(t) for t in it):
+            # two INTEGER operands whose common type is a float (int64 with uint64): the quotient is C's integer division,
+            # like in the reference's `floor(x / y)`; the explicit double keeps floor() unambiguous for the device compiler
+            return f"floor((double)(({x}) / ({y})))"
         return f"floor(({x}) / ({y}))"
     if ot == "bool" or is_uint(ot):
         return f"(({y}) == 0 ? 0 : ({x}) / ({y}))"

@@ -397,3 +397,12 @@ def test_host_integer_evaluator_leaves_c_conversion_corner_cases_to_the_device()
     np.testing.assert_array_equal(r[0], np.array([-6, 10], dtype="int64"))
     r = host_eval_program(prog("Maximum", ["int64", "int64"], "int64"), [np.int64(7), np.int64(9)])
     assert int(r[0]) == 9
+
+
+def test_floor_division_of_two_integers_with_a_float_result_compiles_for_the_device():
+    """uint64 // int32 has the common type float64: the generated `floor(x / y)` got an INTEGER argument, which the device
+    compiler rejects as ambiguous (the host compiler does not) — found by tracing random mixed-dtype graphs; the quotient
+    is now converted explicitly."""
+    p, q = pt.tensor("p", dtype="uint64", shape=(None,)), pt.tensor("q", dtype="int32", shape=(None,))
+    f = pytensor.function([p, q], p // pt.switch(pt.eq(q, 0), 1, q), mode="CUDA")
+    assert trace_function(f, [np.arange(1, 70, dtype="uint64"), np.arange(-34, 35, dtype="int32")]) >= 1   # NVRTC compiles it
