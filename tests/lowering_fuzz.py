@@ -245,7 +245,7 @@ def check_seed(seed):
         exp = pytensor.function(ins, outs, mode="CVM", on_unused_input="ignore")(*[np.array(x, copy=True) for x in vals])
     except Exception:  # noqa: BLE001
         return "skipped"
-    f = pytensor.function(ins, outs, mode="CUDA", on_unused_input="ignore")
+    f = pytensor.function(ins, outs, mode=os.environ.get("FUZZ_MODE", "CUDA"), on_unused_input="ignore")   # or CUDA_BF16
     prog = f.vm.executor.program
     bad = read_before_write(prog.steps, set(prog.inputs) | set(prog.constants))
     assert bad is None, f"seed {seed}: step {bad} reads a slot nobody wrote: {[type(s.impl).__name__ for s in prog.steps]}"
