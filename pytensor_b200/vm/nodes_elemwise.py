@@ -371,7 +371,28 @@ class CAReduceNode(Node):
         src = dev.to_device(np.asarray(self.identity, dtype=self.out_dtype).reshape(()))
         dev.copy_strided(out, src.as_strided(tuple(out.shape), (0,) * out.dim()))
 
+    HOST_MAX = 64
+    _HOST_RED = {"add": np.add, "mul": np.multiply, "maximum": np.maximum, "minimum": np.minimum, "and": np.bitwise_and,
+                 "or": np.bitwise_or, "xor": np.bitwise_xor}
+
+    def _run_host(self, x):
+        """Integer / bool reduction of a small HOST value (shape plumbing: `All(MakeVector(eq(shape_i, shape_j), ...))` in
+        front of the reference's "could not broadcast" Assert): NumPy in the declared accumulator / output types, so that
+        the check never leaves the host — no upload, no device round trip for the Assert, and the program stays
+        capturable into a CUDA graph."""
+        x = np.asarray(x)
+        kept = [i for i in range(self.ndim) if i not in self.axes]
+        if not self.axes:
+            return x.astype(self.out_dtype)
+        if x.size == 0 or any(x.shape[a] == 0 for a in self.axes):
+            return np.full([x.shape[i] for i in kept], self.identity, dtype=self.out_dtype)
+        return np.asarray(self._HOST_RED[self.red_op].reduce(x.astype(self.acc_dtype), axis=self.axes)).astype(self.out_dtype)
+
     def run(self, vals):
+        v = vals[0]
+        if (v.d is None and v.h is not None and np.size(v.h) <= self.HOST_MAX and self.red_op in self._HOST_RED
+                and not any(is_float(d) for d in (self.in_dtype, self.acc_dtype, self.out_dtype))):
+            return [Val(h=self._run_host(v.h))]
         t = vals[0].dev()
         shape = tuple(t.shape)
         kept = [i for i in range(self.ndim) if i not in self.axes]

@@ -406,3 +406,30 @@ def test_floor_division_of_two_integers_with_a_float_result_compiles_for_the_dev
     p, q = pt.tensor("p", dtype="uint64", shape=(None,)), pt.tensor("q", dtype="int32", shape=(None,))
     f = pytensor.function([p, q], p // pt.switch(pt.eq(q, 0), 1, q), mode="CUDA")
     assert trace_function(f, [np.arange(1, 70, dtype="uint64"), np.arange(-34, 35, dtype="int32")]) >= 1   # NVRTC compiles it
+
+
+def test_broadcast_shape_checks_stay_on_the_host():
+    """With statically unknown shapes the reference guards a broadcast by Assert(All(MakeVector(eq(shape_i, shape_j), ...))).
+    The tiny bool reduction used to be uploaded and reduced on the device, so the Assert needed a device round trip (and such
+    a program could not be captured into a CUDA graph); integer / bool reductions of small host values now run on the host.
+    In trace-only mode (no device values) the whole check therefore works — found by tracing random graphs."""
+    from pytensor_b200.vm.nodes_elemwise import CAReduceNode
+
+    pytensor.config.floatX = "float64"
+    x, y, z = pt.dmatrix("x"), pt.lmatrix("y"), pt.lmatrix("z")
+    from pytensor.raise_op import Assert
+
+    same = pt.all(pt.stack([pt.eq(y.shape[0], z.shape[0]), pt.eq(y.shape[1], z.shape[1])]))   # the reference's own idiom
+    out = Assert("shapes differ")(x.max(axis=1, keepdims=True), same) * pt.ones_like(y + z)
+    f = pytensor.function([x, y, z], out, mode="CUDA")
+    steps = f.vm.executor.program.steps
+    assert any(type(s.impl).__name__ == "AssertNode" for s in steps) and any(
+        type(s.impl) is CAReduceNode and s.impl.red_op == "and" for s in steps), [type(s.impl).__name__ for s in steps]
+    assert trace_function(f, [np.zeros((70, 33)), np.ones((70, 33), dtype="int64"), np.ones((70, 33), dtype="int64")]) >= 1
+    # the host reduction follows the declared accumulator / output types
+    n = CAReduceNode("add", (0,), 2, "int8", "int64", "int64", 0)
+    v = np.array([[100, -3], [100, 7], [100, 1]], dtype="int8")
+    np.testing.assert_array_equal(n._run_host(v), np.array([300, 5], dtype="int64"))
+    n = CAReduceNode("and", None, 1, "bool", "bool", "bool", 1)
+    assert n._run_host(np.array([True, True])) == np.bool_(True) and n._run_host(np.array([True, False])) == np.bool_(False)
+    assert n._run_host(np.zeros((0,), dtype=bool)) == np.bool_(True)      # empty: the identity
