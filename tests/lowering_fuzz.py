@@ -23,7 +23,7 @@ from pytensor_b200.link.cuda.fusion import read_before_write  # noqa: E402
 
 
 def build(rng, dtype):
-    lo, hi = (2, 9) if os.environ.get("FUZZ_BIG") != "1" else (60, 90)
+    lo, hi = {"1": (60, 90), "2": (256, 330)}.get(os.environ.get("FUZZ_BIG"), (2, 9))   # 2: tensor-core sized products
     M, N, K = (int(rng.integers(lo, hi)) for _ in range(3))
     a, b, w = pt.matrix("a", dtype=dtype), pt.matrix("b", dtype=dtype), pt.matrix("w", dtype=dtype)
     ws = pt.matrix("ws", dtype=dtype)       # (N, N)
