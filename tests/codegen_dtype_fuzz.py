@@ -43,7 +43,7 @@ def build(rng):
         return pool[int(rng.integers(len(pool)))]
 
     for _ in range(int(rng.integers(1, 6))):
-        k = int(rng.integers(0, 11))
+        k = int(rng.integers(0, 14))
         x, y = pick(), pick()
         try:
             if k == 0:
@@ -66,8 +66,18 @@ def build(rng):
                 r = pt.clip(x, -2, 3) if x.dtype != "bool" else x
             elif k == 9:
                 r = x / pt.switch(pt.eq(y, 0), pt.ones_like(y), y)
+            elif k == 10:
+                to = DTYPES[int(rng.integers(len(DTYPES)))]
+                if x.dtype.startswith("float") and to.startswith("uint"):
+                    to = to[1:]      # (a negative float converted to an UNSIGNED integer is undefined behaviour in C)
+                r = pt.cast(x, to)
+            elif k == 11:      # float functions of integer operands (the result type is upgraded to a float)
+                fn = [pt.exp, pt.tanh, pt.sigmoid, pt.sqrt, pt.log1p, pt.sin, pt.arctan, pt.erf][int(rng.integers(8))]
+                r = fn(pt.abs(x) if fn in (pt.sqrt, pt.log1p) else x) if x.dtype != "bool" else fn(x)
+            elif k == 12:
+                r = pt.sqr(x) + pt.sgn(y) if "bool" not in (x.dtype, y.dtype) else x ^ y if x.dtype == y.dtype == "bool" else x + y
             else:
-                r = pt.cast(x, DTYPES[int(rng.integers(len(DTYPES)))])
+                r = pt.round(x / 3) if x.dtype.startswith("float") else pt.floor(x / 3)
             pool.append(r)
         except Exception:  # noqa: BLE001
             pass
