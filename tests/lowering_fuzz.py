@@ -235,13 +235,71 @@ def build_dtypes(rng):
     return ins, outs, vals
 
 
+def build_scans(rng, dtype):
+    """Third family: Scans — elementwise recurrences (persistent fused kernel), taps, two states, nit-sot outputs, `until`,
+    sequence maps, the matmul recurrence and mixed inner graphs (general loop), with strided / last-k reads of the trace and
+    optional gradients through the loop."""
+    from pytensor.scan.utils import until
+
+    M, N = int(rng.integers(2, 6)), int(rng.integers(2, 7))
+    T = int(rng.integers(1, 7))
+    c = lambda v: np.asarray(v, dtype=dtype)
+    x = pt.matrix("x", dtype=dtype); y = pt.matrix("y", dtype=dtype); a = pt.vector("a", dtype=dtype)
+    W = pt.matrix("W", dtype=dtype); seq = pt.tensor3("seq", dtype=dtype)
+    vals = [rng.standard_normal((M, N)).astype(dtype), rng.standard_normal((M, N)).astype(dtype),
+            rng.uniform(0.5, 1.2, N).astype(dtype), (rng.standard_normal((N, N)) / np.sqrt(N)).astype(dtype),
+            rng.standard_normal((T + 2, M, N)).astype(dtype)]
+    form = int(rng.integers(0, 8))
+    use_seq = rng.random() < 0.4
+    def ew(h, extra=None):
+        k = int(rng.integers(0, 5))
+        e = h * a + c(0.1) if k == 0 else pt.tanh(h * c(0.9)) + c(0.05) if k == 1 else pt.maximum(h, -h) * c(0.5) + a * c(0.1) \
+            if k == 2 else pt.switch(h > 0, h * c(0.5), pt.expm1(h)) if k == 3 else pt.sigmoid(h) - c(0.5) + h * c(0.3)
+        return e + extra if extra is not None else e
+    seqs = [seq[:T]] if use_seq else []
+    if form == 0:      # one state, elementwise
+        fn = (lambda s_t, h: ew(h, s_t)) if use_seq else (lambda h: ew(h))
+        outs_info = [x]; nseq = []
+    elif form == 1:    # two taps
+        fn = (lambda s_t, h1, h2: ew(h1, s_t) * c(0.5) + h2 * c(0.25)) if use_seq else (lambda h1, h2: ew(h1) * c(0.5) + h2 * c(0.25))
+        outs_info = [dict(initial=pt.stack([x, y]), taps=[-1, -2])]; nseq = []
+    elif form == 2:    # two states
+        fn = (lambda s_t, h, g: [ew(h, s_t) - g * c(0.1), ew(g) + h * c(0.2)]) if use_seq else (lambda h, g: [ew(h) - g * c(0.1), ew(g) + h * c(0.2)])
+        outs_info = [x, y]; nseq = []
+    elif form == 3:    # state + nit-sot output
+        fn = (lambda s_t, h: [ew(h, s_t), (h * h).sum(axis=1)]) if use_seq else (lambda h: [ew(h), (h * h).sum(axis=1)])
+        outs_info = [x, None]; nseq = []
+    elif form == 4:    # matmul recurrence
+        fn = (lambda h, W_, a_: pt.tanh(pt.dot(h, W_) + a_)); outs_info = [x]; nseq = [W, a]; seqs = []
+    elif form == 5:    # matmul + elementwise mix (general loop)
+        fn = (lambda h, W_: pt.dot(pt.tanh(h), W_) * c(0.5) + h * c(0.1)); outs_info = [x]; nseq = [W]; seqs = []
+    elif form == 6:    # until
+        fn = (lambda h: (ew(h), until(pt.sum(h * h) > c(5.0 * M * N)))); outs_info = [x]; nseq = []; seqs = []
+    else:              # only a sequence map (no recurrence)
+        fn = (lambda s_t: pt.tanh(s_t) * a); outs_info = [None]; nseq = []; seqs = [seq[:T]]
+    res = pytensor.scan(fn, sequences=seqs, outputs_info=outs_info, non_sequences=nseq, n_steps=None if seqs else T, return_updates=False)
+    res = res if isinstance(res, list | tuple) else [res]
+    outs = []
+    for r in res:
+        k = int(rng.integers(0, 4))
+        outs.append(r[-1] if k == 0 else r if k == 1 else r[::2] if k == 2 else r[-2:].sum(axis=0))
+    if rng.random() < 0.3:
+        cost = sum(o.sum() for o in outs)
+        try:
+            outs = [cost] + list(pytensor.grad(cost, [x, a], disconnected_inputs="ignore"))
+        except Exception:
+            pass
+    return [x, y, a, W, seq], outs, vals
+
+
+
 def check_seed(seed):
     """"ok" | "skipped" (the random graph is ill-shaped for the reference itself); raises on a lowering mismatch."""
     rng = np.random.default_rng(seed)
     dtype = "float32" if seed % 2 else "float64"
     pytensor.config.floatX = dtype
     try:
-        ins, outs, vals = build_dtypes(rng) if seed % 5 == 4 else build(rng, dtype)
+        ins, outs, vals = build_dtypes(rng) if seed % 5 == 4 else build_scans(rng, dtype) if seed % 5 == 3 else build(rng, dtype)
         exp = pytensor.function(ins, outs, mode="CVM", on_unused_input="ignore")(*[np.array(x, copy=True) for x in vals])
     except Exception:  # noqa: BLE001
         return "skipped"
