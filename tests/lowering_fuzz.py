@@ -293,13 +293,64 @@ def build_scans(rng, dtype):
 
 
 
+def build_nd(rng, dtype):
+    """Fourth family: 3-d tensors with row / column broadcast patterns (axes of length 1 included) — multi-axis reductions,
+    dimshuffles, reshapes, negative-step slices, gathers / sets / increments along inner axes, tiling, flatten, CumOp and
+    Argmax over inner axes, joins along every axis."""
+    A, B, C = (int(rng.integers(1, 5)) for _ in range(3))
+    c = lambda v: np.asarray(v, dtype=dtype)
+    t3 = pt.tensor3("t3", dtype=dtype); row = pt.row("row", dtype=dtype); col = pt.col("col", dtype=dtype)
+    m = pt.matrix("m", dtype=dtype); idx = pt.lvector("idx")
+    vals = [rng.standard_normal((A, B, C)).astype(dtype), rng.standard_normal((1, C)).astype(dtype),
+            rng.standard_normal((B, 1)).astype(dtype), rng.standard_normal((B, C)).astype(dtype),
+            rng.integers(-C, C, size=int(rng.integers(1, 5))).astype("int64")]
+    pool = [t3, m, t3 * c(0.5) + row, m + col]
+    def pick(nd=None):
+        cand = [p for p in pool if nd is None or p.ndim == nd]
+        return cand[int(rng.integers(len(cand)))]
+    for _ in range(int(rng.integers(3, 9))):
+        k = int(rng.integers(0, 22))
+        try:
+            if k == 0: r = pick(3) + row
+            elif k == 1: r = pick(3) * col
+            elif k == 2: r = pick(3).sum(axis=(0, 2))
+            elif k == 3: r = pick(3).max(axis=1)
+            elif k == 4: r = pick(3).dimshuffle(2, 0, 1)
+            elif k == 5: r = pick(3).reshape((-1, C))
+            elif k == 6: r = pick(3)[:, ::-1, 1:]
+            elif k == 7: r = pick(3)[:, :, idx]
+            elif k == 8: r = pick(3)[0] + m
+            elif k == 9: x = pick(3); r = pt.set_subtensor(x[:, 0, :], c(0.5))
+            elif k == 10: x = pick(3); r = pt.inc_subtensor(x[:, :, idx], x[:, :, idx])
+            elif k == 11: r = pt.where(pick(3) > 0, pick(3), c(-1.0))
+            elif k == 12: r = pt.tile(pick(2), (2, 1))
+            elif k == 13: r = pick(3).flatten(2)
+            elif k == 14: r = pt.swapaxes(pick(3), 0, 2)
+            elif k == 15: r = pt.cumsum(pick(3), axis=1)
+            elif k == 16: r = pt.cast(pt.argmax(pick(3), axis=2), dtype)
+            elif k == 17: r = pick(3).mean(axis=0)
+            elif k == 18: r = pt.concatenate([pick(3), pick(3)], axis=int(rng.integers(0, 3)))
+            elif k == 19: r = pt.tanh(pick(3)).prod(axis=2)
+            elif k == 20: x = pick(2); r = pt.tril(pt.dot(x.T, x)) if False else pt.dot(x.T, x) * pt.eye(x.shape[1], dtype=dtype)
+            else: r = pt.squeeze(pick(3)[:, :1, :], axis=1) if False else pick(3)[:, 0, :]
+            pool.append(r)
+        except Exception:
+            pass
+    outs = []
+    for _ in range(int(rng.integers(1, 4))):
+        o = pick()
+        outs.append(o if rng.random() < 0.6 else o.sum())
+    return [t3, row, col, m, idx], outs, vals
+
+
+
 def check_seed(seed):
     """"ok" | "skipped" (the random graph is ill-shaped for the reference itself); raises on a lowering mismatch."""
     rng = np.random.default_rng(seed)
     dtype = "float32" if seed % 2 else "float64"
     pytensor.config.floatX = dtype
     try:
-        ins, outs, vals = build_dtypes(rng) if seed % 5 == 4 else build_scans(rng, dtype) if seed % 5 == 3 else build(rng, dtype)
+        ins, outs, vals = build_dtypes(rng) if seed % 5 == 4 else build_scans(rng, dtype) if seed % 5 == 3 else build_nd(rng, dtype) if seed % 5 == 2 else build(rng, dtype)
         exp = pytensor.function(ins, outs, mode="CVM", on_unused_input="ignore")(*[np.array(x, copy=True) for x in vals])
     except Exception:  # noqa: BLE001
         return "skipped"
